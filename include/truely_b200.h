@@ -1,0 +1,154 @@
+/*
+ * truely_b200.h — C ABI of libtruely_b200.so: the B200 (sm_100a) implementation of the
+ * Truely visual-analysis hot path, i.e. everything reference server/model.py::run does per
+ * processed frame between cv2.VideoCapture.read (server/model.py:43) and the run-length
+ * counter (server/model.py:62).
+ *
+ * The reference has no FFI of its own (it is pure Python over facenet_pytorch / torchvision /
+ * OpenCV, all on CPU); each entry point below therefore cites the Python call it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - return 0 (TRL_OK) on success, a negative TRL_E_* code otherwise; no exceptions cross the ABI;
+ *     trl_last_error() gives the message of the last failure on that context.
+ *   - every pointer named d_* is DEVICE memory owned by the caller; h_* is host memory.
+ *   - every call is asynchronous on the CUDA stream passed as `stream` (a cudaStream_t cast to
+ *     void*; NULL = legacy default stream).  The library never calls cudaDeviceSynchronize.
+ *     Workspace is (re)allocated with cudaMalloc only when a call needs more than the context holds.
+ *   - one context per (process, device); a context is not thread safe.
+ *   - frames are BGR uint8, layout [B, H, W, 3] (what cv2.VideoCapture.read returns).
+ *   - there is no CPU fallback: without a CUDA device trl_create fails with TRL_E_CUDA.
+ */
+#ifndef TRUELY_B200_H
+#define TRUELY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRL_OK 0
+#define TRL_E_INVALID (-1)   /* bad argument */
+#define TRL_E_CUDA (-2)      /* CUDA runtime / driver error */
+#define TRL_E_CAPACITY (-3)  /* a candidate buffer overflowed (reported, never silently truncated) */
+#define TRL_E_NOMEM (-4)
+#define TRL_E_STATE (-5)     /* call order / missing weights */
+
+#define TRL_EMB_DIM 512
+#define TRL_MAX_SCALES 24
+
+typedef struct trl_ctx trl_ctx_t;
+
+/* Flat float32 weight blobs (host memory, copied during trl_create).
+ *   pnet / rnet / onet: tensors of the upstream state dict concatenated in the order of
+ *     SURVEY.md Appendix C (conv1.weight, conv1.bias, prelu1.weight, conv2.weight, ...), PyTorch layouts.
+ *   facenet: InceptionResnetV1 with BatchNorm folded (fp32): for every BasicConv2d in execution order
+ *     W[cout][kh][kw][cin] then bias[cout]; then for every residual up-projection W[cout][cin], bias[cout];
+ *     then last_linear folded with last_bn: W[512][1792], bias[512].  (weights.py::pack_facenet) */
+typedef struct {
+  const float* h_pnet;    size_t pnet_len;     /* 6,632 floats   */
+  const float* h_rnet;    size_t rnet_len;     /* 100,178 floats */
+  const float* h_onet;    size_t onet_len;     /* 389,040 floats (dense6_3 landmarks head is accepted and unused) */
+  const float* h_facenet; size_t facenet_len;  /* trl_facenet_blob_len() floats */
+} trl_weights_t;
+
+/* Replaces the constructor arguments of MTCNN() (server/model.py:18, upstream defaults) and the
+ * literals of server/model.py:16,41. */
+typedef struct {
+  int min_face_size;      /* 20 */
+  float thresholds[3];    /* 0.6, 0.7, 0.7 */
+  double factor;          /* 0.709 */
+  int crop_size;          /* 80: side of the FaceNet input (server/model.py:41) */
+  int cand_cap_scale;     /* capacity: P-Net candidates per (frame, scale) */
+  int cand_cap_frame;     /* capacity: R-Net inputs per frame (candidates surviving stage-1 NMS) */
+  int box_cap_frame;      /* capacity: O-Net inputs / final boxes per frame */
+  int facenet_impl;       /* 0 = tcgen05 implicit-GEMM path (product); 1 = SIMT direct-conv kernels (validation) */
+} trl_config_t;
+
+void trl_default_config(trl_config_t* cfg);
+size_t trl_facenet_blob_len(void);
+
+/* Replaces MTCNN() + InceptionResnetV1(pretrained="vggface2").eval()   (server/model.py:18-19). */
+int trl_create(int device, const trl_weights_t* w, const trl_config_t* cfg, trl_ctx_t** out);
+void trl_destroy(trl_ctx_t* ctx);
+const char* trl_last_error(const trl_ctx_t* ctx);
+
+/* Pyramid geometry of detect_face (upstream detect_face.py: scale loop).
+ * Fills up to TRL_MAX_SCALES entries; returns the number of scales (>= 0) or a TRL_E_* code. */
+int trl_pyramid_geometry(const trl_ctx_t* ctx, int H, int W, double* scales, int* hs, int* ws, int* oh, int* ow);
+
+/* ---- stage entry points (each is one stage of detect_face / run, exposed for stage-isolated parity) ---- */
+
+/* K1: imresample(mode="area") + (x-127.5)*0.0078125 for every scale.
+ * d_out: concatenation over scales of float32 [B,3,hs,ws]. */
+int trl_pyramid(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, float* d_out, void* stream);
+
+/* K2: PNet.forward on one pyramid level.  d_in float32 [B,3,hs,ws] -> d_prob [B,oh,ow] (softmax class 1),
+ * d_reg [B,4,oh,ow]. */
+int trl_pnet(trl_ctx_t* ctx, const float* d_in, int B, int hs, int ws, float* d_prob, float* d_reg, void* stream);
+
+/* K4/K5: greedy NMS of one group.  mode 0 = torchvision.ops.nms (area (x2-x1)(y2-y1), suppress IoU > thr,
+ * ties by index ascending); mode 1 = upstream nms_numpy(..., 'Min') (+1 areas, keep o <= thr, ties by index
+ * descending).  d_keep receives indices in pick order, *d_nkeep their count. */
+int trl_nms(trl_ctx_t* ctx, const float* d_boxes, const float* d_scores, int n, float thr, int mode,
+            int* d_keep, int* d_nkeep, void* stream);
+
+/* K7: crop (1-based inclusive y..ey, x..ex as returned by upstream pad()) -> area resample to size x size
+ * -> normalise.  d_pad int32 [N,4] = (y, ey, x, ex); d_img int32 [N]; d_out float32 [N,3,size,size]. */
+int trl_crop_resample(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, const int* d_pad,
+                      const int* d_img, int n, int size, float* d_out, void* stream);
+
+/* K8 / K9: RNet.forward / ONet.forward.  d_in float32 [N,3,24,24] / [N,3,48,48] -> d_prob [N], d_reg [N,4]. */
+int trl_rnet(trl_ctx_t* ctx, const float* d_in, int n, float* d_prob, float* d_reg, void* stream);
+int trl_onet(trl_ctx_t* ctx, const float* d_in, int n, float* d_prob, float* d_reg, void* stream);
+
+/* MTCNN.detect for a batch of frames (server/model.py:47): the whole cascade K1..K9 on device.
+ * d_nfaces int32 [B]; d_boxes float32 [B, box_cap_frame, 5] (x1,y1,x2,y2,score), per frame sorted
+ * largest-area first (select_largest=True); d_counts (optional, may be NULL) int32 [B,4] =
+ * (#P-Net candidates, #R-Net inputs, #O-Net inputs, #final boxes).
+ * Capacity overflow is recorded on device; trl_check_capacity() reports it after a stream sync. */
+int trl_detect(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, int* d_nfaces, float* d_boxes,
+               int* d_counts, void* stream);
+
+/* K10: box truncation + clamp (server/model.py:49-53), crop, cv2.resize(.., (S,S)) INTER_LINEAR uint8
+ * (server/model.py:55-57), bit exact.  d_boxes float32 [B, box_stride] (first 4 floats of each row used),
+ * d_nfaces int32 [B].  d_box_int int32 [B,4]; d_valid uint8 [B] (1 = a face was cropped);
+ * d_crops uint8 [B,S,S,3]. */
+int trl_crop_align(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes,
+                   int box_stride, const int* d_nfaces, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops,
+                   void* stream);
+
+/* K11: F.to_tensor (/255) + InceptionResnetV1.forward (server/model.py:58-59).
+ * d_crops uint8 [N,S,S,3] BGR -> d_emb float32 [N,512], unit norm. */
+int trl_facenet(trl_ctx_t* ctx, const uint8_t* d_crops, int n, int S, float* d_emb, void* stream);
+
+/* K12: cosine similarity against the previous face-bearing frame and the 0.99 test (server/model.py:60-62).
+ * d_emb [B,512], d_valid [B]; d_halo_emb [512] (or NULL) is the last face-bearing embedding before this
+ * range (previous batch or previous rank), d_halo_valid uint8[1] (or NULL = valid) says on the device whether
+ * it holds one, so consecutive batches chain without a host sync.  Outputs: d_sim float32 [B] (NaN where no comparison),
+ * d_below uint8 [B] (1 = sim < thr), d_has_sim uint8 [B];  d_last_emb [512] + d_last_valid uint8[1]
+ * (either may be NULL): the halo to hand to the next range. */
+int trl_consistency(trl_ctx_t* ctx, const float* d_emb, const uint8_t* d_valid, int B, const float* d_halo_emb,
+                    const uint8_t* d_halo_valid, float thr, float* d_sim, uint8_t* d_below, uint8_t* d_has_sim, float* d_last_emb,
+                    uint8_t* d_last_valid, void* stream);
+
+/* The fused per-batch hot path: detect -> crop-align -> facenet (valid frames only) -> consistency.
+ * Equivalent to the body of the reference loop (server/model.py:47-65) for B processed frames. */
+int trl_process(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, const float* d_halo_emb,
+                const uint8_t* d_halo_valid, float thr,
+                int* d_box_int, uint8_t* d_valid, float* d_emb, float* d_sim, uint8_t* d_below, uint8_t* d_has_sim,
+                int* d_nfaces, float* d_last_emb, uint8_t* d_last_valid, void* stream);
+
+/* After the stream has been synchronised by the caller: TRL_E_CAPACITY if any candidate buffer overflowed
+ * since the last check (h_detail, optional int32[4]: which stage, frame, count, capacity). */
+int trl_check_capacity(trl_ctx_t* ctx, int* h_detail);
+
+/* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */
+long long trl_launch_count(const trl_ctx_t* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRUELY_B200_H */

@@ -1,0 +1,288 @@
+// C ABI of libtruely_b200.so (include/truely_b200.h): context, workspace and the device-side MTCNN cascade driver.
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local std::string g_create_err;
+
+extern "C" {
+
+void trl_default_config(trl_config_t* cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->min_face_size = 20;
+  cfg->thresholds[0] = 0.6f; cfg->thresholds[1] = 0.7f; cfg->thresholds[2] = 0.7f;
+  cfg->factor = 0.709;
+  cfg->crop_size = 80;
+  cfg->cand_cap_scale = 2048;
+  cfg->cand_cap_frame = 1024;
+  cfg->box_cap_frame = 128;
+  cfg->facenet_impl = 0;
+}
+
+const char* trl_last_error(const trl_ctx_t* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+long long trl_launch_count(const trl_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+static void free_workspace(trl_ctx* c) {
+  void* ptrs[] = {c->d_pyr, c->d_cand1, c->d_cnt1, c->d_cand2, c->d_cnt2, c->d_cand3, c->d_cnt3, c->d_pad3, c->d_rin,
+                  c->d_cand4, c->d_cnt4, c->d_pad4, c->d_oin, c->d_rprob, c->d_rreg, c->d_oprob, c->d_oreg,
+                  c->d_boxes, c->d_nfaces, c->d_crops};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  c->d_pyr = nullptr; c->d_cand1 = nullptr; c->d_cnt1 = nullptr; c->d_cand2 = nullptr; c->d_cnt2 = nullptr;
+  c->d_cand3 = nullptr; c->d_cnt3 = nullptr; c->d_pad3 = nullptr; c->d_rin = nullptr; c->d_cand4 = nullptr;
+  c->d_cnt4 = nullptr; c->d_pad4 = nullptr; c->d_oin = nullptr; c->d_rprob = nullptr; c->d_rreg = nullptr;
+  c->d_oprob = nullptr; c->d_oreg = nullptr; c->d_boxes = nullptr; c->d_nfaces = nullptr; c->d_crops = nullptr;
+  c->ws_B = c->ws_H = c->ws_W = 0;
+}
+
+void trl_destroy(trl_ctx_t* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  free_workspace(c);
+  facenet_destroy(c);
+  if (c->d_pnet_packed) cudaFree(c->d_pnet_packed);
+  if (c->d_rnet) cudaFree(c->d_rnet);
+  if (c->d_onet) cudaFree(c->d_onet);
+  if (c->d_nms_tmp) cudaFree(c->d_nms_tmp);
+  if (c->h_cap) cudaFreeHost(c->h_cap);
+  delete c;
+}
+
+int trl_create(int device, const trl_weights_t* w, const trl_config_t* cfg, trl_ctx_t** out) {
+  if (!out || !w) { g_create_err = "trl_create: null argument"; return TRL_E_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("trl_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+    return TRL_E_CUDA;
+  }
+  if (device < 0 || device >= ndev) { g_create_err = "trl_create: bad device index"; return TRL_E_INVALID; }
+  trl_ctx* c = new trl_ctx();
+  c->device = device;
+  if (cfg) c->cfg = *cfg; else trl_default_config(&c->cfg);
+  auto fail = [&](int rc) { g_create_err = c->err; trl_destroy(c); return rc; };
+  if (c->cfg.cand_cap_scale > nms_max_n() || c->cfg.cand_cap_frame > nms_max_n() || c->cfg.box_cap_frame > nms_max_n() ||
+      c->cfg.cand_cap_scale < 1 || c->cfg.cand_cap_frame < 1 || c->cfg.box_cap_frame < 1) {
+    c->err = "trl_create: candidate capacities must be in [1, 2048]";
+    return fail(TRL_E_INVALID);
+  }
+  if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(TRL_E_CUDA); }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { c->err = "cudaGetDeviceProperties failed"; return fail(TRL_E_CUDA); }
+  if (prop.major != 10) {
+    c->err = "trl_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ", this library is built for sm_100a only";
+    return fail(TRL_E_CUDA);
+  }
+  if (cudaHostAlloc(&c->h_cap, sizeof(CapFlag), cudaHostAllocMapped) != cudaSuccess) { c->err = "cudaHostAlloc failed"; return fail(TRL_E_NOMEM); }
+  memset(c->h_cap, 0, sizeof(CapFlag));
+  if (cudaHostGetDevicePointer(&c->d_cap, c->h_cap, 0) != cudaSuccess) { c->err = "cudaHostGetDevicePointer failed"; return fail(TRL_E_CUDA); }
+  int rc;
+  if ((rc = nms_init(c)) != TRL_OK) return fail(rc);
+  if (w->h_pnet && (rc = pnet_pack_weights(c, w->h_pnet, w->pnet_len)) != TRL_OK) return fail(rc);
+  if (w->h_rnet && w->h_onet && (rc = ro_pack_weights(c, w->h_rnet, w->rnet_len, w->h_onet, w->onet_len)) != TRL_OK) return fail(rc);
+  if (w->h_facenet && (rc = facenet_create(c, w->h_facenet, w->facenet_len)) != TRL_OK) return fail(rc);
+  *out = c;
+  return TRL_OK;
+}
+
+int trl_pyramid_geometry(const trl_ctx_t* ctx, int H, int W, double* scales, int* hs, int* ws, int* oh, int* ow) {
+  if (!ctx) return TRL_E_INVALID;
+  PyramidGeom g;
+  int rc = compute_geometry(ctx->cfg, H, W, &g);
+  if (rc != TRL_OK) return rc;
+  for (int k = 0; k < g.n; ++k) {
+    if (scales) scales[k] = g.scale[k];
+    if (hs) hs[k] = g.hs[k];
+    if (ws) ws[k] = g.ws[k];
+    if (oh) oh[k] = g.oh[k];
+    if (ow) ow[k] = g.ow[k];
+  }
+  return g.n;
+}
+
+int trl_pyramid(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, float* d_out, void* stream) {
+  if (!c || !d_frames || !d_out || B < 0) return TRL_E_INVALID;
+  PyramidGeom g;
+  int rc = compute_geometry(c->cfg, H, W, &g);
+  if (rc != TRL_OK) TRL_FAIL(c, rc, "trl_pyramid: bad geometry %dx%d", H, W);
+  return launch_pyramid(c, d_frames, B, H, W, g, d_out, (cudaStream_t)stream);
+}
+
+int trl_pnet(trl_ctx_t* c, const float* d_in, int B, int hs, int ws, float* d_prob, float* d_reg, void* stream) {
+  if (!c || !d_in || !d_prob || !d_reg) return TRL_E_INVALID;
+  if (!c->d_pnet_packed) TRL_FAIL(c, TRL_E_STATE, "P-Net weights not loaded");
+  return launch_pnet_maps(c, d_in, B, hs, ws, d_prob, d_reg, (cudaStream_t)stream);
+}
+
+int trl_nms(trl_ctx_t* c, const float* d_boxes, const float* d_scores, int n, float thr, int mode, int* d_keep, int* d_nkeep,
+            void* stream) {
+  if (!c || n < 0 || (mode != 0 && mode != 1)) return TRL_E_INVALID;
+  return launch_plain_nms(c, d_boxes, d_scores, n, thr, mode, d_keep, d_nkeep, (cudaStream_t)stream);
+}
+
+int trl_crop_resample(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, const int* d_pad, const int* d_img, int n,
+                      int size, float* d_out, void* stream) {
+  if (!c || !d_frames || !d_pad || !d_img || !d_out || (size != 24 && size != 48)) return TRL_E_INVALID;
+  return launch_crop_resample(c, d_frames, B, H, W, d_pad, d_img, nullptr, n, size, d_out, (cudaStream_t)stream);
+}
+
+int trl_rnet(trl_ctx_t* c, const float* d_in, int n, float* d_prob, float* d_reg, void* stream) {
+  if (!c || !d_in || !d_prob || !d_reg) return TRL_E_INVALID;
+  if (!c->d_rnet) TRL_FAIL(c, TRL_E_STATE, "R-Net weights not loaded");
+  return launch_rnet(c, d_in, n, nullptr, d_prob, d_reg, (cudaStream_t)stream);
+}
+
+int trl_onet(trl_ctx_t* c, const float* d_in, int n, float* d_prob, float* d_reg, void* stream) {
+  if (!c || !d_in || !d_prob || !d_reg) return TRL_E_INVALID;
+  if (!c->d_onet) TRL_FAIL(c, TRL_E_STATE, "O-Net weights not loaded");
+  return launch_onet(c, d_in, n, nullptr, d_prob, d_reg, (cudaStream_t)stream);
+}
+
+// ---- workspace
+
+#define WS_ALLOC(ptr, bytes)                                                       \
+  do {                                                                             \
+    cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                          \
+    if (_e != cudaSuccess) { free_workspace(c); TRL_FAIL(c, TRL_E_NOMEM, "workspace cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(_e)); } \
+  } while (0)
+
+static int ensure_workspace(trl_ctx* c, int B, int H, int W) {
+  if (c->ws_H == H && c->ws_W == W && c->ws_B >= B) return TRL_OK;
+  const int Bc = (c->ws_H == H && c->ws_W == W && c->ws_B > B) ? c->ws_B : B;
+  free_workspace(c);
+  int rc = compute_geometry(c->cfg, H, W, &c->geom);
+  if (rc != TRL_OK) TRL_FAIL(c, rc, "bad frame geometry %dx%d", H, W);
+  const PyramidGeom& g = c->geom;
+  const size_t c1 = c->cfg.cand_cap_scale, c2 = c->cfg.cand_cap_frame, c4 = c->cfg.box_cap_frame;
+  const int S = c->cfg.crop_size;
+  WS_ALLOC(c->d_pyr, (size_t)Bc * g.px_total * 3 * sizeof(float));
+  WS_ALLOC(c->d_cand1, (size_t)Bc * g.n * c1 * sizeof(Cand));
+  WS_ALLOC(c->d_cnt1, (size_t)Bc * (g.n + 3) * sizeof(int));     // cnt1 [B][n] then cnt2 [B], cnt3 [B], cnt4 [B]
+  c->d_cnt2 = nullptr;
+  WS_ALLOC(c->d_cand2, (size_t)Bc * c2 * sizeof(Cand));
+  WS_ALLOC(c->d_cand3, (size_t)Bc * c2 * sizeof(Cand));
+  WS_ALLOC(c->d_pad3, (size_t)Bc * c2 * 4 * sizeof(int));
+  WS_ALLOC(c->d_rin, (size_t)Bc * c2 * 3 * 24 * 24 * sizeof(float));
+  WS_ALLOC(c->d_rprob, (size_t)Bc * c2 * sizeof(float));
+  WS_ALLOC(c->d_rreg, (size_t)Bc * c2 * 4 * sizeof(float));
+  WS_ALLOC(c->d_cand4, (size_t)Bc * c4 * sizeof(Cand));
+  WS_ALLOC(c->d_pad4, (size_t)Bc * c4 * 4 * sizeof(int));
+  WS_ALLOC(c->d_oin, (size_t)Bc * c4 * 3 * 48 * 48 * sizeof(float));
+  WS_ALLOC(c->d_oprob, (size_t)Bc * c4 * sizeof(float));
+  WS_ALLOC(c->d_oreg, (size_t)Bc * c4 * 4 * sizeof(float));
+  WS_ALLOC(c->d_boxes, (size_t)Bc * c4 * 5 * sizeof(float));
+  WS_ALLOC(c->d_nfaces, (size_t)Bc * sizeof(int));
+  WS_ALLOC(c->d_crops, (size_t)Bc * S * S * 3 + 256);
+  c->ws_B = Bc; c->ws_H = H; c->ws_W = W;
+  return TRL_OK;
+}
+
+static int detect_impl(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, int* d_nfaces, float* d_boxes, int* d_counts,
+                       cudaStream_t s) {
+  if (!c->d_pnet_packed || !c->d_rnet || !c->d_onet) TRL_FAIL(c, TRL_E_STATE, "MTCNN weights not loaded");
+  int rc = ensure_workspace(c, B, H, W);
+  if (rc != TRL_OK) return rc;
+  const PyramidGeom& g = c->geom;
+  const int c1 = c->cfg.cand_cap_scale, c2 = c->cfg.cand_cap_frame, c4 = c->cfg.box_cap_frame;
+  // counters are laid out for the *current* B: cnt1 [B][n], cnt2 [B], cnt3 [B], cnt4 [B]
+  int* cnt1 = c->d_cnt1;
+  int* cnt2 = cnt1 + (size_t)B * g.n;
+  int* cnt3 = cnt2 + B;
+  int* cnt4 = cnt3 + B;
+  TRL_CUDA(c, cudaMemsetAsync(cnt1, 0, (size_t)B * (g.n + 3) * sizeof(int), s));
+  if ((rc = launch_pyramid(c, d_frames, B, H, W, g, c->d_pyr, s)) != TRL_OK) return rc;
+  if ((rc = launch_pnet_candidates(c, c->d_pyr, B, g, c->cfg.thresholds[0], c->d_cand1, cnt1, c1, s)) != TRL_OK) return rc;
+
+  nms::StageParams p{};
+  p.W = W; p.H = H; p.capflag = c->d_cap;
+  // stage 1: per (frame, level) NMS 0.5
+  p.n_levels = g.n; p.cap_in = c1; p.cap_out = c2; p.thr_nms = 0.5f; p.thr_score = 0.f;
+  p.in = c->d_cand1; p.cnt_in = cnt1; p.out = c->d_cand2; p.cnt_out = cnt2;
+  if ((rc = launch_cascade_stage(c, 1, p, B, s)) != TRL_OK) return rc;
+  // stage 2: per frame NMS 0.7 + regression + rerec + pad -> R-Net inputs
+  p.cap_in = c2; p.cap_out = c2; p.thr_nms = 0.7f;
+  p.in = c->d_cand2; p.cnt_in = cnt2; p.out = c->d_cand3; p.cnt_out = cnt3; p.pad_out = c->d_pad3;
+  if ((rc = launch_cascade_stage(c, 2, p, B, s)) != TRL_OK) return rc;
+  if ((rc = launch_crop_resample_ex(c, d_frames, B, H, W, c->d_pad3, nullptr, cnt3, c2, B * c2, 24, c->d_rin, s)) != TRL_OK) return rc;
+  if ((rc = launch_rnet_ex(c, c->d_rin, B * c2, cnt3, c2, c->d_rprob, c->d_rreg, s)) != TRL_OK) return rc;
+  // stage 3: R-Net score > thr, NMS 0.7, bbreg, rerec, pad -> O-Net inputs
+  p.cap_in = c2; p.cap_out = c4; p.thr_nms = 0.7f; p.thr_score = c->cfg.thresholds[1];
+  p.in = c->d_cand3; p.cnt_in = cnt3; p.prob = c->d_rprob; p.reg = c->d_rreg; p.pad_in = c->d_pad3;
+  p.out = c->d_cand4; p.cnt_out = cnt4; p.pad_out = c->d_pad4;
+  if ((rc = launch_cascade_stage(c, 3, p, B, s)) != TRL_OK) return rc;
+  if ((rc = launch_crop_resample_ex(c, d_frames, B, H, W, c->d_pad4, nullptr, cnt4, c4, B * c4, 48, c->d_oin, s)) != TRL_OK) return rc;
+  if ((rc = launch_onet_ex(c, c->d_oin, B * c4, cnt4, c4, c->d_oprob, c->d_oreg, s)) != TRL_OK) return rc;
+  // stage 4: O-Net score > thr, bbreg, 'Min' NMS 0.7, largest-first
+  p.cap_in = c4; p.cap_out = c4; p.thr_nms = 0.7f; p.thr_score = c->cfg.thresholds[2];
+  p.in = c->d_cand4; p.cnt_in = cnt4; p.prob = c->d_oprob; p.reg = c->d_oreg; p.pad_in = c->d_pad4;
+  p.out = nullptr; p.cnt_out = d_nfaces; p.pad_out = nullptr; p.boxes_out = d_boxes;
+  if ((rc = launch_cascade_stage(c, 4, p, B, s)) != TRL_OK) return rc;
+  if (d_counts) {
+    // (#P-Net candidates summed over levels is not needed on the hot path; report per-stage list sizes)
+    TRL_CUDA(c, cudaMemcpy2DAsync(d_counts + 1, 4 * sizeof(int), cnt3, sizeof(int), sizeof(int), B, cudaMemcpyDeviceToDevice, s));
+    TRL_CUDA(c, cudaMemcpy2DAsync(d_counts + 2, 4 * sizeof(int), cnt4, sizeof(int), sizeof(int), B, cudaMemcpyDeviceToDevice, s));
+    TRL_CUDA(c, cudaMemcpy2DAsync(d_counts + 3, 4 * sizeof(int), d_nfaces, sizeof(int), sizeof(int), B, cudaMemcpyDeviceToDevice, s));
+    TRL_CUDA(c, cudaMemcpy2DAsync(d_counts + 0, 4 * sizeof(int), cnt2, sizeof(int), sizeof(int), B, cudaMemcpyDeviceToDevice, s));
+  }
+  return TRL_OK;
+}
+
+int trl_detect(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, int* d_nfaces, float* d_boxes, int* d_counts,
+               void* stream) {
+  if (!c || !d_frames || !d_nfaces || !d_boxes || B <= 0) return TRL_E_INVALID;
+  return detect_impl(c, d_frames, B, H, W, d_nfaces, d_boxes, d_counts, (cudaStream_t)stream);
+}
+
+int trl_crop_align(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
+                   const int* d_nfaces, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops, void* stream) {
+  if (!c || !d_frames || !d_boxes || !d_nfaces || !d_box_int || !d_valid || !d_crops) return TRL_E_INVALID;
+  return launch_crop_align(c, d_frames, B, H, W, d_boxes, box_stride, d_nfaces, c->cfg.crop_size, d_box_int, d_valid, d_crops,
+                           (cudaStream_t)stream);
+}
+
+int trl_facenet(trl_ctx_t* c, const uint8_t* d_crops, int n, int S, float* d_emb, void* stream) {
+  if (!c || !d_crops || !d_emb || n < 0) return TRL_E_INVALID;
+  return facenet_forward(c, d_crops, n, S, d_emb, (cudaStream_t)stream);
+}
+
+int trl_consistency(trl_ctx_t* c, const float* d_emb, const uint8_t* d_valid, int B, const float* d_halo_emb,
+                    const uint8_t* d_halo_valid, float thr,
+                    float* d_sim, uint8_t* d_below, uint8_t* d_has_sim, float* d_last_emb, uint8_t* d_last_valid, void* stream) {
+  if (!c || !d_emb || !d_valid || !d_sim || !d_below || !d_has_sim) return TRL_E_INVALID;
+  return launch_consistency(c, d_emb, d_valid, B, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
+                            d_last_valid, (cudaStream_t)stream);
+}
+
+int trl_process(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, const float* d_halo_emb,
+                const uint8_t* d_halo_valid, float thr, int* d_box_int,
+                uint8_t* d_valid, float* d_emb, float* d_sim, uint8_t* d_below, uint8_t* d_has_sim, int* d_nfaces,
+                float* d_last_emb, uint8_t* d_last_valid, void* stream) {
+  if (!c || !d_frames || !d_box_int || !d_valid || !d_emb || !d_sim || !d_below || !d_has_sim || B <= 0) return TRL_E_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = ensure_workspace(c, B, H, W);
+  if (rc != TRL_OK) return rc;
+  int* nf = d_nfaces ? d_nfaces : c->d_nfaces;
+  if ((rc = detect_impl(c, d_frames, B, H, W, nf, c->d_boxes, nullptr, s)) != TRL_OK) return rc;
+  const int S = c->cfg.crop_size;
+  if ((rc = launch_crop_align(c, d_frames, B, H, W, c->d_boxes, c->cfg.box_cap_frame * 5, nf, S, d_box_int, d_valid, c->d_crops, s)) != TRL_OK) return rc;
+  // FaceNet runs on all B crops (faceless frames carry a zero crop; their embeddings are never compared):
+  // this keeps the whole batch free of host synchronisation.
+  if ((rc = facenet_forward(c, c->d_crops, B, S, d_emb, s)) != TRL_OK) return rc;
+  return launch_consistency(c, d_emb, d_valid, B, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
+                            d_last_valid, s);
+}
+
+int trl_check_capacity(trl_ctx_t* c, int* h_detail) {
+  if (!c) return TRL_E_INVALID;
+  if (c->h_cap->overflow) {
+    if (h_detail) { h_detail[0] = c->h_cap->stage; h_detail[1] = c->h_cap->frame; h_detail[2] = c->h_cap->count; h_detail[3] = c->h_cap->capacity; }
+    c->err = "candidate buffer overflow at stage " + std::to_string(c->h_cap->stage) + " (frame " + std::to_string(c->h_cap->frame) +
+             ": " + std::to_string(c->h_cap->count) + " > capacity " + std::to_string(c->h_cap->capacity) + ")";
+    memset(c->h_cap, 0, sizeof(CapFlag));
+    return TRL_E_CAPACITY;
+  }
+  return TRL_OK;
+}
+
+}  // extern "C"

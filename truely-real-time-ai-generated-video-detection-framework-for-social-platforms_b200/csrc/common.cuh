@@ -1,0 +1,181 @@
+// Shared declarations of libtruely_b200 (sm_100a).  See include/truely_b200.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/truely_b200.h"
+
+#define TRL_NUM_SMS 148
+
+// ----------------------------------------------------------------------------- candidates
+// One detection candidate as it travels through the cascade (40 bytes).
+struct __align__(8) Cand {
+  float x1, y1, x2, y2;   // box
+  float score;
+  float r0, r1, r2, r3;   // regression offsets of the producing net
+  uint32_t key;           // tie-break key: position in the upstream list at this stage
+};
+
+// capacity overflow record, written by kernels into pinned mapped host memory
+struct CapFlag {
+  int overflow;   // 0 = ok
+  int stage;      // 1 = pnet per-scale, 2 = stage-1 per-frame, 3 = rnet per-frame, 4 = final per-frame
+  int frame;
+  int count;
+  int capacity;
+};
+
+struct PyramidGeom {
+  int n;
+  double scale[TRL_MAX_SCALES];
+  float scale_f[TRL_MAX_SCALES];
+  int hs[TRL_MAX_SCALES], ws[TRL_MAX_SCALES];   // resampled image size
+  int oh[TRL_MAX_SCALES], ow[TRL_MAX_SCALES];   // P-Net output map size
+  long long off[TRL_MAX_SCALES];                // float offset of level k in the pyramid buffer, per frame count B: off*B
+  long long px_total;                           // sum hs*ws
+};
+
+// kernel-parameter view of the pyramid (passed by value)
+struct PyrParams {
+  int n;
+  int hs[TRL_MAX_SCALES], ws[TRL_MAX_SCALES];
+  int oh[TRL_MAX_SCALES], ow[TRL_MAX_SCALES];
+  float scale[TRL_MAX_SCALES];
+  long long off[TRL_MAX_SCALES];       // float offset (already multiplied by B) of level k
+  int blk_start[TRL_MAX_SCALES + 1];   // prefix of work blocks per level (kernel specific)
+  int grp[TRL_MAX_SCALES];             // lanes cooperating per output pixel (pyramid kernel)
+};
+
+namespace nms {
+// parameters of one cascade NMS stage (nms.cu)
+struct StageParams {
+  int n_levels;          // stage 1
+  int cap_in, cap_out;
+  float thr_nms, thr_score;
+  int W, H;
+  const Cand* in;        // stage1: [B][L][cap_in]; others: [B][cap_in]
+  const int* cnt_in;
+  const float* prob;     // stage 3/4: net outputs [B][cap_in]
+  const float* reg;      //            [B][cap_in][4]
+  const int* pad_in;     // stage 3/4: pad of the inputs (degenerate crops are dropped)
+  Cand* out;             // [B][cap_out]
+  int* cnt_out;          // [B]
+  int* pad_out;          // [B][cap_out][4]
+  float* boxes_out;      // stage 4: [B][cap_out][5]
+  CapFlag* capflag;
+};
+}  // namespace nms
+
+struct FaceNetEngine;   // facenet_plan.cu
+
+struct trl_ctx {
+  int device = 0;
+  trl_config_t cfg{};
+  std::string err;
+  long long launches = 0;
+
+  // weights (device)
+  float* d_pnet_packed = nullptr;   // smem image of P-Net (pnet.cu layout)
+  float* d_rnet = nullptr;          // packed R-Net (mtcnn_ro.cu layout)
+  float* d_onet = nullptr;
+  FaceNetEngine* facenet = nullptr;
+
+  // workspace for trl_detect / trl_process, sized for (ws_B, ws_H, ws_W)
+  int ws_B = 0, ws_H = 0, ws_W = 0;
+  PyramidGeom geom{};
+  float* d_pyr = nullptr;
+  Cand* d_cand1 = nullptr;       // [B][n_scales][cand_cap_scale]   P-Net candidates
+  int* d_cnt1 = nullptr;         // [B][n_scales]
+  Cand* d_cand2 = nullptr;       // [B][cand_cap_frame]             after per-scale NMS
+  int* d_cnt2 = nullptr;         // [B]
+  Cand* d_cand3 = nullptr;       // [B][cand_cap_frame]             R-Net inputs (after cross-scale NMS)
+  int* d_cnt3 = nullptr;         // [B]
+  int* d_pad3 = nullptr;         // [B][cand_cap_frame][4]
+  float* d_rin = nullptr;        // [B*cand_cap_frame][3][24][24]
+  Cand* d_cand4 = nullptr;       // [B][box_cap_frame]              O-Net inputs
+  int* d_cnt4 = nullptr;         // [B]
+  int* d_pad4 = nullptr;
+  float* d_oin = nullptr;        // [B*box_cap_frame][3][48][48]
+  float* d_rprob = nullptr;      // [B][cand_cap_frame]   R-Net outputs
+  float* d_rreg = nullptr;       // [B][cand_cap_frame][4]
+  float* d_oprob = nullptr;      // [B][box_cap_frame]    O-Net outputs
+  float* d_oreg = nullptr;
+  // process scratch
+  float* d_boxes = nullptr;      // [B][box_cap_frame][5]
+  int* d_nfaces = nullptr;
+  uint8_t* d_crops = nullptr;    // [B][S][S][3]
+
+  CapFlag* h_cap = nullptr;      // pinned, mapped
+  CapFlag* d_cap = nullptr;      // device alias of h_cap
+
+  // scratch for the stand-alone trl_nms entry point
+  Cand* d_nms_tmp = nullptr; int nms_tmp_cap = 0;
+};
+
+#define TRL_FAIL(ctx, code, ...)                                   \
+  do {                                                             \
+    char _b[512];                                                  \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);                         \
+    (ctx)->err = _b;                                               \
+    return (code);                                                 \
+  } while (0)
+
+#define TRL_CUDA(ctx, expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) TRL_FAIL(ctx, TRL_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define TRL_LAUNCH_CHECK(ctx)                                                                 \
+  do {                                                                                        \
+    (ctx)->launches++;                                                                        \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) TRL_FAIL(ctx, TRL_E_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ----------------------------------------------------------------------------- stage launchers (internal)
+int compute_geometry(const trl_config_t& cfg, int H, int W, PyramidGeom* g);
+
+int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const PyramidGeom& g, float* d_out,
+                   cudaStream_t s);
+int launch_crop_resample(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const int* d_pad, const int* d_img,
+                         const int* d_count, int n_max, int size, float* d_out, cudaStream_t s);
+int launch_crop_align(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
+                      const int* d_nfaces, int S, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops, cudaStream_t s);
+
+int pnet_pack_weights(trl_ctx* c, const float* h_pnet, size_t len);
+// maps mode: d_prob/d_reg non-null, one level.  candidate mode: all levels, thresholded append.
+int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float* d_prob, float* d_reg, cudaStream_t s);
+int launch_pnet_candidates(trl_ctx* c, const float* d_pyr, int B, const PyramidGeom& g, float thr, Cand* d_cand,
+                           int* d_cnt, int cap, cudaStream_t s);
+
+int ro_pack_weights(trl_ctx* c, const float* h_rnet, size_t rlen, const float* h_onet, size_t olen);
+int launch_rnet(trl_ctx* c, const float* d_in, int n_max, const int* d_count, float* d_prob, float* d_reg, cudaStream_t s);
+int launch_onet(trl_ctx* c, const float* d_in, int n_max, const int* d_count, float* d_prob, float* d_reg, cudaStream_t s);
+
+int facenet_create(trl_ctx* c, const float* h_blob, size_t len);
+void facenet_destroy(trl_ctx* c);
+int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, float* d_emb, cudaStream_t s);
+
+int nms_init(trl_ctx* c);
+int nms_max_n();
+int launch_plain_nms(trl_ctx* c, const float* d_boxes, const float* d_scores, int n, float thr, int mode, int* d_keep,
+                     int* d_nkeep, cudaStream_t s);
+int launch_cascade_stage(trl_ctx* c, int stage, const nms::StageParams& p, int B, cudaStream_t s);
+int launch_crop_resample_ex(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const int* d_pad, const int* d_img,
+                            const int* d_count, int per_frame_cap, int n_slots, int size, float* d_out, cudaStream_t s);
+int launch_rnet_ex(trl_ctx* c, const float* d_in, int n_slots, const int* d_count, int per_frame_cap, float* d_prob,
+                   float* d_reg, cudaStream_t s);
+int launch_onet_ex(trl_ctx* c, const float* d_in, int n_slots, const int* d_count, int per_frame_cap, float* d_prob,
+                   float* d_reg, cudaStream_t s);
+
+int launch_consistency(trl_ctx* c, const float* d_emb, const uint8_t* d_valid, int B, const float* d_halo,
+                       const uint8_t* d_halo_valid, float thr,
+                       float* d_sim, uint8_t* d_below, uint8_t* d_has_sim, float* d_last_emb, uint8_t* d_last_valid,
+                       cudaStream_t s);

@@ -1,0 +1,359 @@
+// K11: InceptionResnetV1 convolutions as bf16 implicit GEMM on the 5th-gen tensor cores (sm_100a).
+//
+//   D[128 x BN] (fp32, TMEM) += A[128 x BK] (smem, K-major, TMA) * W[BN x BK]^T (smem, K-major, TMA)
+//
+// * A is never materialised: for filter tap (ky,kx) and channel block c0 the 128 rows of the tile are one 4-D TMA box
+//   {BK channels, box_w, box_h, box_n} of the NHWC input at (c0, ox0*s+kx-pw, oy0*s+ky-ph, n0); out-of-bounds
+//   elements (the zero padding) are filled by the TMA unit, strided convs use the map's element strides.
+//   1x1 stride-1 convs use a flat (channels x pixels) view, so tiles carry no spatial padding at all.
+// * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) is issued by one thread; accumulators live in TMEM.
+// * warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue (tcgen05.ld -> bias / residual /
+//   ReLU -> bf16 -> channel slice of the destination: concat-free Inception blocks).
+// * smem ring of `stages` {A,B} tiles guarded by full/empty mbarriers; tcgen05.commit releases a stage.
+// Every mbarrier wait is bounded (trap after ~2 s) so a protocol bug surfaces as a CUDA error, never as a hang.
+#include "facenet.cuh"
+
+namespace umma {
+
+constexpr int BLOCK_M = 128;
+constexpr int NUM_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1 for swizzled K-major) | [32,46) SBO>>4 (8 rows * row bytes) | [46,48) version=1
+//   | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) |
+         ((uint64_t)layout << 61);
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_constant__ ConvOp op, int n_img, int tiles_w,
+                                                                int tiles_h, int stages, uint32_t tmem_cols) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BK = op.block_k, BN = op.block_n;
+  const uint32_t a_bytes = BLOCK_M * BK * 2, b_bytes = BN * BK * 2;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + stages * a_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + stages * b_bytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* accum_bar = empty_bar + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x;
+  const int tw = mt % tiles_w, th = (mt / tiles_w) % tiles_h, tn = mt / (tiles_w * tiles_h);
+  const int ox0 = tw * op.box_w, oy0 = th * op.box_h, n0 = tn * op.box_n;
+  const int n_off = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&op.tmap_a);
+    prefetch_tmap(&op.tmap_w);
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int cin_blocks = op.Cin / BK;
+  const int k_iters = op.kh * op.kw * cin_blocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer
+      const uint32_t box_rows = (uint32_t)(op.box_w * op.box_h * op.box_n);
+      const uint32_t tx_bytes = box_rows * BK * 2 + b_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const int tap = it / cin_blocks, cb = it - tap * cin_blocks;
+        const int ky = tap / op.kw, kx = tap - ky * op.kw;
+        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+        tma_load_4d(smem_u32(smem_a + stage * a_bytes), &op.tmap_a, &full_bar[stage], cb * BK,
+                    ox0 * op.stride + kx - op.pad_w, oy0 * op.stride + ky - op.pad_h, n0);
+        tma_load_2d(smem_u32(smem_b + stage * b_bytes), &op.tmap_w, &full_bar[stage], tap * op.Cin + cb * BK, n_off);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      const uint32_t layout = (BK == 64) ? 2u : 4u;
+      const uint32_t sbo = 8u * (uint32_t)BK * 2u;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * a_bytes), sbo, layout);
+        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * b_bytes), sbo, layout);
+        for (int kk = 0; kk < BK / 16; ++kk)
+          mma_bf16(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        mma_commit(&empty_bar[stage]);          // frees this smem stage when the MMAs above retire
+        if (it == k_iters - 1) mma_commit(accum_bar);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 ; thread <-> one output pixel (tile row)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    bool valid;
+    long long m;
+    if (op.flat) {
+      m = (long long)ox0 + r;
+      valid = m < (long long)n_img * op.Hout * op.Wout;
+    } else {
+      const int per_img = op.box_w * op.box_h;
+      const int ni = r / per_img, rem = r - ni * per_img;
+      const int hy = rem / op.box_w, wx = rem - hy * op.box_w;
+      const int n = n0 + ni, oy = oy0 + hy, ox = ox0 + wx;
+      valid = (ni < op.box_n) && (n < n_img) && (oy < op.Hout) && (ox < op.Wout);
+      m = ((long long)n * op.Hout + oy) * op.Wout + ox;
+    }
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c = 0; c < BN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr_row + (uint32_t)c, v);
+      if (valid) {
+        const int ng = n_off + c;
+        float f[16];
+        const float4* b4 = reinterpret_cast<const float4*>(op.bias + ng);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 bv = __ldg(b4 + j);
+          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bv.x;
+          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv.y;
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv.z;
+          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv.w;
+        }
+        if (op.epi != EPI_RELU) {
+          const uint4* xr = reinterpret_cast<const uint4*>(op.resid + (size_t)m * op.Cout + ng);
+          const uint4 x0 = xr[0], x1 = xr[1];
+          const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&x0);
+          const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&x1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 a = __bfloat1622float2(h0[j]), b = __bfloat1622float2(h1[j]);
+            f[2 * j] = fmaf(op.scale, f[2 * j], a.x);
+            f[2 * j + 1] = fmaf(op.scale, f[2 * j + 1], a.y);
+            f[8 + 2 * j] = fmaf(op.scale, f[8 + 2 * j], b.x);
+            f[8 + 2 * j + 1] = fmaf(op.scale, f[8 + 2 * j + 1], b.y);
+          }
+        }
+        if (op.epi != EPI_RESID) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        uint4 o0, o1;
+        o0.x = pack_bf16(f[0], f[1]); o0.y = pack_bf16(f[2], f[3]); o0.z = pack_bf16(f[4], f[5]); o0.w = pack_bf16(f[6], f[7]);
+        o1.x = pack_bf16(f[8], f[9]); o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
+        for (int sidx = 0; sidx < op.nseg; ++sidx) {
+          const OutSeg& sg = op.seg[sidx];
+          if (ng >= sg.n_begin && ng < sg.n_end) {
+            uint4* d = reinterpret_cast<uint4*>(sg.dst + (size_t)m * sg.dst_ctot + sg.dst_coff + (ng - sg.n_begin));
+            d[0] = o0;
+            d[1] = o1;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+}  // namespace umma
+
+// ----------------------------------------------------------------------------- host side
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+int umma_init(trl_ctx* c) {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    TRL_CUDA(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) TRL_FAIL(c, TRL_E_CUDA, "cuTensorMapEncodeTiled unavailable");
+    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  }
+  TRL_CUDA(c, cudaFuncSetAttribute(umma::conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  return TRL_OK;
+}
+
+// Choose the 128-row tile shape (box_w, box_h, box_n) that minimises the number of tiles for a nominal batch.
+static void choose_box(const ConvOp& op, int* bw, int* bh, int* bn) {
+  const int NB = 240;   // nominal batch
+  long long best = -1;
+  const int lim = 256 / op.stride;      // TMA boxDim <= 256 along the traversed extent
+  for (int w = 1; w <= op.Wout && w <= 128 && w <= lim; ++w)
+    for (int h = 1; h <= op.Hout && w * h <= 128 && h <= lim; ++h) {
+      const int nn = 128 / (w * h);
+      const long long tiles = (long long)ceil_div(op.Wout, w) * ceil_div(op.Hout, h) * ceil_div(NB, nn);
+      if (best < 0 || tiles < best) { best = tiles; *bw = w; *bh = h; *bn = nn; }
+    }
+}
+
+int umma_encode_maps(trl_ctx* c, ConvOp& op, int n_cap) {
+  if (op.Cin % 64 == 0) op.block_k = 64;
+  else if (op.Cin % 32 == 0) op.block_k = 32;
+  else TRL_FAIL(c, TRL_E_INVALID, "%s: Cin=%d not a multiple of 32", op.name, op.Cin);
+  if (op.Cout % 128 == 0) op.block_n = 128;
+  else if (op.Cout <= 256 && op.Cout % 16 == 0) op.block_n = op.Cout;
+  else if (op.Cout % 96 == 0) op.block_n = 96;
+  else if (op.Cout % 64 == 0) op.block_n = 64;
+  else TRL_FAIL(c, TRL_E_INVALID, "%s: unsupported Cout=%d", op.name, op.Cout);
+  if (op.block_n > 256) TRL_FAIL(c, TRL_E_INVALID, "%s: block_n", op.name);
+  op.flat = (op.kh == 1 && op.kw == 1 && op.stride == 1 && op.pad_h == 0 && op.pad_w == 0) ? 1 : 0;
+  const CUtensorMapSwizzle swz = (op.block_k == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], estr[4];
+  const cuuint64_t pix = (cuuint64_t)n_cap * op.Hin * op.Win;
+  if (op.flat) {
+    op.box_w = 128; op.box_h = 1; op.box_n = 1;
+    dims[0] = op.Cin; dims[1] = pix; dims[2] = 1; dims[3] = 1;
+    strides[0] = (cuuint64_t)op.in_ctot * 2; strides[1] = pix * op.in_ctot * 2; strides[2] = strides[1];
+    box[0] = op.block_k; box[1] = 128; box[2] = 1; box[3] = 1;
+    estr[0] = estr[1] = estr[2] = estr[3] = 1;
+  } else {
+    choose_box(op, &op.box_w, &op.box_h, &op.box_n);
+    dims[0] = op.Cin; dims[1] = op.Win; dims[2] = op.Hin; dims[3] = n_cap;
+    strides[0] = (cuuint64_t)op.in_ctot * 2;
+    strides[1] = (cuuint64_t)op.Win * op.in_ctot * 2;
+    strides[2] = (cuuint64_t)op.Hin * op.Win * op.in_ctot * 2;
+    box[0] = op.block_k; box[1] = op.box_w * op.stride; box[2] = op.box_h * op.stride; box[3] = op.box_n;
+    estr[0] = 1; estr[1] = op.stride; estr[2] = op.stride; estr[3] = 1;
+  }
+  CUresult r = g_encode(&op.tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)(op.in + op.in_coff), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) TRL_FAIL(c, TRL_E_CUDA, "%s: cuTensorMapEncodeTiled(A) failed with %d", op.name, (int)r);
+  const cuuint64_t ktot = (cuuint64_t)op.kh * op.kw * op.Cin;
+  cuuint64_t wd[2] = {ktot, (cuuint64_t)op.Cout};
+  cuuint64_t ws[1] = {ktot * 2};
+  cuuint32_t wb[2] = {(cuuint32_t)op.block_k, (cuuint32_t)op.block_n};
+  cuuint32_t we[2] = {1, 1};
+  r = g_encode(&op.tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)op.w, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) TRL_FAIL(c, TRL_E_CUDA, "%s: cuTensorMapEncodeTiled(W) failed with %d", op.name, (int)r);
+  return TRL_OK;
+}
+
+int launch_conv_umma(trl_ctx* c, const ConvOp& op, int n, cudaStream_t s) {
+  using namespace umma;
+  if (n <= 0) return TRL_OK;
+  int tiles_w, tiles_h, tiles_n;
+  if (op.flat) {
+    tiles_w = (int)(((long long)n * op.Hout * op.Wout + 127) / 128);
+    tiles_h = 1; tiles_n = 1;
+  } else {
+    tiles_w = ceil_div(op.Wout, op.box_w);
+    tiles_h = ceil_div(op.Hout, op.box_h);
+    tiles_n = ceil_div(n, op.box_n);
+  }
+  const int k_iters = op.kh * op.kw * (op.Cin / op.block_k);
+  const int stage_bytes = (BLOCK_M + op.block_n) * op.block_k * 2;
+  int stages = k_iters < 4 ? k_iters : 4;
+  while (stages > 2 && stages * stage_bytes > 100 * 1024) --stages;
+  if (stages < 1) stages = 1;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  uint32_t cols = 32;
+  while ((int)cols < op.block_n) cols <<= 1;
+  dim3 grid(tiles_w * tiles_h * tiles_n, op.Cout / op.block_n);
+  conv_umma_kernel<<<grid, NUM_THREADS, smem, s>>>(op, n, tiles_w, tiles_h, stages, cols);
+  TRL_LAUNCH_CHECK(c);
+  return TRL_OK;
+}

@@ -1,0 +1,341 @@
+// K8 / K9: R-Net (24x24) and O-Net (48x48) of the MTCNN cascade, fp32 on the FMA pipe.
+// One CTA per candidate; all activations stay in shared memory, weights stream from L2 (they are shared by
+// every CTA in flight), the first conv+pool layers are evaluated in row bands to bound shared memory.
+//
+// upstream: models/mtcnn.py RNet.forward / ONet.forward.  ceil_mode pooling clips the
+// window at the border; the flatten before the first dense layer is (W, H, C) ordered upstream -- the host
+// permutes the dense weight rows once so the kernel reads its [C][H][W] activations directly.
+#include "common.cuh"
+
+namespace ro {
+
+__device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : v * a; }
+
+// conv (valid, stride 1) + bias + PReLU for conv output rows [r0, r1): in [CIN][HIN][WIN] (smem) ->
+// out [COUT][r1-r0][WOUT] (smem).  w: global [CIN*K*K][COUT].  item = 4 channels x 4 pixels of one row.
+template <int CIN, int COUT, int K, int HIN, int WIN>
+__device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* __restrict__ out, int r0, int r1,
+                                          const float* __restrict__ w, const float* __restrict__ bias,
+                                          const float* __restrict__ alpha) {
+  constexpr int WOUT = WIN - K + 1;
+  constexpr int PXG = (WOUT + 3) / 4;
+  constexpr int CG = COUT / 4;
+  static_assert(COUT % 4 == 0, "COUT");
+  const int rows = r1 - r0;
+  const int items = CG * rows * PXG;
+  for (int item = threadIdx.x; item < items; item += blockDim.x) {
+    const int cg = item / (rows * PXG);
+    const int rem = item - cg * (rows * PXG);
+    const int row = rem / PXG, pg = rem - row * PXG;
+    const int x0 = pg * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        const float* ir = in + (ci * HIN + r0 + row + ky) * WIN + x0;
+        float v[4 + K - 1];
+#pragma unroll
+        for (int t = 0; t < 4 + K - 1; ++t) v[t] = (x0 + t < WIN) ? ir[t] : 0.f;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(w + ((ci * K + ky) * K + kx) * COUT + cg * 4));
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            acc[px][0] = fmaf(v[px + kx], wv.x, acc[px][0]);
+            acc[px][1] = fmaf(v[px + kx], wv.y, acc[px][1]);
+            acc[px][2] = fmaf(v[px + kx], wv.z, acc[px][2]);
+            acc[px][3] = fmaf(v[px + kx], wv.w, acc[px][3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = cg * 4 + j;
+      const float b = __ldg(bias + co), a = __ldg(alpha + co);
+#pragma unroll
+      for (int px = 0; px < 4; ++px)
+        if (x0 + px < WOUT) out[(co * rows + row) * WOUT + x0 + px] = prelu(acc[px][j] + b, a);
+    }
+  }
+}
+
+// MaxPool2d(PK, PS, ceil_mode=True) for pooled rows [p0, p1) from a conv band that starts at conv row band_r0.
+template <int C, int HC, int WC, int PK, int PS, int HP, int WP>
+__device__ __forceinline__ void pool_rows(const float* __restrict__ band, int band_r0, int band_rows,
+                                          float* __restrict__ out, int p0, int p1) {
+  const int n = C * (p1 - p0) * WP;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i / ((p1 - p0) * WP);
+    const int rem = i - c * ((p1 - p0) * WP);
+    const int py = p0 + rem / WP, px = rem % WP;
+    float m = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < PK; ++dy) {
+      const int y = py * PS + dy;
+      if (y >= HC) continue;
+#pragma unroll
+      for (int dx = 0; dx < PK; ++dx) {
+        const int x = px * PS + dx;
+        if (x >= WC) continue;
+        m = fmaxf(m, band[(c * band_rows + (y - band_r0)) * WC + x]);
+      }
+    }
+    out[(c * HP + py) * WP + px] = m;
+  }
+}
+
+// conv + PReLU + ceil-mode maxpool, banded over PR pooled rows at a time
+template <int CIN, int COUT, int K, int HIN, int WIN, int PK, int PS, int PR>
+__device__ __forceinline__ void conv_pool(const float* in, float* band, float* out, const float* w, const float* b,
+                                          const float* a) {
+  constexpr int HC = HIN - K + 1, WC = WIN - K + 1;
+  constexpr int HP = (HC - PK + PS - 1) / PS + 1, WP = (WC - PK + PS - 1) / PS + 1;
+  for (int p0 = 0; p0 < HP; p0 += PR) {
+    const int p1 = min(p0 + PR, HP);
+    const int r0 = p0 * PS, r1 = min((p1 - 1) * PS + PK, HC);
+    conv_rows<CIN, COUT, K, HIN, WIN>(in, band, r0, r1, w, b, a);
+    __syncthreads();
+    pool_rows<COUT, HC, WC, PK, PS, HP, WP>(band, r0, r1 - r0, out, p0, p1);
+    __syncthreads();
+  }
+}
+
+// dense + bias (+ PReLU): in_s[IN] -> out_s[OUT]; w global [IN][OUT]; blockDim.x must be a multiple of OUT
+template <int IN, int OUT, bool PRELU>
+__device__ __forceinline__ void dense(const float* __restrict__ in_s, float* __restrict__ out_s, float* __restrict__ part_s,
+                                      const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ a) {
+  const int ks_n = blockDim.x / OUT;
+  const int o = threadIdx.x % OUT, ks = threadIdx.x / OUT;
+  if (ks < ks_n) {
+    const int k0 = (IN * ks) / ks_n, k1 = (IN * (ks + 1)) / ks_n;
+    float acc0 = 0.f, acc1 = 0.f;
+    int k = k0;
+    for (; k + 1 < k1; k += 2) {
+      acc0 = fmaf(in_s[k], __ldg(w + (size_t)k * OUT + o), acc0);
+      acc1 = fmaf(in_s[k + 1], __ldg(w + (size_t)(k + 1) * OUT + o), acc1);
+    }
+    if (k < k1) acc0 = fmaf(in_s[k], __ldg(w + (size_t)k * OUT + o), acc0);
+    part_s[ks * OUT + o] = acc0 + acc1;
+  }
+  __syncthreads();
+  if (threadIdx.x < OUT) {
+    float v = __ldg(b + o);
+    for (int q = 0; q < ks_n; ++q) v += part_s[q * OUT + o];
+    out_s[o] = PRELU ? prelu(v, __ldg(a + o)) : v;
+  }
+  __syncthreads();
+}
+
+// heads: 6 outputs (2 class logits, 4 box offsets) = one warp each; w global [6][IN]
+template <int IN>
+__device__ __forceinline__ void heads(const float* __restrict__ in_s, const float* __restrict__ w, const float* __restrict__ b,
+                                      float* __restrict__ h_s) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < 6) {
+    float acc = 0.f;
+    for (int k = lane; k < IN; k += 32) acc = fmaf(in_s[k], __ldg(w + warp * IN + k), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) h_s[warp] = acc + __ldg(b + warp);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void write_outputs(const float* h_s, int slot, float* prob, float* reg) {
+  if (threadIdx.x == 0) {
+    const float mx = fmaxf(h_s[0], h_s[1]);
+    const float e0 = expf(h_s[0] - mx), e1 = expf(h_s[1] - mx);
+    prob[slot] = __fdiv_rn(e1, e0 + e1);
+    reg[slot * 4 + 0] = h_s[2]; reg[slot * 4 + 1] = h_s[3]; reg[slot * 4 + 2] = h_s[4]; reg[slot * 4 + 3] = h_s[5];
+  }
+}
+
+__device__ __forceinline__ bool slot_live(int slot, const int* d_count, int per_frame_cap) {
+  if (per_frame_cap > 0) {
+    const int b = slot / per_frame_cap;
+    return slot - b * per_frame_cap < d_count[b];
+  }
+  return d_count == nullptr || slot < *d_count;
+}
+
+// ---------------------------------------------------------------- R-Net
+// packed weights: w1[27][28] b1 a1 | w2[252][48] b2 a2 | w3[192][64] b3 a3 | w4[576][128] b4 a4 | wh[6][128] bh[6]
+namespace r {
+constexpr int W1 = 0, B1 = W1 + 27 * 28, A1 = B1 + 28;
+constexpr int W2 = A1 + 28, B2 = W2 + 252 * 48, A2 = B2 + 48;
+constexpr int W3 = A2 + 48, B3 = W3 + 192 * 64, A3 = B3 + 64;
+constexpr int W4 = A3 + 64, B4 = W4 + 576 * 128, A4 = B4 + 128;
+constexpr int WH = A4 + 128, BH = WH + 6 * 128;
+constexpr int TOTAL = ((BH + 6 + 3) / 4) * 4;
+// smem (floats)
+constexpr int S_IN = 0;                    // 3*24*24 = 1728
+constexpr int S_BAND = S_IN + 1728;        // max(28*9*22 = 5544, 48*9*9 = 3888)
+constexpr int S_P1 = S_BAND + 5544;        // 28*11*11 = 3388
+constexpr int S_P2 = S_P1 + 3388;          // 48*4*4 = 768
+constexpr int S_C3 = S_P2 + 768;           // 64*3*3 = 576
+constexpr int S_D4 = S_C3 + 576;           // 128
+constexpr int S_PART = S_D4 + 128;         // 256
+constexpr int S_H = S_PART + 256;          // 8
+constexpr int S_TOTAL = S_H + 8;
+}  // namespace r
+
+__global__ void __launch_bounds__(256) rnet_kernel(const float* __restrict__ in, const float* __restrict__ wp,
+                                                  const int* __restrict__ d_count, int per_frame_cap,
+                                                  float* __restrict__ prob, float* __restrict__ reg) {
+  using namespace r;
+  extern __shared__ __align__(16) float sm[];
+  const int slot = blockIdx.x;
+  if (!slot_live(slot, d_count, per_frame_cap)) return;
+  const float* src = in + (size_t)slot * 1728;
+  for (int i = threadIdx.x; i < 1728 / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(sm + S_IN)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+  __syncthreads();
+  conv_pool<3, 28, 3, 24, 24, 3, 2, 4>(sm + S_IN, sm + S_BAND, sm + S_P1, wp + W1, wp + B1, wp + A1);    // -> 28x11x11
+  conv_pool<28, 48, 3, 11, 11, 3, 2, 4>(sm + S_P1, sm + S_BAND, sm + S_P2, wp + W2, wp + B2, wp + A2);   // -> 48x4x4
+  conv_rows<48, 64, 2, 4, 4>(sm + S_P2, sm + S_C3, 0, 3, wp + W3, wp + B3, wp + A3);                    // -> 64x3x3
+  __syncthreads();
+  dense<576, 128, true>(sm + S_C3, sm + S_D4, sm + S_PART, wp + W4, wp + B4, wp + A4);
+  heads<128>(sm + S_D4, wp + WH, wp + BH, sm + S_H);
+  write_outputs(sm + S_H, slot, prob, reg);
+}
+
+// ---------------------------------------------------------------- O-Net
+// packed: w1[27][32] | w2[288][64] | w3[576][64] | w4[256][128] | w5[1152][256] | wh[6][256] bh[6]  (+ b/a each)
+namespace o {
+constexpr int W1 = 0, B1 = W1 + 27 * 32, A1 = B1 + 32;
+constexpr int W2 = A1 + 32, B2 = W2 + 288 * 64, A2 = B2 + 64;
+constexpr int W3 = A2 + 64, B3 = W3 + 576 * 64, A3 = B3 + 64;
+constexpr int W4 = A3 + 64, B4 = W4 + 256 * 128, A4 = B4 + 128;
+constexpr int W5 = A4 + 128, B5 = W5 + 1152 * 256, A5 = B5 + 256;
+constexpr int WH = A5 + 256, BH = WH + 6 * 256;
+constexpr int TOTAL = ((BH + 6 + 3) / 4) * 4;
+// smem (floats)
+constexpr int S_IN = 0;                     // 3*48*48 = 6912; later p2 64*10*10 = 6400
+constexpr int S_P1 = S_IN + 6912;           // 32*23*23 = 16928
+constexpr int S_BAND = S_P1 + 16928;        // max(32*9*46 = 13248, 64*11*21 = 14784, 64*8*8 = 4096)
+constexpr int S_P3 = S_BAND + 14784;        // 64*4*4 = 1024
+constexpr int S_C4 = S_P3 + 1024;           // 128*3*3 = 1152
+constexpr int S_D5 = S_C4 + 1152;           // 256
+constexpr int S_PART = S_D5 + 256;          // 512
+constexpr int S_H = S_PART + 512;
+constexpr int S_TOTAL = S_H + 8;
+}  // namespace o
+
+__global__ void __launch_bounds__(512) onet_kernel(const float* __restrict__ in, const float* __restrict__ wp,
+                                                  const int* __restrict__ d_count, int per_frame_cap,
+                                                  float* __restrict__ prob, float* __restrict__ reg) {
+  using namespace o;
+  extern __shared__ __align__(16) float sm[];
+  const int slot = blockIdx.x;
+  if (!slot_live(slot, d_count, per_frame_cap)) return;
+  const float* src = in + (size_t)slot * 6912;
+  for (int i = threadIdx.x; i < 6912 / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(sm + S_IN)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+  __syncthreads();
+  conv_pool<3, 32, 3, 48, 48, 3, 2, 4>(sm + S_IN, sm + S_BAND, sm + S_P1, wp + W1, wp + B1, wp + A1);     // -> 32x23x23
+  float* p2 = sm + S_IN;                                                                                  // input is dead
+  conv_pool<32, 64, 3, 23, 23, 3, 2, 5>(sm + S_P1, sm + S_BAND, p2, wp + W2, wp + B2, wp + A2);           // -> 64x10x10
+  conv_pool<64, 64, 3, 10, 10, 2, 2, 4>(p2, sm + S_BAND, sm + S_P3, wp + W3, wp + B3, wp + A3);           // -> 64x4x4
+  conv_rows<64, 128, 2, 4, 4>(sm + S_P3, sm + S_C4, 0, 3, wp + W4, wp + B4, wp + A4);                     // -> 128x3x3
+  __syncthreads();
+  dense<1152, 256, true>(sm + S_C4, sm + S_D5, sm + S_PART, wp + W5, wp + B5, wp + A5);
+  heads<256>(sm + S_D5, wp + WH, wp + BH, sm + S_H);
+  write_outputs(sm + S_H, slot, prob, reg);
+}
+
+}  // namespace ro
+
+// ---------------------------------------------------------------- host: weight packing + launch
+
+static void pack_conv(std::vector<float>& pk, int off, const float* w, int cout, int cin, int k) {
+  // upstream [cout][cin][k][k] -> [(ci,ky,kx)][cout]
+  for (int co = 0; co < cout; ++co)
+    for (int q = 0; q < cin * k * k; ++q) pk[off + q * cout + co] = w[co * cin * k * k + q];
+}
+
+// upstream dense weight [out][in] with in = (x*H + y)*C + c  ->  [ (c*H + y)*W + x ][out]
+static void pack_dense_whc(std::vector<float>& pk, int off, const float* w, int out, int C, int H, int W) {
+  const int in = C * H * W;
+  for (int o = 0; o < out; ++o)
+    for (int c = 0; c < C; ++c)
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x)
+          pk[off + ((c * H + y) * W + x) * out + o] = w[(size_t)o * in + (x * H + y) * C + c];
+}
+
+int ro_pack_weights(trl_ctx* c, const float* h_r, size_t rlen, const float* h_o, size_t olen) {
+  using namespace ro;
+  if (rlen != 100178) TRL_FAIL(c, TRL_E_INVALID, "rnet blob has %zu floats, expected 100178", rlen);
+  if (olen != 389040) TRL_FAIL(c, TRL_E_INVALID, "onet blob has %zu floats, expected 389040", olen);
+  {
+    std::vector<float> pk(r::TOTAL, 0.f);
+    const float* p = h_r;
+    pack_conv(pk, r::W1, p, 28, 3, 3); p += 28 * 27;
+    memcpy(&pk[r::B1], p, 28 * 4); p += 28; memcpy(&pk[r::A1], p, 28 * 4); p += 28;
+    pack_conv(pk, r::W2, p, 48, 28, 3); p += 48 * 252;
+    memcpy(&pk[r::B2], p, 48 * 4); p += 48; memcpy(&pk[r::A2], p, 48 * 4); p += 48;
+    pack_conv(pk, r::W3, p, 64, 48, 2); p += 64 * 192;
+    memcpy(&pk[r::B3], p, 64 * 4); p += 64; memcpy(&pk[r::A3], p, 64 * 4); p += 64;
+    pack_dense_whc(pk, r::W4, p, 128, 64, 3, 3); p += 128 * 576;
+    memcpy(&pk[r::B4], p, 128 * 4); p += 128; memcpy(&pk[r::A4], p, 128 * 4); p += 128;
+    // dense5_1 [2][128], bias[2], dense5_2 [4][128], bias[4]
+    memcpy(&pk[r::WH], p, 2 * 128 * 4); p += 256;
+    memcpy(&pk[r::BH], p, 2 * 4); p += 2;
+    memcpy(&pk[r::WH + 256], p, 4 * 128 * 4); p += 512;
+    memcpy(&pk[r::BH + 2], p, 4 * 4); p += 4;
+    TRL_CUDA(c, cudaMalloc(&c->d_rnet, pk.size() * 4));
+    TRL_CUDA(c, cudaMemcpy(c->d_rnet, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+  }
+  {
+    std::vector<float> pk(o::TOTAL, 0.f);
+    const float* p = h_o;
+    pack_conv(pk, o::W1, p, 32, 3, 3); p += 32 * 27;
+    memcpy(&pk[o::B1], p, 32 * 4); p += 32; memcpy(&pk[o::A1], p, 32 * 4); p += 32;
+    pack_conv(pk, o::W2, p, 64, 32, 3); p += 64 * 288;
+    memcpy(&pk[o::B2], p, 64 * 4); p += 64; memcpy(&pk[o::A2], p, 64 * 4); p += 64;
+    pack_conv(pk, o::W3, p, 64, 64, 3); p += 64 * 576;
+    memcpy(&pk[o::B3], p, 64 * 4); p += 64; memcpy(&pk[o::A3], p, 64 * 4); p += 64;
+    pack_conv(pk, o::W4, p, 128, 64, 2); p += 128 * 256;
+    memcpy(&pk[o::B4], p, 128 * 4); p += 128; memcpy(&pk[o::A4], p, 128 * 4); p += 128;
+    pack_dense_whc(pk, o::W5, p, 256, 128, 3, 3); p += 256 * 1152;
+    memcpy(&pk[o::B5], p, 256 * 4); p += 256; memcpy(&pk[o::A5], p, 256 * 4); p += 256;
+    // dense6_1 [2][256] + bias, dense6_2 [4][256] + bias, dense6_3 (landmarks) ignored
+    memcpy(&pk[o::WH], p, 2 * 256 * 4); p += 512;
+    memcpy(&pk[o::BH], p, 2 * 4); p += 2;
+    memcpy(&pk[o::WH + 512], p, 4 * 256 * 4); p += 1024;
+    memcpy(&pk[o::BH + 2], p, 4 * 4); p += 4;
+    TRL_CUDA(c, cudaMalloc(&c->d_onet, pk.size() * 4));
+    TRL_CUDA(c, cudaMemcpy(c->d_onet, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+  }
+  TRL_CUDA(c, cudaFuncSetAttribute(rnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, r::S_TOTAL * 4));
+  TRL_CUDA(c, cudaFuncSetAttribute(onet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, o::S_TOTAL * 4));
+  return TRL_OK;
+}
+
+int launch_rnet_ex(trl_ctx* c, const float* d_in, int n_slots, const int* d_count, int per_frame_cap, float* d_prob,
+                   float* d_reg, cudaStream_t s) {
+  if (n_slots <= 0) return TRL_OK;
+  ro::rnet_kernel<<<n_slots, 256, ro::r::S_TOTAL * 4, s>>>(d_in, c->d_rnet, d_count, per_frame_cap, d_prob, d_reg);
+  TRL_LAUNCH_CHECK(c);
+  return TRL_OK;
+}
+
+int launch_onet_ex(trl_ctx* c, const float* d_in, int n_slots, const int* d_count, int per_frame_cap, float* d_prob,
+                   float* d_reg, cudaStream_t s) {
+  if (n_slots <= 0) return TRL_OK;
+  ro::onet_kernel<<<n_slots, 512, ro::o::S_TOTAL * 4, s>>>(d_in, c->d_onet, d_count, per_frame_cap, d_prob, d_reg);
+  TRL_LAUNCH_CHECK(c);
+  return TRL_OK;
+}
+
+int launch_rnet(trl_ctx* c, const float* d_in, int n_max, const int* d_count, float* d_prob, float* d_reg, cudaStream_t s) {
+  return launch_rnet_ex(c, d_in, n_max, d_count, 0, d_prob, d_reg, s);
+}
+int launch_onet(trl_ctx* c, const float* d_in, int n_max, const int* d_count, float* d_prob, float* d_reg, cudaStream_t s) {
+  return launch_onet_ex(c, d_in, n_max, d_count, 0, d_prob, d_reg, s);
+}

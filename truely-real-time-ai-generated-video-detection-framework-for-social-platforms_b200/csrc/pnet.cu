@@ -1,0 +1,398 @@
+// K2 + K3: fused P-Net (conv1+PReLU+maxpool, conv2+PReLU, conv3+PReLU, conv4_1 -> softmax, conv4_2) and
+// generateBoundingBox, fp32 on the FMA pipe.  One CTA computes a 16x32 tile of output cells; every intermediate
+// lives in shared memory, the only HBM traffic is the input tile and the (rare) candidates.
+//
+// upstream: models/mtcnn.py PNet.forward, models/utils/detect_face.py generateBoundingBox.
+//
+// Thread tiles are register blocked (4 px x 4|8 channels) with weights broadcast from shared memory by
+// LDS.128, so the inner loops issue ~90 % FFMA.  FLOP roof, not HBM, binds this kernel.
+#include "common.cuh"
+
+namespace pnet {
+
+constexpr int TOY = 16, TOX = 32;            // output cells per CTA
+constexpr int P1H = TOY + 4, P1W = TOX + 4;  // pooled conv1 tile (20 x 36)
+constexpr int P1P = 40;                      // pitch (conv2 over-reads to col 37)
+constexpr int C2H = TOY + 2, C2W = 36;       // conv2 tile rows x computed cols (34 valid + 2 slack)
+constexpr int C2P = 36;
+constexpr int INH = 2 * TOY + 10, INW = 2 * TOX + 10;   // 42 x 74 input tile
+constexpr int INP = 76;
+
+// packed weights (floats), k = (ci*3+ky)*3+kx
+constexpr int W1 = 0;                 // [27][12]
+constexpr int B1 = W1 + 27 * 12;      // [12]
+constexpr int A1 = B1 + 12;           // [12]
+constexpr int W2 = A1 + 12;           // [90][16]
+constexpr int B2 = W2 + 90 * 16;
+constexpr int A2 = B2 + 16;
+constexpr int W3 = A2 + 16;           // [144][32]
+constexpr int B3 = W3 + 144 * 32;
+constexpr int A3 = B3 + 32;
+constexpr int WH = A3 + 32;           // [32][8]: cols 0,1 conv4_1; 2..5 conv4_2
+constexpr int BH = WH + 32 * 8;       // [8]
+constexpr int WTOTAL = BH + 8;        // 6756 floats
+static_assert(WTOTAL % 4 == 0, "float4 copy");
+
+constexpr int SM_IN = 3 * INH * INP;          // 9576
+constexpr int SM_C2 = 16 * C2H * C2P;         // 10368   (aliases the input tile)
+constexpr int SM_A = SM_C2 > SM_IN ? SM_C2 : SM_IN;
+constexpr int SM_P1 = 10 * P1H * P1P;         // 8000    (later: head partial sums, 24*128)
+constexpr int SMEM_FLOATS = WTOTAL + SM_A + SM_P1;
+constexpr int SMEM_BYTES = SMEM_FLOATS * 4;   // ~100 KB -> 2 CTAs / SM
+
+struct Level {
+  const float* in;     // [B][3][hs][ws]
+  int hs, ws, oh, ow;
+  int tiles_x, tiles;  // tiles per frame
+  float scale;
+  float* prob;         // optional maps
+  float* reg;
+  Cand* cand;          // optional: candidate list of (frame, level): cand + (b*n_levels + lvl)*cap
+  int* cnt;
+};
+
+struct Params {
+  int n_levels;
+  int blk_start[TRL_MAX_SCALES + 1];
+  Level lv[TRL_MAX_SCALES];
+  float thr;
+  int cap;
+  CapFlag* capflag;
+};
+
+__device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : v * a; }
+
+__global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ wpacked, const __grid_constant__ Params p) {
+  extern __shared__ __align__(16) float smem[];
+  float* w_s = smem;
+  float* a_s = smem + WTOTAL;          // input tile, later conv2 output
+  float* p1_s = a_s + SM_A;            // pooled conv1, later head partials
+  const int tid = threadIdx.x;
+
+  int lvl = 0;
+  while (lvl + 1 < p.n_levels && (int)blockIdx.x >= p.blk_start[lvl + 1]) ++lvl;
+  const Level& L = p.lv[lvl];
+  const int b = blockIdx.y;
+  const int tile = (int)blockIdx.x - p.blk_start[lvl];
+  const int ty = tile / L.tiles_x, tx = tile - ty * L.tiles_x;
+  const int oy0 = ty * TOY, ox0 = tx * TOX;
+  const int hs = L.hs, ws = L.ws;
+
+  // ---- stage weights and the input tile
+  for (int i = tid; i < WTOTAL / 4; i += 256)
+    reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(wpacked) + i);
+  {
+    const float* src = L.in + (size_t)b * 3 * hs * ws;
+    const int iy0 = 2 * oy0, ix0 = 2 * ox0;
+    for (int i = tid; i < 3 * INH * INW; i += 256) {
+      const int ci = i / (INH * INW);
+      const int r = (i - ci * INH * INW) / INW;
+      const int cx = i - ci * INH * INW - r * INW;
+      const int gy = iy0 + r, gx = ix0 + cx;
+      float v = 0.f;
+      if (gy < hs && gx < ws) v = __ldg(src + ((size_t)ci * hs + gy) * ws + gx);
+      a_s[(ci * INH + r) * INP + cx] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- conv1 (3->10, 3x3) + PReLU + maxpool(2,2,ceil): one pooled pixel x 10 channels per item
+  {
+    const int c1h = hs - 2, c1w = ws - 2;     // valid conv1 extent (ceil-mode pooling clips to it)
+    for (int item = tid; item < P1H * P1W; item += 256) {
+      const int py = item / P1W, px = item - py * P1W;
+      float patch[3][4][4];
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float2 v0 = *reinterpret_cast<const float2*>(&a_s[(ci * INH + 2 * py + r) * INP + 2 * px]);
+          const float2 v1 = *reinterpret_cast<const float2*>(&a_s[(ci * INH + 2 * py + r) * INP + 2 * px + 2]);
+          patch[ci][r][0] = v0.x; patch[ci][r][1] = v0.y; patch[ci][r][2] = v1.x; patch[ci][r][3] = v1.y;
+        }
+      float acc[4][12];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int co = 0; co < 12; ++co) acc[q][co] = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float* wr = &w_s[W1 + ((ci * 3 + ky) * 3 + kx) * 12];
+            const float4 wa = *reinterpret_cast<const float4*>(wr);
+            const float4 wb = *reinterpret_cast<const float4*>(wr + 4);
+            const float4 wc = *reinterpret_cast<const float4*>(wr + 8);
+            const float w[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float v = patch[ci][(q >> 1) + ky][(q & 1) + kx];
+#pragma unroll
+              for (int co = 0; co < 10; ++co) acc[q][co] = fmaf(v, w[co], acc[q][co]);
+            }
+          }
+      const int gy = 2 * (oy0 + py), gx = 2 * (ox0 + px);
+#pragma unroll
+      for (int co = 0; co < 10; ++co) {
+        const float bias = w_s[B1 + co], al = w_s[A1 + co];
+        float m = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool ok = (gy + (q >> 1) < c1h) && (gx + (q & 1) < c1w);
+          const float v = prelu(acc[q][co] + bias, al);
+          m = ok ? fmaxf(m, v) : m;
+        }
+        p1_s[(co * P1H + py) * P1P + px] = (m == -INFINITY) ? 0.f : m;
+      }
+    }
+    // slack columns read by conv2's last pixel group
+    for (int i = tid; i < 10 * P1H * (P1P - P1W); i += 256) {
+      const int co = i / (P1H * (P1P - P1W));
+      const int r = (i / (P1P - P1W)) % P1H;
+      const int cx = P1W + i % (P1P - P1W);
+      p1_s[(co * P1H + r) * P1P + cx] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  // ---- conv2 (10->16, 3x3) + PReLU: item = (4 channels, row, 4 px); output over the dead input tile
+  {
+    constexpr int PXG = C2W / 4;                   // 9
+    constexpr int ITEMS = 4 * C2H * PXG;           // 648
+    for (int item = tid; item < ITEMS; item += 256) {
+      const int cg = item / (C2H * PXG);
+      const int rem = item - cg * (C2H * PXG);
+      const int row = rem / PXG, pg = rem - row * PXG;
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+      for (int ci = 0; ci < 10; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float* ir = &p1_s[(ci * P1H + row + ky) * P1P + 4 * pg];
+          const float4 i0 = *reinterpret_cast<const float4*>(ir);
+          const float2 i1 = *reinterpret_cast<const float2*>(ir + 4);
+          const float in[6] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y};
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 w = *reinterpret_cast<const float4*>(&w_s[W2 + ((ci * 3 + ky) * 3 + kx) * 16 + cg * 4]);
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+              acc[px][0] = fmaf(in[px + kx], w.x, acc[px][0]);
+              acc[px][1] = fmaf(in[px + kx], w.y, acc[px][1]);
+              acc[px][2] = fmaf(in[px + kx], w.z, acc[px][2]);
+              acc[px][3] = fmaf(in[px + kx], w.w, acc[px][3]);
+            }
+          }
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int co = cg * 4 + j;
+        const float bias = w_s[B2 + co], al = w_s[A2 + co];
+        float4 o;
+        o.x = prelu(acc[0][j] + bias, al);
+        o.y = prelu(acc[1][j] + bias, al);
+        o.z = prelu(acc[2][j] + bias, al);
+        o.w = prelu(acc[3][j] + bias, al);
+        *reinterpret_cast<float4*>(&a_s[(co * C2H + row) * C2P + 4 * pg]) = o;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- conv3 (16->32, 3x3) + PReLU + heads.  thread = (4 px, 16 channels); halves are warp uniform.
+  const int pgi = tid & 127, half = tid >> 7;
+  const int row = pgi >> 3, pg = pgi & 7;
+  float hp[4][6];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) hp[i][j] = 0.f;
+#pragma unroll 1
+  for (int sub = 0; sub < 2; ++sub) {
+    const int c0 = (half * 2 + sub) * 8;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+    for (int ci = 0; ci < 16; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const float* ir = &a_s[(ci * C2H + row + ky) * C2P + 4 * pg];
+        const float4 i0 = *reinterpret_cast<const float4*>(ir);
+        const float2 i1 = *reinterpret_cast<const float2*>(ir + 4);
+        const float in[6] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y};
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float* wr = &w_s[W3 + ((ci * 3 + ky) * 3 + kx) * 32 + c0];
+          const float4 wa = *reinterpret_cast<const float4*>(wr);
+          const float4 wb = *reinterpret_cast<const float4*>(wr + 4);
+          const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+          for (int px = 0; px < 4; ++px)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(in[px + kx], w[j], acc[px][j]);
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = c0 + j;
+      const float bias = w_s[B3 + co], al = w_s[A3 + co];
+      const float4 ha = *reinterpret_cast<const float4*>(&w_s[WH + co * 8]);
+      const float2 hb = *reinterpret_cast<const float2*>(&w_s[WH + co * 8 + 4]);
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        const float v = prelu(acc[px][j] + bias, al);
+        hp[px][0] = fmaf(v, ha.x, hp[px][0]);
+        hp[px][1] = fmaf(v, ha.y, hp[px][1]);
+        hp[px][2] = fmaf(v, ha.z, hp[px][2]);
+        hp[px][3] = fmaf(v, ha.w, hp[px][3]);
+        hp[px][4] = fmaf(v, hb.x, hp[px][4]);
+        hp[px][5] = fmaf(v, hb.y, hp[px][5]);
+      }
+    }
+  }
+  // combine the two channel halves through shared memory (pooled conv1 tile is dead)
+  __syncthreads();
+  if (half == 1) {
+#pragma unroll
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) p1_s[(px * 6 + j) * 128 + pgi] = hp[px][j];
+  }
+  __syncthreads();
+  if (half == 0) {
+    const int oy = oy0 + row;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const int ox = ox0 + 4 * pg + px;
+      float h[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) h[j] = hp[px][j] + p1_s[(px * 6 + j) * 128 + pgi] + w_s[BH + j];
+      if (oy < L.oh && ox < L.ow) {
+        // softmax over (h0, h1), class 1 -- same form as ATen's softmax (subtract max, exp, normalise)
+        const float mx = fmaxf(h[0], h[1]);
+        const float e0 = expf(h[0] - mx), e1 = expf(h[1] - mx);
+        const float prob = __fdiv_rn(e1, e0 + e1);
+        const size_t cell = (size_t)oy * L.ow + ox;
+        if (L.prob) {
+          const size_t plane = (size_t)L.oh * L.ow;
+          L.prob[(size_t)b * plane + cell] = prob;
+          float* rg = L.reg + (size_t)b * 4 * plane + cell;
+          rg[0] = h[2]; rg[plane] = h[3]; rg[2 * plane] = h[4]; rg[3 * plane] = h[5];
+        }
+        if (L.cand && prob >= p.thr) {
+          // generateBoundingBox: q1 = floor((2*c + 1)/scale), q2 = floor((2*c + 12)/scale)  (fp32, true division)
+          const int slotbase = b * p.n_levels + lvl;
+          const int slot = atomicAdd(&L.cnt[slotbase], 1);
+          if (slot < p.cap) {
+            Cand cd;
+            cd.x1 = floorf(__fdiv_rn((float)(2 * ox + 1), L.scale));
+            cd.y1 = floorf(__fdiv_rn((float)(2 * oy + 1), L.scale));
+            cd.x2 = floorf(__fdiv_rn((float)(2 * ox + 12), L.scale));
+            cd.y2 = floorf(__fdiv_rn((float)(2 * oy + 12), L.scale));
+            cd.score = prob;
+            cd.r0 = h[2]; cd.r1 = h[3]; cd.r2 = h[4]; cd.r3 = h[5];
+            cd.key = (uint32_t)cell;
+            L.cand[(size_t)slotbase * p.cap + slot] = cd;
+          } else if (p.capflag) {
+            p.capflag->overflow = 1; p.capflag->stage = 1; p.capflag->frame = b;
+            p.capflag->count = slot + 1; p.capflag->capacity = p.cap;
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace pnet
+
+// upstream layouts -> packed shared-memory image
+int pnet_pack_weights(trl_ctx* c, const float* h, size_t len) {
+  using namespace pnet;
+  if (len != 6632) TRL_FAIL(c, TRL_E_INVALID, "pnet blob has %zu floats, expected 6632", len);
+  std::vector<float> pk(WTOTAL, 0.f);
+  const float* w1 = h;                   // [10][3][3][3]
+  const float* b1 = w1 + 270;
+  const float* a1 = b1 + 10;
+  const float* w2 = a1 + 10;             // [16][10][3][3]
+  const float* b2 = w2 + 1440;
+  const float* a2 = b2 + 16;
+  const float* w3 = a2 + 16;             // [32][16][3][3]
+  const float* b3 = w3 + 4608;
+  const float* a3 = b3 + 32;
+  const float* w41 = a3 + 32;            // [2][32]
+  const float* b41 = w41 + 64;
+  const float* w42 = b41 + 2;            // [4][32]
+  const float* b42 = w42 + 128;
+  for (int co = 0; co < 10; ++co)
+    for (int k = 0; k < 27; ++k) pk[W1 + k * 12 + co] = w1[co * 27 + k];
+  for (int co = 0; co < 10; ++co) { pk[B1 + co] = b1[co]; pk[A1 + co] = a1[co]; }
+  for (int co = 0; co < 16; ++co)
+    for (int k = 0; k < 90; ++k) pk[W2 + k * 16 + co] = w2[co * 90 + k];
+  for (int co = 0; co < 16; ++co) { pk[B2 + co] = b2[co]; pk[A2 + co] = a2[co]; }
+  for (int co = 0; co < 32; ++co)
+    for (int k = 0; k < 144; ++k) pk[W3 + k * 32 + co] = w3[co * 144 + k];
+  for (int co = 0; co < 32; ++co) { pk[B3 + co] = b3[co]; pk[A3 + co] = a3[co]; }
+  for (int ci = 0; ci < 32; ++ci) {
+    pk[WH + ci * 8 + 0] = w41[0 * 32 + ci];
+    pk[WH + ci * 8 + 1] = w41[1 * 32 + ci];
+    for (int j = 0; j < 4; ++j) pk[WH + ci * 8 + 2 + j] = w42[j * 32 + ci];
+  }
+  pk[BH + 0] = b41[0]; pk[BH + 1] = b41[1];
+  for (int j = 0; j < 4; ++j) pk[BH + 2 + j] = b42[j];
+  TRL_CUDA(c, cudaMalloc(&c->d_pnet_packed, WTOTAL * sizeof(float)));
+  TRL_CUDA(c, cudaMemcpy(c->d_pnet_packed, pk.data(), WTOTAL * sizeof(float), cudaMemcpyHostToDevice));
+  TRL_CUDA(c, cudaFuncSetAttribute(pnet::pnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  return TRL_OK;
+}
+
+int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float* d_prob, float* d_reg, cudaStream_t s) {
+  using namespace pnet;
+  Params p{};
+  p.n_levels = 1;
+  Level& L = p.lv[0];
+  L.in = d_in; L.hs = hs; L.ws = ws;
+  L.oh = (hs - 2 + 1) / 2 - 4; L.ow = (ws - 2 + 1) / 2 - 4;
+  if (L.oh <= 0 || L.ow <= 0) TRL_FAIL(c, TRL_E_INVALID, "pnet input %dx%d too small", hs, ws);
+  L.tiles_x = ceil_div(L.ow, TOX);
+  L.tiles = L.tiles_x * ceil_div(L.oh, TOY);
+  L.scale = 1.f; L.prob = d_prob; L.reg = d_reg; L.cand = nullptr; L.cnt = nullptr;
+  p.blk_start[0] = 0; p.blk_start[1] = L.tiles;
+  p.thr = 2.f; p.cap = 0; p.capflag = nullptr;
+  pnet_kernel<<<dim3(L.tiles, B), 256, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
+  TRL_LAUNCH_CHECK(c);
+  return TRL_OK;
+}
+
+int launch_pnet_candidates(trl_ctx* c, const float* d_pyr, int B, const PyramidGeom& g, float thr, Cand* d_cand,
+                           int* d_cnt, int cap, cudaStream_t s) {
+  using namespace pnet;
+  Params p{};
+  p.n_levels = g.n;
+  int blocks = 0;
+  for (int k = 0; k < g.n; ++k) {
+    Level& L = p.lv[k];
+    L.in = d_pyr + g.off[k] * B;
+    L.hs = g.hs[k]; L.ws = g.ws[k]; L.oh = g.oh[k]; L.ow = g.ow[k];
+    L.tiles_x = ceil_div(L.ow, TOX);
+    L.tiles = L.tiles_x * ceil_div(L.oh, TOY);
+    L.scale = g.scale_f[k];
+    L.prob = nullptr; L.reg = nullptr; L.cand = d_cand; L.cnt = d_cnt;
+    p.blk_start[k] = blocks;
+    blocks += L.tiles;
+  }
+  p.blk_start[g.n] = blocks;
+  p.thr = thr; p.cap = cap; p.capflag = c->d_cap;
+  if (blocks == 0 || B == 0) return TRL_OK;
+  pnet_kernel<<<dim3(blocks, B), 256, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
+  TRL_LAUNCH_CHECK(c);
+  return TRL_OK;
+}

@@ -1,0 +1,286 @@
+// K1 pyramid (area resample + normalise), K7 candidate crop-resample, K10 crop-align.
+// All three are HBM/L2-bound byte kernels with exact integer window arithmetic.
+//
+// Parity notes (checked on CPU against torch 2.11 / OpenCV 4.13, see tests/test_host_numerics.py):
+//  * F.interpolate(mode="area") == adaptive_avg_pool2d: window [floor(i*H/oh), ceil((i+1)*H/oh)),
+//    value = (sum / kh) / kw in fp32 (two divisions, in that order) -- bit exact with ATen.
+//  * (x - 127.5) * 0.0078125 : one rounding (the subtract), the multiply is exact.
+//  * cv2.resize(INTER_LINEAR, uint8): 11-bit fixed-point coefficients, horizontal pass in int32,
+//    vertical pass ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2; x coefficients are clamped at the
+//    borders, y rows are clipped instead (coefficients kept) -- bit exact with OpenCV.
+#include "common.cuh"
+
+// ----------------------------------------------------------------------------- shared device helpers
+
+// Sum of the u8 BGR window [y0,y1) x [x0,x1) of one frame, split over `grp` cooperating lanes
+// (lane `sub` takes columns x0+sub, x0+sub+grp, ...).  Integer sums are exact, so the split is free.
+__device__ __forceinline__ void window_sum(const uint8_t* __restrict__ frame, int W, int y0, int y1, int x0, int x1,
+                                           int sub, int grp, int& s0, int& s1, int& s2) {
+  s0 = s1 = s2 = 0;
+  for (int y = y0; y < y1; ++y) {
+    const uint8_t* row = frame + ((size_t)y * W) * 3;
+    for (int x = x0 + sub; x < x1; x += grp) {
+      const uint8_t* p = row + x * 3;
+      s0 += p[0];
+      s1 += p[1];
+      s2 += p[2];
+    }
+  }
+}
+
+__device__ __forceinline__ float area_norm(int s, int kh, int kw) {
+  float v = __fdiv_rn(__fdiv_rn((float)s, (float)kh), (float)kw);
+  return __fmul_rn(__fsub_rn(v, 127.5f), 0.0078125f);
+}
+
+// ----------------------------------------------------------------------------- K1 pyramid
+
+// grid.x = work blocks over all levels (PyrParams::blk_start), grid.y = frame.  256 threads.
+__global__ void __launch_bounds__(256) pyramid_kernel(const uint8_t* __restrict__ frames, int H, int W, PyrParams p,
+                                                     float* __restrict__ out) {
+  int lvl = 0;
+  while (lvl + 1 < p.n && (int)blockIdx.x >= p.blk_start[lvl + 1]) ++lvl;
+  const int hs = p.hs[lvl], ws = p.ws[lvl], grp = p.grp[lvl];
+  const int b = blockIdx.y;
+  const int px_per_blk = 256 / grp;
+  const int pix = ((int)blockIdx.x - p.blk_start[lvl]) * px_per_blk + (int)threadIdx.x / grp;
+  const int sub = threadIdx.x % grp;
+  const bool valid = pix < hs * ws;
+  int s0 = 0, s1 = 0, s2 = 0, kh = 1, kw = 1, oy = 0, ox = 0;
+  if (valid) {
+    oy = pix / ws;
+    ox = pix - oy * ws;
+    const int y0 = (int)(((long long)oy * H) / hs), y1 = (int)(((long long)(oy + 1) * H + hs - 1) / hs);
+    const int x0 = (int)(((long long)ox * W) / ws), x1 = (int)(((long long)(ox + 1) * W + ws - 1) / ws);
+    kh = y1 - y0;
+    kw = x1 - x0;
+    window_sum(frames + (size_t)b * H * W * 3, W, y0, y1, x0, x1, sub, grp, s0, s1, s2);
+  }
+  for (int o = grp >> 1; o > 0; o >>= 1) {   // grp divides 32: groups never straddle a warp
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (valid && sub == 0) {
+    float* o = out + p.off[lvl] + ((size_t)b * 3) * hs * ws + (size_t)oy * ws + ox;
+    o[0] = area_norm(s0, kh, kw);
+    o[(size_t)hs * ws] = area_norm(s1, kh, kw);
+    o[(size_t)2 * hs * ws] = area_norm(s2, kh, kw);
+  }
+}
+
+static int pick_group(int in_extent, int out_extent) {
+  int kw = (in_extent + out_extent - 1) / out_extent + 1;   // upper bound of the window width
+  int g = 1;
+  while (g < 32 && g * 2 <= kw) g <<= 1;
+  return g;
+}
+
+int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const PyramidGeom& g, float* d_out,
+                   cudaStream_t s) {
+  PyrParams p{};
+  p.n = g.n;
+  int blocks = 0;
+  for (int k = 0; k < g.n; ++k) {
+    p.hs[k] = g.hs[k];
+    p.ws[k] = g.ws[k];
+    p.off[k] = g.off[k] * B;
+    p.grp[k] = pick_group(W, g.ws[k]);
+    p.blk_start[k] = blocks;
+    blocks += ceil_div(g.hs[k] * g.ws[k], 256 / p.grp[k]);
+  }
+  p.blk_start[g.n] = blocks;
+  if (blocks == 0 || B == 0) return TRL_OK;
+  pyramid_kernel<<<dim3(blocks, B), 256, 0, s>>>(d_frames, H, W, p, d_out);
+  TRL_LAUNCH_CHECK(c);
+  return TRL_OK;
+}
+
+// ----------------------------------------------------------------------------- K7 crop-resample
+
+// One CTA per candidate slot.  grid = (n_max slots).  The crop is rows [y-1, ey) x cols [x-1, ex) (0-based),
+// clipped by pad() upstream, never zero padded.  Output float32 [slot][3][S][S].
+// d_count (optional) holds the live number of slots; slots >= *d_count exit.
+__global__ void __launch_bounds__(256) crop_resample_kernel(const uint8_t* __restrict__ frames, int H, int W,
+                                                           const int* __restrict__ pad4, const int* __restrict__ img,
+                                                           const int* __restrict__ d_count, int per_frame_cap,
+                                                           int S, float* __restrict__ out) {
+  const int slot = blockIdx.x;
+  int b, n_live;
+  if (per_frame_cap > 0) {          // slot = frame * cap + i, counts per frame
+    b = slot / per_frame_cap;
+    n_live = d_count[b];
+    if (slot - b * per_frame_cap >= n_live) return;
+  } else {
+    if (d_count && slot >= *d_count) return;
+    b = img[slot];
+  }
+  const int y = pad4[slot * 4 + 0], ey = pad4[slot * 4 + 1], x = pad4[slot * 4 + 2], ex = pad4[slot * 4 + 3];
+  float* o = out + (size_t)slot * 3 * S * S;
+  const int ch = ey - (y - 1), cw = ex - (x - 1);
+  if (ch <= 0 || cw <= 0) {   // degenerate: upstream skips such crops (detect_face.py stage 2/3 loop guard)
+    for (int i = threadIdx.x; i < 3 * S * S; i += blockDim.x) o[i] = 0.f;
+    return;
+  }
+  const uint8_t* frame = frames + (size_t)b * H * W * 3;
+  int grp = 1;
+  {
+    int kw = (cw + S - 1) / S + 1;
+    while (grp < 32 && grp * 2 <= kw) grp <<= 1;
+  }
+  const int sub = threadIdx.x % grp;
+  const int per_iter = blockDim.x / grp;
+  const int total = S * S;
+  const int iters = (total + per_iter - 1) / per_iter;
+  for (int it = 0; it < iters; ++it) {
+    const int pix = it * per_iter + (int)threadIdx.x / grp;
+    const bool valid = pix < total;
+    int s0 = 0, s1 = 0, s2 = 0, kh = 1, kw = 1;
+    if (valid) {
+      const int oy = pix / S, ox = pix - oy * S;
+      const int y0 = (oy * ch) / S, y1 = ((oy + 1) * ch + S - 1) / S;
+      const int x0 = (ox * cw) / S, x1 = ((ox + 1) * cw + S - 1) / S;
+      kh = y1 - y0;
+      kw = x1 - x0;
+      window_sum(frame, W, (y - 1) + y0, (y - 1) + y1, (x - 1) + x0, (x - 1) + x1, sub, grp, s0, s1, s2);
+    }
+    for (int d = grp >> 1; d > 0; d >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    if (valid && sub == 0) {
+      o[pix] = area_norm(s0, kh, kw);
+      o[total + pix] = area_norm(s1, kh, kw);
+      o[2 * total + pix] = area_norm(s2, kh, kw);
+    }
+  }
+}
+
+// d_count semantics: if per_frame_cap > 0, d_count is int[B] and slots are frame*cap+i; else a single int (or null).
+int launch_crop_resample_ex(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const int* d_pad, const int* d_img,
+                            const int* d_count, int per_frame_cap, int n_slots, int size, float* d_out, cudaStream_t s) {
+  if (n_slots <= 0) return TRL_OK;
+  crop_resample_kernel<<<n_slots, 256, 0, s>>>(d_frames, H, W, d_pad, d_img, d_count, per_frame_cap, size, d_out);
+  TRL_LAUNCH_CHECK(c);
+  return TRL_OK;
+}
+
+int launch_crop_resample(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const int* d_pad, const int* d_img,
+                         const int* d_count, int n_max, int size, float* d_out, cudaStream_t s) {
+  return launch_crop_resample_ex(c, d_frames, B, H, W, d_pad, d_img, d_count, 0, n_max, size, d_out, s);
+}
+
+// ----------------------------------------------------------------------------- K10 crop-align
+
+struct ResizeCoef {
+  int idx;     // source index (already clamped for x; raw for y)
+  int c0, c1;  // 11-bit fixed point coefficients
+};
+
+// OpenCV resize.cpp: fx = (float)((d + 0.5) * scale - 0.5); s = floor(fx); fx -= s; coefficients
+// saturate_cast<short>(v * 2048) (round half to even).  `clamp_coef`: the x direction resets fx at the borders.
+__device__ __forceinline__ ResizeCoef resize_coef(int d, int ssize, int dsize, bool clamp_coef) {
+  const double scale = 1.0 / ((double)dsize / (double)ssize);
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  int sidx = (int)floorf(f);
+  f = __fsub_rn(f, (float)sidx);
+  if (clamp_coef) {
+    if (sidx < 0) { f = 0.f; sidx = 0; }
+    if (sidx >= ssize - 1) { f = 0.f; sidx = ssize - 1; }
+  }
+  ResizeCoef r;
+  r.idx = sidx;
+  r.c1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  r.c0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  return r;
+}
+
+// One CTA per frame.  Selects boxes[0] (already largest-first), truncates toward zero, clamps
+// (server/model.py:49-53), and resamples the crop to SxS exactly like cv2.resize(INTER_LINEAR) on uint8.
+__global__ void __launch_bounds__(256) crop_align_kernel(const uint8_t* __restrict__ frames, int H, int W,
+                                                        const float* __restrict__ boxes, int box_stride,
+                                                        const int* __restrict__ nfaces, int S,
+                                                        int* __restrict__ box_int, uint8_t* __restrict__ valid,
+                                                        uint8_t* __restrict__ crops) {
+  const int b = blockIdx.x;
+  __shared__ int sb[4];
+  __shared__ int sok;
+  if (threadIdx.x == 0) {
+    int ok = 0;
+    int x1 = 0, y1 = 0, x2 = 0, y2 = 0;
+    if (nfaces[b] > 0) {
+      const float* bx = boxes + (size_t)b * box_stride;
+      x1 = (int)bx[0]; y1 = (int)bx[1]; x2 = (int)bx[2]; y2 = (int)bx[3];   // astype(int): toward zero
+      x1 = max(0, x1); y1 = max(0, y1); x2 = min(W, x2); y2 = min(H, y2);
+      ok = (x2 > x1 && y2 > y1) ? 1 : 0;
+    }
+    sb[0] = x1; sb[1] = y1; sb[2] = x2; sb[3] = y2;
+    sok = ok;
+    box_int[b * 4 + 0] = x1; box_int[b * 4 + 1] = y1; box_int[b * 4 + 2] = x2; box_int[b * 4 + 3] = y2;
+    valid[b] = (uint8_t)ok;
+  }
+  __syncthreads();
+  uint8_t* o = crops + (size_t)b * S * S * 3;
+  if (!sok) {
+    for (int i = threadIdx.x; i < S * S * 3; i += blockDim.x) o[i] = 0;
+    return;
+  }
+  const int x1 = sb[0], y1 = sb[1], sw = sb[2] - sb[0], sh = sb[3] - sb[1];
+  const uint8_t* src = frames + ((size_t)b * H * W + (size_t)y1 * W + x1) * 3;
+  for (int pix = threadIdx.x; pix < S * S; pix += blockDim.x) {
+    const int dy = pix / S, dx = pix - dy * S;
+    const ResizeCoef cx = resize_coef(dx, sw, S, true);
+    const ResizeCoef cy = resize_coef(dy, sh, S, false);
+    const int xa = cx.idx, xb = min(cx.idx + 1, sw - 1);
+    const int ya = min(max(cy.idx, 0), sh - 1), yb = min(max(cy.idx + 1, 0), sh - 1);
+    const uint8_t* ra = src + (size_t)ya * W * 3;
+    const uint8_t* rb = src + (size_t)yb * W * 3;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const int h0 = ra[xa * 3 + ch] * cx.c0 + ra[xb * 3 + ch] * cx.c1;
+      const int h1 = rb[xa * 3 + ch] * cx.c0 + rb[xb * 3 + ch] * cx.c1;
+      int v = (((cy.c0 * (h0 >> 4)) >> 16) + ((cy.c1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      v = min(max(v, 0), 255);
+      o[pix * 3 + ch] = (uint8_t)v;
+    }
+  }
+}
+
+int launch_crop_align(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
+                      const int* d_nfaces, int S, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops, cudaStream_t s) {
+  if (B <= 0) return TRL_OK;
+  crop_align_kernel<<<B, 256, 0, s>>>(d_frames, H, W, d_boxes, box_stride, d_nfaces, S, d_box_int, d_valid, d_crops);
+  TRL_LAUNCH_CHECK(c);
+  return TRL_OK;
+}
+
+// ----------------------------------------------------------------------------- pyramid geometry (host)
+
+// upstream detect_face: m = 12/minsize; scales m*factor^k while min(h,w)*m*factor^k >= 12, all in doubles;
+// level size (int(h*scale+1), int(w*scale+1)); P-Net map = ceil((hs-2)/2) - 4.
+int compute_geometry(const trl_config_t& cfg, int H, int W, PyramidGeom* g) {
+  g->n = 0;
+  g->px_total = 0;
+  if (H <= 0 || W <= 0 || cfg.min_face_size <= 0) return TRL_E_INVALID;
+  const double m = 12.0 / (double)cfg.min_face_size;
+  double minl = (double)(H < W ? H : W) * m;
+  double scale_i = m;
+  long long off = 0;
+  while (minl >= 12.0) {
+    if (g->n >= TRL_MAX_SCALES) return TRL_E_INVALID;
+    const int k = g->n++;
+    g->scale[k] = scale_i;
+    g->scale_f[k] = (float)scale_i;
+    g->hs[k] = (int)((double)H * scale_i + 1.0);
+    g->ws[k] = (int)((double)W * scale_i + 1.0);
+    g->oh[k] = (g->hs[k] - 2 + 1) / 2 - 4;
+    g->ow[k] = (g->ws[k] - 2 + 1) / 2 - 4;
+    g->off[k] = off;
+    off += 3LL * g->hs[k] * g->ws[k];
+    g->px_total += (long long)g->hs[k] * g->ws[k];
+    scale_i = scale_i * cfg.factor;
+    minl = minl * cfg.factor;
+  }
+  return TRL_OK;
+}

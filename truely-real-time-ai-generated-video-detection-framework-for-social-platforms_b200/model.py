@@ -1,0 +1,437 @@
+"""Host side of the drop-in: ``run(video_path_one, video_path_two) -> int`` (reference server/model.py:11-95).
+
+Same signature, guards, printed messages, side effects (annotated copy of every frame) and integer
+score as the reference.  What differs is where the per-frame work happens: processed frames
+(server/model.py:46) are batched, copied to the GPU from pinned memory and pushed through
+``libtruely_b200.so`` (MTCNN cascade -> crop-align -> FaceNet -> consecutive-embedding cosine), while
+this module keeps what the reference also does on the host: OpenCV decode / annotate / encode and the
+run-length state machine + score (server/model.py:62-70, 83-95), which is exact integer logic.
+
+PyTorch is used for device buffers, pinned staging buffers and the CUDA stream only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time
+from collections import deque
+from dataclasses import dataclass
+
+import cv2
+import numpy as np
+
+from . import _lib as L
+from . import weights as W
+
+THRESHOLD_FACE_SIMILARITY = 0.99      # server/model.py:16
+THRESHOLD_FRAMES_FOR_DEEPFAKE = 15    # server/model.py:17
+CROP_SIZE = 80                        # server/model.py:41
+
+
+def _vp(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+@dataclass
+class BatchResult:
+    """Per processed frame outputs of one batch (numpy, host)."""
+    nfaces: np.ndarray      # int32 [B]
+    box: np.ndarray         # int32 [B,4]  truncated + clamped box of the largest face (server/model.py:49-53)
+    valid: np.ndarray       # uint8 [B]    1 = a face was embedded
+    emb: np.ndarray         # float32 [B,512]
+    sim: np.ndarray         # float32 [B]  NaN where there was nothing to compare with
+    below: np.ndarray       # uint8 [B]    sim < threshold
+    has_sim: np.ndarray     # uint8 [B]
+    box_f: np.ndarray | None = None    # float32 [B,4] untruncated (detail mode only)
+    boxes: np.ndarray | None = None    # float32 [B,cap,5]            (detail mode only)
+    counts: np.ndarray | None = None   # int32 [B,4] candidates per stage (detail mode only)
+
+
+class Analyzer:
+    """Process-global GPU context: weights resident on the device, reusable across ``run`` calls
+    (the reference rebuilds both models on every call, server/model.py:18-19; behaviourally invisible)."""
+
+    def __init__(self, device: int = 0, facenet_impl: int | None = None, crop_size: int = CROP_SIZE,
+                 cand_cap_scale: int | None = None, cand_cap_frame: int | None = None, box_cap_frame: int | None = None):
+        import torch
+        self.torch = torch
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("truely_b200: no CUDA device visible; the hot path has no CPU fallback")
+        self.device = device
+        torch.cuda.set_device(device)
+        cfg = L.Config()
+        self.lib.trl_default_config(C.byref(cfg))
+        cfg.crop_size = crop_size
+        if facenet_impl is None:
+            facenet_impl = int(os.environ.get("TRUELY_FACENET_IMPL", "0"))
+        cfg.facenet_impl = facenet_impl
+        if cand_cap_scale:
+            cfg.cand_cap_scale = cand_cap_scale
+        if cand_cap_frame:
+            cfg.cand_cap_frame = cand_cap_frame
+        if box_cap_frame:
+            cfg.box_cap_frame = box_cap_frame
+        self.cfg = cfg
+        mt, self.mtcnn_source = W.load_mtcnn_state()
+        fn, self.facenet_source = W.load_facenet_state()
+        blobs = [W.pack_mtcnn(mt, "pnet"), W.pack_mtcnn(mt, "rnet"), W.pack_mtcnn(mt, "onet"), W.pack_facenet(fn)]
+        w = L.Weights()
+        fp = C.POINTER(C.c_float)
+        w.h_pnet, w.pnet_len = blobs[0].ctypes.data_as(fp), blobs[0].size
+        w.h_rnet, w.rnet_len = blobs[1].ctypes.data_as(fp), blobs[1].size
+        w.h_onet, w.onet_len = blobs[2].ctypes.data_as(fp), blobs[2].size
+        w.h_facenet, w.facenet_len = blobs[3].ctypes.data_as(fp), blobs[3].size
+        ctx = C.c_void_p()
+        rc = self.lib.trl_create(device, C.byref(w), C.byref(cfg), C.byref(ctx))
+        if rc != L.TRL_OK:
+            raise L.TrlError(rc, self.lib.trl_last_error(None).decode())
+        self.ctx = ctx
+        self.stream = torch.cuda.Stream(device=device)
+        self.box_cap = cfg.box_cap_frame
+        self.crop_size = crop_size
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.trl_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc):
+        if rc != L.TRL_OK:
+            raise L.TrlError(rc, self.lib.trl_last_error(self.ctx).decode())
+
+    def check_capacity(self):
+        """Call after a stream synchronise: raises TRL_E_CAPACITY if a candidate list overflowed."""
+        detail = (C.c_int * 4)()
+        self._check(self.lib.trl_check_capacity(self.ctx, detail))
+
+    def launch_count(self) -> int:
+        return int(self.lib.trl_launch_count(self.ctx))
+
+    def _sptr(self):
+        return C.c_void_p(self.stream.cuda_stream)
+
+    def alloc_outputs(self, B):
+        t, dev = self.torch, f"cuda:{self.device}"
+        return dict(
+            nfaces=t.empty(B, dtype=t.int32, device=dev), box=t.empty((B, 4), dtype=t.int32, device=dev),
+            valid=t.empty(B, dtype=t.uint8, device=dev), emb=t.empty((B, L.EMB_DIM), dtype=t.float32, device=dev),
+            sim=t.empty(B, dtype=t.float32, device=dev), below=t.empty(B, dtype=t.uint8, device=dev),
+            has_sim=t.empty(B, dtype=t.uint8, device=dev),
+            last_emb=t.zeros(L.EMB_DIM, dtype=t.float32, device=dev), last_valid=t.zeros(1, dtype=t.uint8, device=dev))
+
+    # ------------------------------------------------------------------ device-resident API
+    def process_device(self, d_frames, out, halo=None, thr=THRESHOLD_FACE_SIMILARITY):
+        """One fused batch on device tensors (uint8 [B,H,W,3]); asynchronous on ``self.stream``.
+        ``halo`` = (emb float32[512], valid uint8[1]) device tensors of the preceding range, or None."""
+        B, H, Wd, _ = d_frames.shape
+        he, hv = (halo if halo is not None else (None, None))
+        self._check(self.lib.trl_process(
+            self.ctx, _vp(d_frames), B, H, Wd, _vp(he), _vp(hv), thr, _vp(out["box"]), _vp(out["valid"]),
+            _vp(out["emb"]), _vp(out["sim"]), _vp(out["below"]), _vp(out["has_sim"]), _vp(out["nfaces"]),
+            _vp(out["last_emb"]), _vp(out["last_valid"]), self._sptr()))
+
+    # ------------------------------------------------------------------ host-buffer API
+    def process_frames(self, frames: np.ndarray, halo=None, detail: bool = True,
+                       thr: float = THRESHOLD_FACE_SIMILARITY) -> BatchResult:
+        """frames: uint8 [B,H,W,3] BGR on the host.  Synchronous convenience wrapper (tests, smoke)."""
+        t = self.torch
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        B, H, Wd, _ = frames.shape
+        dev = f"cuda:{self.device}"
+        with t.cuda.stream(self.stream):
+            d_frames = t.from_numpy(frames).pin_memory().to(dev, non_blocking=True)
+            out = self.alloc_outputs(B)
+            he = hv = None
+            if halo is not None:
+                he = t.from_numpy(np.ascontiguousarray(halo, np.float32)).to(dev)
+                hv = t.ones(1, dtype=t.uint8, device=dev)
+            boxes = counts = None
+            if detail:
+                boxes = t.zeros((B, self.box_cap, 5), dtype=t.float32, device=dev)
+                counts = t.zeros((B, 4), dtype=t.int32, device=dev)
+                crops = t.empty((B, self.crop_size, self.crop_size, 3), dtype=t.uint8, device=dev)
+                self._check(self.lib.trl_detect(self.ctx, _vp(d_frames), B, H, Wd, _vp(out["nfaces"]), _vp(boxes),
+                                                _vp(counts), self._sptr()))
+                self._check(self.lib.trl_crop_align(self.ctx, _vp(d_frames), B, H, Wd, _vp(boxes), self.box_cap * 5,
+                                                    _vp(out["nfaces"]), _vp(out["box"]), _vp(out["valid"]), _vp(crops),
+                                                    self._sptr()))
+                self._check(self.lib.trl_facenet(self.ctx, _vp(crops), B, self.crop_size, _vp(out["emb"]), self._sptr()))
+                self._check(self.lib.trl_consistency(self.ctx, _vp(out["emb"]), _vp(out["valid"]), B, _vp(he), _vp(hv), thr,
+                                                     _vp(out["sim"]), _vp(out["below"]), _vp(out["has_sim"]),
+                                                     _vp(out["last_emb"]), _vp(out["last_valid"]), self._sptr()))
+            else:
+                self.process_device(d_frames, out, (he, hv) if halo is not None else None, thr)
+        self.stream.synchronize()
+        self.check_capacity()
+        res = BatchResult(nfaces=out["nfaces"].cpu().numpy(), box=out["box"].cpu().numpy(), valid=out["valid"].cpu().numpy(),
+                          emb=out["emb"].cpu().numpy(), sim=out["sim"].cpu().numpy(), below=out["below"].cpu().numpy(),
+                          has_sim=out["has_sim"].cpu().numpy())
+        if detail:
+            res.boxes = boxes.cpu().numpy()
+            res.box_f = res.boxes[:, 0, :4].copy()
+            res.counts = counts.cpu().numpy()
+        return res
+
+
+_ANALYZER = None
+
+
+def get_analyzer() -> Analyzer:
+    global _ANALYZER
+    if _ANALYZER is None:
+        _ANALYZER = Analyzer(device=int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("TRUELY_USE_LOCAL_RANK") else 0)
+    return _ANALYZER
+
+
+# ---------------------------------------------------------------------- K13: run-length state machine + score (host)
+
+class RunLength:
+    """server/model.py:37-39, 62-70: deepfake_count / deep_fake_frame_count, exact integer logic."""
+
+    def __init__(self):
+        self.deepfake_count = 0
+        self.deep_fake_frame_count = 0
+
+    def step(self, below: bool) -> bool:
+        """Feed one compared frame; returns True if the frame is flagged (counted)."""
+        if below:
+            self.deepfake_count += 1
+        else:
+            self.deepfake_count = 0
+        if self.deepfake_count > THRESHOLD_FRAMES_FOR_DEEPFAKE:
+            self.deep_fake_frame_count += 1
+            return True
+        return False
+
+
+def final_score(deep_fake_frame_count: int, deepfake_count: int, frame_count: int, fps: int, stride: int) -> int:
+    """server/model.py:83-95."""
+    if frame_count == 0:
+        return 0
+    total_processed_frames = sum(1 for i in range(frame_count) if i % stride == 0)
+    if total_processed_frames == 0:
+        return 0
+    deepfake_percentage = (deep_fake_frame_count / total_processed_frames) * 100
+    confidence_factor = min(deepfake_percentage * (deepfake_count / THRESHOLD_FRAMES_FOR_DEEPFAKE), 100)
+    if frame_count > fps * 30:
+        weighted_score = min(deepfake_percentage + confidence_factor * 0.5, 100)
+    else:
+        weighted_score = min(deepfake_percentage + confidence_factor * 0.3, 100)
+    return max(0, min(100, int(weighted_score)))
+
+
+def frame_stride(fps: int) -> int:
+    return max(1, int(fps / 7))   # server/model.py:40
+
+
+# ---------------------------------------------------------------------- streaming driver
+
+@dataclass
+class Trace:
+    score: int = 0
+    frame_count: int = 0
+    stride: int = 1
+    flagged_count: int = 0
+    final_run: int = 0
+    frame_index: list = None
+    valid: list = None
+    box: list = None
+    sim: list = None
+    flagged: list = None
+    nfaces: list = None
+    emb: list = None
+    timings: dict = None
+
+
+class _Chunk:
+    __slots__ = ("frames", "proc_pos", "proc_idx", "pinned", "out", "host", "event", "n")
+
+
+def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, analyzer: Analyzer | None = None,
+                   chunk: int | None = None, keep_emb: bool = False) -> Trace:
+    """The hot loop of server/model.py:42-77 as a two-deep software pipeline.
+
+    While the GPU works on chunk k (H2D copy + trl_process, all asynchronous), the host decodes chunk k+1;
+    when chunk k's small result arrays are back, its frames are annotated and written in order.
+    ``frame_iter`` yields BGR uint8 frames; ``writer`` (optional) is a cv2.VideoWriter.
+    """
+    an = analyzer or get_analyzer()
+    t = an.torch
+    stride = frame_stride(fps)
+    if chunk is None:
+        chunk = max(4, min(64, int(96e6 // max(1, width * height * 3))))   # ~96 MB of pinned frames per chunk
+    tr = Trace(stride=stride, frame_index=[], valid=[], box=[], sim=[], flagged=[], nfaces=[], emb=[] if keep_emb else None,
+               timings=dict(decode_s=0.0, submit_s=0.0, finish_s=0.0))
+    rl = RunLength()
+    dev = f"cuda:{an.device}"
+    pending = deque()
+    free_bufs = []
+    halo = None
+    frame_count = 0
+
+    def new_chunk():
+        c = _Chunk()
+        c.frames, c.proc_pos, c.proc_idx, c.n = [], [], [], 0
+        if free_bufs:
+            c.pinned, c.out, c.host = free_bufs.pop()
+        else:
+            c.pinned = t.empty((chunk, height, width, 3), dtype=t.uint8, pin_memory=True)
+            c.out = an.alloc_outputs(chunk)
+            c.out["frames"] = t.empty((chunk, height, width, 3), dtype=t.uint8, device=dev)
+            c.host = {k: t.empty(c.out[k].shape, dtype=c.out[k].dtype, pin_memory=True)
+                      for k in ("nfaces", "box", "valid", "sim", "below", "has_sim")}
+            if keep_emb:
+                c.host["emb"] = t.empty(c.out["emb"].shape, dtype=t.float32, pin_memory=True)
+        return c
+
+    def submit(c):
+        nonlocal halo
+        t0 = time.perf_counter()
+        n = c.n
+        if n > 0:
+            with t.cuda.stream(an.stream):
+                d_frames = c.out["frames"][:n]
+                d_frames.copy_(c.pinned[:n], non_blocking=True)
+                view = {k: (v[:n] if k not in ("last_emb", "last_valid", "frames") else v) for k, v in c.out.items()}
+                an.process_device(d_frames, view, halo)
+                halo = (c.out["last_emb"], c.out["last_valid"])
+                for k, h in c.host.items():
+                    h[:n].copy_(c.out[k][:n], non_blocking=True)
+                c.event = t.cuda.Event()
+                c.event.record(an.stream)
+        else:
+            c.event = None
+        pending.append(c)
+        tr.timings["submit_s"] += time.perf_counter() - t0
+
+    def finish(c):
+        t0 = time.perf_counter()
+        if c.event is not None:
+            c.event.synchronize()
+            an.check_capacity()
+        host = {k: v[:c.n].numpy() for k, v in c.host.items()}
+        k = 0
+        for pos, frame in enumerate(c.frames):
+            if k < c.n and c.proc_pos[k] == pos:
+                fidx = c.proc_idx[k]
+                valid = bool(host["valid"][k])
+                box = host["box"][k]
+                flagged = False
+                if valid and host["has_sim"][k]:
+                    flagged = rl.step(bool(host["below"][k]))
+                    if writer is not None:                       # server/model.py:66-74
+                        if flagged:
+                            cv2.rectangle(frame, (int(box[0]), int(box[1])), (int(box[2]), int(box[3])), (0, 0, 255), 2)
+                            cv2.putText(frame, f"AI Detected - Frame {fidx}", (10, 30), cv2.FONT_HERSHEY_SIMPLEX, 1,
+                                        (0, 0, 255), 2, cv2.LINE_AA)
+                        else:
+                            cv2.rectangle(frame, (int(box[0]), int(box[1])), (int(box[2]), int(box[3])), (0, 255, 0), 2)
+                            cv2.putText(frame, "Real Frame", (int(box[0]), int(box[1]) - 10), cv2.FONT_HERSHEY_SIMPLEX, 0.5,
+                                        (0, 255, 0), 2, cv2.LINE_AA)
+                tr.frame_index.append(fidx)
+                tr.valid.append(valid)
+                tr.box.append(box.copy())
+                tr.sim.append(float(host["sim"][k]) if host["has_sim"][k] else None)
+                tr.flagged.append(flagged)
+                tr.nfaces.append(int(host["nfaces"][k]))
+                if keep_emb:
+                    tr.emb.append(host["emb"][k].copy())
+                k += 1
+            if writer is not None:
+                writer.write(frame)                               # server/model.py:77: every frame, in order
+        c.frames = []
+        free_bufs.append((c.pinned, c.out, c.host))
+        tr.timings["finish_s"] += time.perf_counter() - t0
+
+    cur = new_chunk()
+    t_dec = time.perf_counter()
+    for frame in frame_iter:
+        tr.timings["decode_s"] += time.perf_counter() - t_dec
+        if frame_count % stride == 0:                             # server/model.py:46
+            cur.pinned[cur.n].copy_(t.from_numpy(frame))
+            cur.proc_pos.append(len(cur.frames))
+            cur.proc_idx.append(frame_count)
+            cur.n += 1
+        if writer is not None:
+            cur.frames.append(frame)
+        elif frame_count % stride == 0:
+            cur.frames.append(None)
+        frame_count += 1
+        if cur.n == chunk:
+            submit(cur)
+            while len(pending) > 1:
+                finish(pending.popleft())
+            cur = new_chunk()
+        t_dec = time.perf_counter()
+    if cur.n > 0 or cur.frames:
+        submit(cur)
+    while pending:
+        finish(pending.popleft())
+    tr.frame_count = frame_count
+    tr.flagged_count = rl.deep_fake_frame_count
+    tr.final_run = rl.deepfake_count
+    tr.score = final_score(rl.deep_fake_frame_count, rl.deepfake_count, frame_count, fps, stride)
+    return tr
+
+
+def _video_frames(cap):
+    while cap.isOpened():
+        ret, frame = cap.read()
+        if not ret:
+            break
+        yield frame
+
+
+def _open_writer(path, fps, width, height):
+    """Reference: fourcc 'H264' (server/model.py:35-36).  OpenCV wheels without an H.264 encoder cannot open that
+    writer; server.py rejects a missing/empty output file, so fall back to 'mp4v' and say so."""
+    out = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"H264"), fps, (width, height))
+    if not out.isOpened():
+        out.release()
+        print("Note: this OpenCV build has no H264 encoder; writing the annotated video with fourcc 'mp4v' instead")
+        out = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), fps, (width, height))
+    return out
+
+
+def run_trace(video_path_one: str, video_path_two: str | None, analyzer: Analyzer | None = None,
+              keep_emb: bool = False) -> Trace:
+    """``run`` plus the per-frame trace (superset used by the tests).  ``video_path_two=None`` skips the writer."""
+    start_time = time.time()
+    if not os.path.exists(video_path_one) or os.path.getsize(video_path_one) == 0:
+        print(f"Error: Input video file {video_path_one} doesn't exist or is empty")
+        return Trace()
+    cap = cv2.VideoCapture(video_path_one)
+    if not cap.isOpened():
+        print(f"Error: OpenCV couldn't open video file {video_path_one}")
+        return Trace()
+    fps = int(cap.get(cv2.CAP_PROP_FPS))
+    width = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH))
+    height = int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+    if width <= 0 or height <= 0 or fps <= 0:
+        print(f"Error: Invalid video properties: width={width}, height={height}, fps={fps}")
+        cap.release()
+        return Trace()
+    out = _open_writer(video_path_two, fps, width, height) if video_path_two is not None else None
+    tr = analyze_stream(_video_frames(cap), fps, width, height, writer=out, analyzer=analyzer, keep_emb=keep_emb)
+    execution_time = time.time() - start_time
+    print(f"Total Execution Time: {execution_time} seconds")
+    cap.release()
+    if out is not None:
+        out.release()
+    if tr.frame_count == 0:
+        print("Error: No frames were processed")
+        tr.score = 0
+    return tr
+
+
+def run(video_path_one: str, video_path_two: str) -> int:
+    """Drop-in for reference server/model.py::run (same signature, return value and side effects)."""
+    return run_trace(video_path_one, video_path_two).score
