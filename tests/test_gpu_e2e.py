@@ -1,0 +1,205 @@
+"""GPU: the cascade and the whole drop-in against the oracle / committed goldens (BASELINE.json tolerances:
+same face count per frame, box IoU >= 0.95, embedding cosine >= 0.999, identical flagged set outside a 1e-3 band)."""
+import importlib.util
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle.reference_run import reference_run_frames
+from truely_b200 import model as M
+from truely_b200.synth import SyntheticClip
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _mg():
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _match_boxes(got, ref):
+    """every reference box has a distinct detected box with IoU >= 0.95"""
+    used = set()
+    for r in ref:
+        best, bi = 0.0, -1
+        for j, g in enumerate(got):
+            if j in used:
+                continue
+            v = H.box_iou(r, g)
+            if v > best:
+                best, bi = v, j
+        assert best >= 0.95, f"reference box {r} best IoU {best}"
+        used.add(bi)
+
+
+def test_detect_matches_oracle_per_stage(analyzer):
+    """Face count, boxes and the candidate counts entering R-Net / O-Net, single and multi face, two resolutions."""
+    mt = H.oracle_mtcnn()
+    cases = [SyntheticClip(360, 640, 30, 64, n_faces=(1, 1), face_h=(90.0, 130.0), jitter=0.5, seed=3),
+             SyntheticClip(540, 960, 60, 64, n_faces=(3, 3), face_h=(60.0, 160.0), seed=5),
+             SyntheticClip(240, 320, 30, 64, n_faces=(0, 0), seed=8)]          # no face at all
+    for clip in cases:
+        frames = [clip.frame(i) for i in (0, 7, 19, 33)]
+        res = analyzer.process_frames(np.stack(frames), detail=True)
+        for k, f in enumerate(frames):
+            tr = {}
+            boxes, probs = mt.detect(f, trace=tr)
+            n_ref = 0 if boxes is None else len(boxes)
+            assert res.nfaces[k] == n_ref, f"frame {k}: {res.nfaces[k]} faces vs oracle {n_ref}"
+            assert res.counts[k, 1] == len(tr["s1_boxes"]), "R-Net input count"
+            assert res.counts[k, 2] == len(tr["s2_boxes"]), "O-Net input count"
+            if n_ref:
+                _match_boxes(res.boxes[k, :n_ref, :4], boxes)
+                # largest-first order and scores
+                assert H.box_iou(res.boxes[k, 0, :4], boxes[0]) >= 0.95
+                assert abs(res.boxes[k, 0, 4] - probs[0]) < 1e-3
+
+
+def test_detect_stress_low_thresholds(analyzer):
+    """Hundreds of candidates per frame (thresholds lowered in both paths): exercises NMS blocks, ties and capacity."""
+    import copy
+    mt2 = copy.deepcopy(H.oracle_mtcnn())
+    mt2.thresholds = [0.3, 0.4, 0.5]
+    a3 = _analyzer_with_thresholds((0.3, 0.4, 0.5))
+    clip = SyntheticClip(540, 960, 60, 64, n_faces=(4, 4), face_h=(50.0, 200.0), seed=15)
+    frames = [clip.frame(i) for i in (2, 30)]
+    res = a3.process_frames(np.stack(frames), detail=True)
+    for k, f in enumerate(frames):
+        tr = {}
+        boxes, _ = mt2.detect(f, trace=tr)
+        n_ref = 0 if boxes is None else len(boxes)
+        assert res.counts[k, 1] == len(tr["s1_boxes"])
+        assert res.counts[k, 2] == len(tr["s2_boxes"])
+        assert res.nfaces[k] == n_ref
+        if n_ref:
+            _match_boxes(res.boxes[k, :n_ref, :4], boxes)
+    a3.close()
+
+
+def _analyzer_with_thresholds(thr):
+    """Analyzer whose trl_config_t carries other MTCNN thresholds (the reference's are fixed literals)."""
+    import ctypes as C
+    from truely_b200 import _lib as L
+    from truely_b200 import weights as W
+    from truely_b200.model import Analyzer
+    an = Analyzer.__new__(Analyzer)
+    an.torch = torch
+    an.lib = L.load()
+    an.device = 0
+    cfg = L.Config()
+    an.lib.trl_default_config(C.byref(cfg))
+    cfg.thresholds[0], cfg.thresholds[1], cfg.thresholds[2] = thr
+    cfg.facenet_impl = 1
+    mt, _ = W.load_mtcnn_state()
+    fn, _ = W.load_facenet_state()
+    blobs = [W.pack_mtcnn(mt, "pnet"), W.pack_mtcnn(mt, "rnet"), W.pack_mtcnn(mt, "onet"), W.pack_facenet(fn)]
+    w = L.Weights()
+    fp = C.POINTER(C.c_float)
+    w.h_pnet, w.pnet_len = blobs[0].ctypes.data_as(fp), blobs[0].size
+    w.h_rnet, w.rnet_len = blobs[1].ctypes.data_as(fp), blobs[1].size
+    w.h_onet, w.onet_len = blobs[2].ctypes.data_as(fp), blobs[2].size
+    w.h_facenet, w.facenet_len = blobs[3].ctypes.data_as(fp), blobs[3].size
+    ctx = C.c_void_p()
+    rc = an.lib.trl_create(0, C.byref(w), C.byref(cfg), C.byref(ctx))
+    assert rc == 0, an.lib.trl_last_error(None)
+    an.ctx, an.cfg = ctx, cfg
+    an.stream = torch.cuda.Stream(device=0)
+    an.box_cap, an.crop_size = cfg.box_cap_frame, 80
+    return an
+
+
+def test_capacity_overflow_is_reported_not_truncated():
+    import ctypes as C
+    from truely_b200 import _lib as L
+    from truely_b200.model import Analyzer
+    an = Analyzer(device=0, facenet_impl=1, cand_cap_scale=2, cand_cap_frame=2, box_cap_frame=2)
+    clip = SyntheticClip(540, 960, 60, 8, n_faces=(4, 4), face_h=(50.0, 200.0), seed=15)
+    with pytest.raises(L.TrlError) as e:
+        an.process_frames(np.stack([clip.frame(0)]), detail=True)
+    assert e.value.code == L.TRL_E_CAPACITY
+    an.close()
+
+
+def test_golden_run_flagged_set_and_score(analyzer):
+    """The whole hot loop on the golden clip vs the committed oracle trace."""
+    g = np.load(os.path.join(GOLD, "reference_run.npz"))
+    clip = _mg().golden_clip()
+    tr = M.analyze_stream(iter(clip), clip.fps, clip.width, clip.height, writer=None, analyzer=analyzer, chunk=16, keep_emb=True)
+    assert tr.frame_count == int(g["frame_count"]) and tr.frame_index == list(g["frame_index"])
+    assert tr.nfaces == list(g["n_faces"])
+    assert tr.valid == [bool(v) for v in g["embedded"]]
+    near = []
+    for k in range(len(tr.frame_index)):
+        if not tr.valid[k]:
+            continue
+        assert np.abs(tr.box[k] - g["box"][k]).max() <= 1, f"frame {k} box"
+        # the crop may differ by one pixel when a float box lands on the other side of an integer; cosine bar still holds
+        assert H.cosine(tr.emb[k], g["emb"][k]) >= 0.999, f"frame {k} embedding"
+        if not np.isnan(g["sim"][k]):
+            assert abs(tr.sim[k] - g["sim"][k]) < 1e-3, f"frame {k} sim {tr.sim[k]} vs {g['sim'][k]}"
+            if abs(g["sim"][k] - 0.99) < 1e-3:
+                near.append(k)
+    if not near:
+        assert tr.flagged == [bool(v) for v in g["flagged"]]
+        assert tr.flagged_count == int(g["flagged_count"]) and tr.final_run == int(g["final_run"])
+        assert tr.score == int(g["score"])
+
+
+def test_run_dropin_on_encoded_clip_matches_oracle(analyzer, tmp_path):
+    """run(video_path_one, video_path_two) on an mp4 (decode path) vs the oracle loop on the same decoded frames."""
+    clip = SyntheticClip(240, 320, 30, 140, n_faces=(1, 1), face_h=(70.0, 110.0), jitter=1.6, seed=31)
+    src = str(tmp_path / "clip.mp4")
+    wr = cv2.VideoWriter(src, cv2.VideoWriter_fourcc(*"mp4v"), 30, (320, 240))
+    assert wr.isOpened()
+    for f in clip:
+        wr.write(f)
+    wr.release()
+    dst = str(tmp_path / "clip_output.mp4")
+    M._ANALYZER = analyzer
+    score = M.run(src, dst)
+    assert isinstance(score, int) and 0 <= score <= 100
+    assert os.path.exists(dst) and os.path.getsize(dst) > 0            # server/server.py:612-627 rejects a missing file
+    cap = cv2.VideoCapture(dst)
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 140
+    cap.release()
+    # oracle on the same decoded frames
+    cap = cv2.VideoCapture(src)
+    frames = []
+    while True:
+        ok_, f = cap.read()
+        if not ok_:
+            break
+        frames.append(f)
+    cap.release()
+    ref = reference_run_frames(iter([f.copy() for f in frames]), 30, 320, 240, H.oracle_mtcnn(), H.oracle_facenet())
+    tr = M.analyze_stream(iter(frames), 30, 320, 240, analyzer=analyzer, keep_emb=True)
+    assert tr.frame_count == ref.frame_count
+    band = False
+    for k, f in enumerate(ref.frames):
+        assert tr.nfaces[k] == f.n_faces
+        assert tr.valid[k] == f.embedded
+        if f.embedded:
+            assert H.cosine(tr.emb[k], f.emb) >= 0.999
+            if f.sim is not None:
+                assert abs(tr.sim[k] - f.sim) < 1e-3
+                band |= abs(f.sim - 0.99) < 1e-3
+    if not band:
+        assert tr.flagged == [f.flagged for f in ref.frames]
+        assert tr.score == ref.score == score
+
+
+def test_fused_process_equals_staged_calls(analyzer):
+    clip = SyntheticClip(360, 640, 30, 64, n_faces=(1, 1), face_h=(90.0, 130.0), jitter=1.0, seed=77)
+    frames = np.stack([clip.frame(i) for i in range(0, 40, 4)])
+    a = analyzer.process_frames(frames, detail=True)
+    b = analyzer.process_frames(frames, detail=False)
+    assert np.array_equal(a.nfaces, b.nfaces) and np.array_equal(a.box, b.box) and np.array_equal(a.valid, b.valid)
+    assert np.array_equal(a.emb, b.emb) and np.array_equal(a.below, b.below)
+    assert np.allclose(a.sim, b.sim, equal_nan=True)
