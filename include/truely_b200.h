@@ -37,6 +37,7 @@ extern "C" {
 #define TRL_E_STATE (-5)     /* call order / missing weights */
 
 #define TRL_EMB_DIM 512
+#define TRL_NUM_STAGES 13
 #define TRL_MAX_SCALES 24
 
 typedef struct trl_ctx trl_ctx_t;
@@ -144,6 +145,14 @@ int trl_process(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, co
 /* After the stream has been synchronised by the caller: TRL_E_CAPACITY if any candidate buffer overflowed
  * since the last check (h_detail, optional int32[4]: which stage, frame, count, capacity). */
 int trl_check_capacity(trl_ctx_t* ctx, int* h_detail);
+
+/* Per-stage device timing of trl_process (measurement only; off by default).  With profiling on, CUDA events are
+ * recorded on the launching stream around each stage; trl_read_stage_times (after the caller synchronised the
+ * stream) returns in h_ms[TRL_NUM_STAGES] the summed milliseconds per stage since the last read, and as return
+ * value the number of trl_process calls accumulated.  trl_stage_name gives the stage labels. */
+int trl_set_profiling(trl_ctx_t* ctx, int on);
+int trl_read_stage_times(trl_ctx_t* ctx, float* h_ms);
+int trl_stage_name(int stage, char* buf, int len);
 
 /* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */
 long long trl_launch_count(const trl_ctx_t* ctx);

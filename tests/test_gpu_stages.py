@@ -271,10 +271,11 @@ def test_facenet_umma_layers_match_simt(analyzer, analyzer_simt):
         assert lib.trl_debug_facenet_output(analyzer_simt.ctx, idx, n, b.ctypes.data_as(C.c_void_p)) == 0
         fa = torch.from_numpy(a.view(np.int16)).view(torch.bfloat16).float()
         fb = torch.from_numpy(b.view(np.int16)).view(torch.bfloat16).float()
-        err = (fa - fb).abs().max().item()
-        scale = fb.abs().max().item() + 1e-6
+        # (buffers are re-used by later blocks, so for repeated blocks this compares the last writer's output)
+        err = (fa - fb).norm().item()
+        scale = fb.norm().item() + 1e-6
         worst.append((err / scale, name.value.decode(), err, scale))
-    bad = [w for w in worst if w[0] > 0.03]
+    bad = [w for w in worst if w[0] > 0.02]
     assert not bad, f"layers deviating: {bad[:8]}"
 
 

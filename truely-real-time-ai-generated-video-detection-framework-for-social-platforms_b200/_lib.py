@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libtruely_b200.so")
 TRL_OK, TRL_E_INVALID, TRL_E_CUDA, TRL_E_CAPACITY, TRL_E_NOMEM, TRL_E_STATE = 0, -1, -2, -3, -4, -5
 EMB_DIM = 512
 MAX_SCALES = 24
+NUM_STAGES = 13
 
 
 class TrlError(RuntimeError):
@@ -54,6 +55,9 @@ SIGNATURES = {
     "trl_process": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trl_check_capacity": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "trl_launch_count": (C.c_longlong, [_P]),
+    "trl_set_profiling": (C.c_int, [_P, C.c_int]),
+    "trl_read_stage_times": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "trl_stage_name": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
 }
 # validation-only exports (not part of the public header)
 DEBUG_SIGNATURES = {

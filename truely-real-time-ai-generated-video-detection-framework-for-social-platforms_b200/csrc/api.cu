@@ -5,6 +5,29 @@
 
 static thread_local std::string g_create_err;
 
+// ---- optional per-stage timing (trl_set_profiling): CUDA events recorded on the launching stream around each stage
+static const char* kStageNames[TRL_NUM_STAGES] = {"pyramid", "pnet", "nms_scale", "nms_frame", "crop24", "rnet", "nms_rnet",
+                                                  "crop48", "onet", "nms_final", "crop_align", "facenet", "consistency"};
+struct StageTimer {
+  trl_ctx* c;
+  cudaStream_t s;
+  std::vector<cudaEvent_t>* ev;
+  StageTimer(trl_ctx* c_, cudaStream_t s_) : c(c_), s(s_), ev(nullptr) {
+    if (c->profiling) {
+      c->prof_events.emplace_back();
+      ev = &c->prof_events.back();
+      mark();
+    }
+  }
+  void mark() {
+    if (!ev) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    ev->push_back(e);
+  }
+};
+
 extern "C" {
 
 void trl_default_config(trl_config_t* cfg) {
@@ -179,7 +202,7 @@ static int ensure_workspace(trl_ctx* c, int B, int H, int W) {
 }
 
 static int detect_impl(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, int* d_nfaces, float* d_boxes, int* d_counts,
-                       cudaStream_t s) {
+                       cudaStream_t s, StageTimer* tm) {
   if (!c->d_pnet_packed || !c->d_rnet || !c->d_onet) TRL_FAIL(c, TRL_E_STATE, "MTCNN weights not loaded");
   int rc = ensure_workspace(c, B, H, W);
   if (rc != TRL_OK) return rc;
@@ -191,8 +214,11 @@ static int detect_impl(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W,
   int* cnt3 = cnt2 + B;
   int* cnt4 = cnt3 + B;
   TRL_CUDA(c, cudaMemsetAsync(cnt1, 0, (size_t)B * (g.n + 3) * sizeof(int), s));
+  if (tm) tm->mark();   // (memset belongs to nobody: restart the clock)
   if ((rc = launch_pyramid(c, d_frames, B, H, W, g, c->d_pyr, s)) != TRL_OK) return rc;
+  if (tm) tm->mark();
   if ((rc = launch_pnet_candidates(c, c->d_pyr, B, g, c->cfg.thresholds[0], c->d_cand1, cnt1, c1, s)) != TRL_OK) return rc;
+  if (tm) tm->mark();
 
   nms::StageParams p{};
   p.W = W; p.H = H; p.capflag = c->d_cap;
@@ -200,24 +226,32 @@ static int detect_impl(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W,
   p.n_levels = g.n; p.cap_in = c1; p.cap_out = c2; p.thr_nms = 0.5f; p.thr_score = 0.f;
   p.in = c->d_cand1; p.cnt_in = cnt1; p.out = c->d_cand2; p.cnt_out = cnt2;
   if ((rc = launch_cascade_stage(c, 1, p, B, s)) != TRL_OK) return rc;
+  if (tm) tm->mark();
   // stage 2: per frame NMS 0.7 + regression + rerec + pad -> R-Net inputs
   p.cap_in = c2; p.cap_out = c2; p.thr_nms = 0.7f;
   p.in = c->d_cand2; p.cnt_in = cnt2; p.out = c->d_cand3; p.cnt_out = cnt3; p.pad_out = c->d_pad3;
   if ((rc = launch_cascade_stage(c, 2, p, B, s)) != TRL_OK) return rc;
+  if (tm) tm->mark();
   if ((rc = launch_crop_resample_ex(c, d_frames, B, H, W, c->d_pad3, nullptr, cnt3, c2, B * c2, 24, c->d_rin, s)) != TRL_OK) return rc;
+  if (tm) tm->mark();
   if ((rc = launch_rnet_ex(c, c->d_rin, B * c2, cnt3, c2, c->d_rprob, c->d_rreg, s)) != TRL_OK) return rc;
+  if (tm) tm->mark();
   // stage 3: R-Net score > thr, NMS 0.7, bbreg, rerec, pad -> O-Net inputs
   p.cap_in = c2; p.cap_out = c4; p.thr_nms = 0.7f; p.thr_score = c->cfg.thresholds[1];
   p.in = c->d_cand3; p.cnt_in = cnt3; p.prob = c->d_rprob; p.reg = c->d_rreg; p.pad_in = c->d_pad3;
   p.out = c->d_cand4; p.cnt_out = cnt4; p.pad_out = c->d_pad4;
   if ((rc = launch_cascade_stage(c, 3, p, B, s)) != TRL_OK) return rc;
+  if (tm) tm->mark();
   if ((rc = launch_crop_resample_ex(c, d_frames, B, H, W, c->d_pad4, nullptr, cnt4, c4, B * c4, 48, c->d_oin, s)) != TRL_OK) return rc;
+  if (tm) tm->mark();
   if ((rc = launch_onet_ex(c, c->d_oin, B * c4, cnt4, c4, c->d_oprob, c->d_oreg, s)) != TRL_OK) return rc;
+  if (tm) tm->mark();
   // stage 4: O-Net score > thr, bbreg, 'Min' NMS 0.7, largest-first
   p.cap_in = c4; p.cap_out = c4; p.thr_nms = 0.7f; p.thr_score = c->cfg.thresholds[2];
   p.in = c->d_cand4; p.cnt_in = cnt4; p.prob = c->d_oprob; p.reg = c->d_oreg; p.pad_in = c->d_pad4;
   p.out = nullptr; p.cnt_out = d_nfaces; p.pad_out = nullptr; p.boxes_out = d_boxes;
   if ((rc = launch_cascade_stage(c, 4, p, B, s)) != TRL_OK) return rc;
+  if (tm) tm->mark();
   if (d_counts) {
     // (#P-Net candidates summed over levels is not needed on the hot path; report per-stage list sizes)
     TRL_CUDA(c, cudaMemcpy2DAsync(d_counts + 1, 4 * sizeof(int), cnt3, sizeof(int), sizeof(int), B, cudaMemcpyDeviceToDevice, s));
@@ -231,7 +265,7 @@ static int detect_impl(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W,
 int trl_detect(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, int* d_nfaces, float* d_boxes, int* d_counts,
                void* stream) {
   if (!c || !d_frames || !d_nfaces || !d_boxes || B <= 0) return TRL_E_INVALID;
-  return detect_impl(c, d_frames, B, H, W, d_nfaces, d_boxes, d_counts, (cudaStream_t)stream);
+  return detect_impl(c, d_frames, B, H, W, d_nfaces, d_boxes, d_counts, (cudaStream_t)stream, nullptr);
 }
 
 int trl_crop_align(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
@@ -263,14 +297,52 @@ int trl_process(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, cons
   int rc = ensure_workspace(c, B, H, W);
   if (rc != TRL_OK) return rc;
   int* nf = d_nfaces ? d_nfaces : c->d_nfaces;
-  if ((rc = detect_impl(c, d_frames, B, H, W, nf, c->d_boxes, nullptr, s)) != TRL_OK) return rc;
+  StageTimer tm(c, s);
+  if ((rc = detect_impl(c, d_frames, B, H, W, nf, c->d_boxes, nullptr, s, &tm)) != TRL_OK) return rc;
   const int S = c->cfg.crop_size;
   if ((rc = launch_crop_align(c, d_frames, B, H, W, c->d_boxes, c->cfg.box_cap_frame * 5, nf, S, d_box_int, d_valid, c->d_crops, s)) != TRL_OK) return rc;
+  tm.mark();
   // FaceNet runs on all B crops (faceless frames carry a zero crop; their embeddings are never compared):
   // this keeps the whole batch free of host synchronisation.
   if ((rc = facenet_forward(c, c->d_crops, B, S, d_emb, s)) != TRL_OK) return rc;
-  return launch_consistency(c, d_emb, d_valid, B, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
-                            d_last_valid, s);
+  tm.mark();
+  rc = launch_consistency(c, d_emb, d_valid, B, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
+                          d_last_valid, s);
+  tm.mark();
+  return rc;
+}
+
+int trl_set_profiling(trl_ctx_t* c, int on) {
+  if (!c) return TRL_E_INVALID;
+  c->profiling = on != 0;
+  return TRL_OK;
+}
+
+int trl_stage_name(int stage, char* buf, int len) {
+  if (stage < 0 || stage >= TRL_NUM_STAGES || !buf) return TRL_E_INVALID;
+  snprintf(buf, len, "%s", kStageNames[stage]);
+  return TRL_OK;
+}
+
+/* Sum of the per-stage device times (ms) of every trl_process call since the last read; the caller must have
+ * synchronised the stream.  h_ms: float[TRL_NUM_STAGES].  Returns the number of calls accumulated. */
+int trl_read_stage_times(trl_ctx_t* c, float* h_ms) {
+  if (!c || !h_ms) return TRL_E_INVALID;
+  for (int i = 0; i < TRL_NUM_STAGES; ++i) h_ms[i] = 0.f;
+  int calls = 0;
+  for (auto& ev : c->prof_events) {
+    // marks: [0] start, [1] after memset, then one per stage
+    if ((int)ev.size() == TRL_NUM_STAGES + 2) {
+      for (int i = 0; i < TRL_NUM_STAGES; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev[i + 1], ev[i + 2]) == cudaSuccess) h_ms[i] += ms;
+      }
+      ++calls;
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+  c->prof_events.clear();
+  return calls;
 }
 
 int trl_check_capacity(trl_ctx_t* c, int* h_detail) {

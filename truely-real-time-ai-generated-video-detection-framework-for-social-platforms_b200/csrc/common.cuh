@@ -112,6 +112,9 @@ struct trl_ctx {
   CapFlag* h_cap = nullptr;      // pinned, mapped
   CapFlag* d_cap = nullptr;      // device alias of h_cap
 
+  bool profiling = false;
+  std::vector<std::vector<cudaEvent_t>> prof_events;   // one vector of marks per trl_process call
+
   // scratch for the stand-alone trl_nms entry point
   Cand* d_nms_tmp = nullptr; int nms_tmp_cap = 0;
 };

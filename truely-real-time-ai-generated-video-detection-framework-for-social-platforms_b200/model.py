@@ -118,6 +118,21 @@ class Analyzer:
     def _sptr(self):
         return C.c_void_p(self.stream.cuda_stream)
 
+    def set_profiling(self, on: bool):
+        self._check(self.lib.trl_set_profiling(self.ctx, 1 if on else 0))
+
+    def read_stage_times(self):
+        """-> ({stage name: summed ms}, n_calls) since the last read; synchronises the stream first."""
+        self.stream.synchronize()
+        ms = (C.c_float * L.NUM_STAGES)()
+        calls = self.lib.trl_read_stage_times(self.ctx, ms)
+        names = []
+        for i in range(L.NUM_STAGES):
+            b = C.create_string_buffer(32)
+            self.lib.trl_stage_name(i, b, 32)
+            names.append(b.value.decode())
+        return {n: float(ms[i]) for i, n in enumerate(names)}, calls
+
     def alloc_outputs(self, B):
         t, dev = self.torch, f"cuda:{self.device}"
         return dict(
@@ -179,6 +194,54 @@ class Analyzer:
             res.box_f = res.boxes[:, 0, :4].copy()
             res.counts = counts.cpu().numpy()
         return res
+
+
+    # ------------------------------------------------------------------ clip-level API on staged frames
+    def analyze_resident(self, frames, chunk: int = 90, host_out=None, halo=None, h2d: bool = False, dev_frames=None):
+        """All processed frames of a clip in one go.
+
+        ``frames``: uint8 [N,H,W,3] tensor, either on the device (``h2d=False``) or in pinned host memory
+        (``h2d=True``: each chunk is copied to the device inside this call, into ``dev_frames`` [chunk,H,W,3]).
+        Chunks are chained through the device-side halo embedding, so nothing synchronises until the end.
+        Returns the dict of device outputs [N, ...]; if ``host_out`` (pinned tensors keyed like the outputs) is given,
+        the small per-frame results are copied back asynchronously as well.
+        """
+        t = self.torch
+        N = frames.shape[0]
+        out = getattr(self, "_res_out", None)
+        if out is None or out["valid"].shape[0] < N:
+            out = self.alloc_outputs(N)
+            out["halo_emb"] = [t.zeros(L.EMB_DIM, dtype=t.float32, device=f"cuda:{self.device}") for _ in range(2)]
+            out["halo_valid"] = [t.zeros(1, dtype=t.uint8, device=f"cuda:{self.device}") for _ in range(2)]
+            self._res_out = out
+        with t.cuda.stream(self.stream):
+            k = 0
+            for a in range(0, N, chunk):
+                b = min(N, a + chunk)
+                if h2d:
+                    d = dev_frames[: b - a]
+                    d.copy_(frames[a:b], non_blocking=True)
+                else:
+                    d = frames[a:b]
+                view = {key: out[key][a:b] for key in ("nfaces", "box", "valid", "emb", "sim", "below", "has_sim")}
+                view["last_emb"], view["last_valid"] = out["halo_emb"][k & 1], out["halo_valid"][k & 1]
+                self.process_device(d, view, halo)
+                halo = (view["last_emb"], view["last_valid"])
+                k += 1
+            out["last_emb"], out["last_valid"] = halo
+            if host_out is not None:
+                for key, h in host_out.items():
+                    h[:N].copy_(out[key][:N], non_blocking=True)
+        return out
+
+
+def score_from_flags(valid, has_sim, below, frame_count: int, fps: int, stride: int):
+    """K13 on the host: run-length machine over the per-frame flags (server/model.py:62-70) + score (83-95)."""
+    rl = RunLength()
+    flagged = []
+    for v, h, b in zip(valid, has_sim, below):
+        flagged.append(rl.step(bool(b)) if (v and h) else False)
+    return final_score(rl.deep_fake_frame_count, rl.deepfake_count, frame_count, fps, stride), flagged, rl
 
 
 _ANALYZER = None
