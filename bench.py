@@ -195,7 +195,7 @@ def main():
     frame_count = clip.n_frames
     dev = f"cuda:{local_rank}"
     d_frames = pinned.to(dev)                                   # resident in HBM before the timed region
-    stage_buf = torch.empty((args.chunk, H, W, 3), dtype=torch.uint8, device=dev)
+    stage_buf = torch.empty((2, args.chunk, H, W, 3), dtype=torch.uint8, device=dev)     # double-buffered H2D staging
     host_out = {k: torch.empty(n_local, dtype=torch.uint8, pin_memory=True) for k in ("valid", "has_sim", "below")}
     sharded = ShardedAnalyzer(an, None) if world > 1 else None
     last = {}

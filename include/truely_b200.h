@@ -142,6 +142,12 @@ int trl_process(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, co
                 int* d_box_int, uint8_t* d_valid, float* d_emb, float* d_sim, uint8_t* d_below, uint8_t* d_has_sim,
                 int* d_nfaces, float* d_last_emb, uint8_t* d_last_valid, void* stream);
 
+/* First half of trl_process: detect + crop-align only (server/model.py:47-57), writing the crops of this batch into a
+ * caller-owned buffer d_crops uint8 [B,S,S,3].  Lets a host that holds a whole clip run the cascade chunk by chunk
+ * and then embed every crop with ONE trl_facenet call (large-M GEMMs) followed by one trl_consistency call. */
+int trl_detect_align(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, int* d_box_int, uint8_t* d_valid,
+                     int* d_nfaces, uint8_t* d_crops, void* stream);
+
 /* After the stream has been synchronised by the caller: TRL_E_CAPACITY if any candidate buffer overflowed
  * since the last check (h_detail, optional int32[4]: which stage, frame, count, capacity). */
 int trl_check_capacity(trl_ctx_t* ctx, int* h_detail);
@@ -149,7 +155,7 @@ int trl_check_capacity(trl_ctx_t* ctx, int* h_detail);
 /* Per-stage device timing of trl_process (measurement only; off by default).  With profiling on, CUDA events are
  * recorded on the launching stream around each stage; trl_read_stage_times (after the caller synchronised the
  * stream) returns in h_ms[TRL_NUM_STAGES] the summed milliseconds per stage since the last read, and as return
- * value the number of trl_process calls accumulated.  trl_stage_name gives the stage labels. */
+ * value the number of timed stage launches accumulated.  trl_stage_name gives the stage labels. */
 int trl_set_profiling(trl_ctx_t* ctx, int on);
 int trl_read_stage_times(trl_ctx_t* ctx, float* h_ms);
 int trl_stage_name(int stage, char* buf, int len);

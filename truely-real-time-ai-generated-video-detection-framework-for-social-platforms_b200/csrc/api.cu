@@ -8,25 +8,32 @@ static thread_local std::string g_create_err;
 // ---- optional per-stage timing (trl_set_profiling): CUDA events recorded on the launching stream around each stage
 static const char* kStageNames[TRL_NUM_STAGES] = {"pyramid", "pnet", "nms_scale", "nms_frame", "crop24", "rnet", "nms_rnet",
                                                   "crop48", "onet", "nms_final", "crop_align", "facenet", "consistency"};
-struct StageTimer {
+// scoped timer: records an event pair on the stream around one stage when profiling is on
+struct StageScope {
   trl_ctx* c;
   cudaStream_t s;
-  std::vector<cudaEvent_t>* ev;
-  StageTimer(trl_ctx* c_, cudaStream_t s_) : c(c_), s(s_), ev(nullptr) {
+  int stage;
+  cudaEvent_t e0 = nullptr;
+  StageScope(trl_ctx* c_, cudaStream_t s_, int stage_) : c(c_), s(s_), stage(stage_) {
     if (c->profiling) {
-      c->prof_events.emplace_back();
-      ev = &c->prof_events.back();
-      mark();
+      cudaEventCreate(&e0);
+      cudaEventRecord(e0, s);
     }
   }
-  void mark() {
-    if (!ev) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, s);
-    ev->push_back(e);
+  ~StageScope() {
+    if (e0) {
+      cudaEvent_t e1;
+      cudaEventCreate(&e1);
+      cudaEventRecord(e1, s);
+      c->prof_events.push_back({stage, e0, e1});
+    }
   }
 };
+#define TIMED(stage_id, expr)                      \
+  do {                                             \
+    StageScope _sc(c, s, stage_id);                \
+    if ((rc = (expr)) != TRL_OK) return rc;        \
+  } while (0)
 
 extern "C" {
 
@@ -67,6 +74,7 @@ void trl_destroy(trl_ctx_t* c) {
   if (c->d_rnet) cudaFree(c->d_rnet);
   if (c->d_onet) cudaFree(c->d_onet);
   if (c->d_nms_tmp) cudaFree(c->d_nms_tmp);
+  if (c->d_pyr_tab) cudaFree(c->d_pyr_tab);
   if (c->h_cap) cudaFreeHost(c->h_cap);
   delete c;
 }
@@ -202,7 +210,7 @@ static int ensure_workspace(trl_ctx* c, int B, int H, int W) {
 }
 
 static int detect_impl(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, int* d_nfaces, float* d_boxes, int* d_counts,
-                       cudaStream_t s, StageTimer* tm) {
+                       cudaStream_t s) {
   if (!c->d_pnet_packed || !c->d_rnet || !c->d_onet) TRL_FAIL(c, TRL_E_STATE, "MTCNN weights not loaded");
   int rc = ensure_workspace(c, B, H, W);
   if (rc != TRL_OK) return rc;
@@ -214,44 +222,33 @@ static int detect_impl(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W,
   int* cnt3 = cnt2 + B;
   int* cnt4 = cnt3 + B;
   TRL_CUDA(c, cudaMemsetAsync(cnt1, 0, (size_t)B * (g.n + 3) * sizeof(int), s));
-  if (tm) tm->mark();   // (memset belongs to nobody: restart the clock)
-  if ((rc = launch_pyramid(c, d_frames, B, H, W, g, c->d_pyr, s)) != TRL_OK) return rc;
-  if (tm) tm->mark();
-  if ((rc = launch_pnet_candidates(c, c->d_pyr, B, g, c->cfg.thresholds[0], c->d_cand1, cnt1, c1, s)) != TRL_OK) return rc;
-  if (tm) tm->mark();
+  TIMED(0, launch_pyramid(c, d_frames, B, H, W, g, c->d_pyr, s));
+  TIMED(1, launch_pnet_candidates(c, c->d_pyr, B, g, c->cfg.thresholds[0], c->d_cand1, cnt1, c1, s));
 
   nms::StageParams p{};
   p.W = W; p.H = H; p.capflag = c->d_cap;
   // stage 1: per (frame, level) NMS 0.5
   p.n_levels = g.n; p.cap_in = c1; p.cap_out = c2; p.thr_nms = 0.5f; p.thr_score = 0.f;
   p.in = c->d_cand1; p.cnt_in = cnt1; p.out = c->d_cand2; p.cnt_out = cnt2;
-  if ((rc = launch_cascade_stage(c, 1, p, B, s)) != TRL_OK) return rc;
-  if (tm) tm->mark();
+  TIMED(2, launch_cascade_stage(c, 1, p, B, s));
   // stage 2: per frame NMS 0.7 + regression + rerec + pad -> R-Net inputs
   p.cap_in = c2; p.cap_out = c2; p.thr_nms = 0.7f;
   p.in = c->d_cand2; p.cnt_in = cnt2; p.out = c->d_cand3; p.cnt_out = cnt3; p.pad_out = c->d_pad3;
-  if ((rc = launch_cascade_stage(c, 2, p, B, s)) != TRL_OK) return rc;
-  if (tm) tm->mark();
-  if ((rc = launch_crop_resample_ex(c, d_frames, B, H, W, c->d_pad3, nullptr, cnt3, c2, B * c2, 24, c->d_rin, s)) != TRL_OK) return rc;
-  if (tm) tm->mark();
-  if ((rc = launch_rnet_ex(c, c->d_rin, B * c2, cnt3, c2, c->d_rprob, c->d_rreg, s)) != TRL_OK) return rc;
-  if (tm) tm->mark();
+  TIMED(3, launch_cascade_stage(c, 2, p, B, s));
+  TIMED(4, launch_crop_resample_ex(c, d_frames, B, H, W, c->d_pad3, nullptr, cnt3, c2, B * c2, 24, c->d_rin, s));
+  TIMED(5, launch_rnet_ex(c, c->d_rin, B * c2, cnt3, c2, c->d_rprob, c->d_rreg, s));
   // stage 3: R-Net score > thr, NMS 0.7, bbreg, rerec, pad -> O-Net inputs
   p.cap_in = c2; p.cap_out = c4; p.thr_nms = 0.7f; p.thr_score = c->cfg.thresholds[1];
   p.in = c->d_cand3; p.cnt_in = cnt3; p.prob = c->d_rprob; p.reg = c->d_rreg; p.pad_in = c->d_pad3;
   p.out = c->d_cand4; p.cnt_out = cnt4; p.pad_out = c->d_pad4;
-  if ((rc = launch_cascade_stage(c, 3, p, B, s)) != TRL_OK) return rc;
-  if (tm) tm->mark();
-  if ((rc = launch_crop_resample_ex(c, d_frames, B, H, W, c->d_pad4, nullptr, cnt4, c4, B * c4, 48, c->d_oin, s)) != TRL_OK) return rc;
-  if (tm) tm->mark();
-  if ((rc = launch_onet_ex(c, c->d_oin, B * c4, cnt4, c4, c->d_oprob, c->d_oreg, s)) != TRL_OK) return rc;
-  if (tm) tm->mark();
+  TIMED(6, launch_cascade_stage(c, 3, p, B, s));
+  TIMED(7, launch_crop_resample_ex(c, d_frames, B, H, W, c->d_pad4, nullptr, cnt4, c4, B * c4, 48, c->d_oin, s));
+  TIMED(8, launch_onet_ex(c, c->d_oin, B * c4, cnt4, c4, c->d_oprob, c->d_oreg, s));
   // stage 4: O-Net score > thr, bbreg, 'Min' NMS 0.7, largest-first
   p.cap_in = c4; p.cap_out = c4; p.thr_nms = 0.7f; p.thr_score = c->cfg.thresholds[2];
   p.in = c->d_cand4; p.cnt_in = cnt4; p.prob = c->d_oprob; p.reg = c->d_oreg; p.pad_in = c->d_pad4;
   p.out = nullptr; p.cnt_out = d_nfaces; p.pad_out = nullptr; p.boxes_out = d_boxes;
-  if ((rc = launch_cascade_stage(c, 4, p, B, s)) != TRL_OK) return rc;
-  if (tm) tm->mark();
+  TIMED(9, launch_cascade_stage(c, 4, p, B, s));
   if (d_counts) {
     // (#P-Net candidates summed over levels is not needed on the hot path; report per-stage list sizes)
     TRL_CUDA(c, cudaMemcpy2DAsync(d_counts + 1, 4 * sizeof(int), cnt3, sizeof(int), sizeof(int), B, cudaMemcpyDeviceToDevice, s));
@@ -265,7 +262,7 @@ static int detect_impl(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W,
 int trl_detect(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, int* d_nfaces, float* d_boxes, int* d_counts,
                void* stream) {
   if (!c || !d_frames || !d_nfaces || !d_boxes || B <= 0) return TRL_E_INVALID;
-  return detect_impl(c, d_frames, B, H, W, d_nfaces, d_boxes, d_counts, (cudaStream_t)stream, nullptr);
+  return detect_impl(c, d_frames, B, H, W, d_nfaces, d_boxes, d_counts, (cudaStream_t)stream);
 }
 
 int trl_crop_align(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
@@ -277,15 +274,34 @@ int trl_crop_align(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, c
 
 int trl_facenet(trl_ctx_t* c, const uint8_t* d_crops, int n, int S, float* d_emb, void* stream) {
   if (!c || !d_crops || !d_emb || n < 0) return TRL_E_INVALID;
-  return facenet_forward(c, d_crops, n, S, d_emb, (cudaStream_t)stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  TIMED(11, facenet_forward(c, d_crops, n, S, d_emb, s));
+  return TRL_OK;
 }
 
 int trl_consistency(trl_ctx_t* c, const float* d_emb, const uint8_t* d_valid, int B, const float* d_halo_emb,
                     const uint8_t* d_halo_valid, float thr,
                     float* d_sim, uint8_t* d_below, uint8_t* d_has_sim, float* d_last_emb, uint8_t* d_last_valid, void* stream) {
   if (!c || !d_emb || !d_valid || !d_sim || !d_below || !d_has_sim) return TRL_E_INVALID;
-  return launch_consistency(c, d_emb, d_valid, B, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
-                            d_last_valid, (cudaStream_t)stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  TIMED(12, launch_consistency(c, d_emb, d_valid, B, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
+                               d_last_valid, s));
+  return TRL_OK;
+}
+
+int trl_detect_align(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, int* d_box_int, uint8_t* d_valid,
+                     int* d_nfaces, uint8_t* d_crops, void* stream) {
+  if (!c || !d_frames || !d_box_int || !d_valid || !d_crops || B <= 0) return TRL_E_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = ensure_workspace(c, B, H, W);
+  if (rc != TRL_OK) return rc;
+  int* nf = d_nfaces ? d_nfaces : c->d_nfaces;
+  if ((rc = detect_impl(c, d_frames, B, H, W, nf, c->d_boxes, nullptr, s)) != TRL_OK) return rc;
+  TIMED(10, launch_crop_align(c, d_frames, B, H, W, c->d_boxes, c->cfg.box_cap_frame * 5, nf, c->cfg.crop_size, d_box_int,
+                              d_valid, d_crops, s));
+  return TRL_OK;
 }
 
 int trl_process(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, const float* d_halo_emb,
@@ -294,22 +310,14 @@ int trl_process(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, cons
                 float* d_last_emb, uint8_t* d_last_valid, void* stream) {
   if (!c || !d_frames || !d_box_int || !d_valid || !d_emb || !d_sim || !d_below || !d_has_sim || B <= 0) return TRL_E_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = ensure_workspace(c, B, H, W);
+  int rc = trl_detect_align(c, d_frames, B, H, W, d_box_int, d_valid, d_nfaces, c->d_crops, stream);
   if (rc != TRL_OK) return rc;
-  int* nf = d_nfaces ? d_nfaces : c->d_nfaces;
-  StageTimer tm(c, s);
-  if ((rc = detect_impl(c, d_frames, B, H, W, nf, c->d_boxes, nullptr, s, &tm)) != TRL_OK) return rc;
-  const int S = c->cfg.crop_size;
-  if ((rc = launch_crop_align(c, d_frames, B, H, W, c->d_boxes, c->cfg.box_cap_frame * 5, nf, S, d_box_int, d_valid, c->d_crops, s)) != TRL_OK) return rc;
-  tm.mark();
   // FaceNet runs on all B crops (faceless frames carry a zero crop; their embeddings are never compared):
   // this keeps the whole batch free of host synchronisation.
-  if ((rc = facenet_forward(c, c->d_crops, B, S, d_emb, s)) != TRL_OK) return rc;
-  tm.mark();
-  rc = launch_consistency(c, d_emb, d_valid, B, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
-                          d_last_valid, s);
-  tm.mark();
-  return rc;
+  TIMED(11, facenet_forward(c, c->d_crops, B, c->cfg.crop_size, d_emb, s));
+  TIMED(12, launch_consistency(c, d_emb, d_valid, B, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
+                               d_last_valid, s));
+  return TRL_OK;
 }
 
 int trl_set_profiling(trl_ctx_t* c, int on) {
@@ -324,25 +332,21 @@ int trl_stage_name(int stage, char* buf, int len) {
   return TRL_OK;
 }
 
-/* Sum of the per-stage device times (ms) of every trl_process call since the last read; the caller must have
- * synchronised the stream.  h_ms: float[TRL_NUM_STAGES].  Returns the number of calls accumulated. */
+/* Sum of the per-stage device times (ms) since the last read; the caller must have synchronised the stream.
+ * h_ms: float[TRL_NUM_STAGES].  Returns the number of timed stage launches accumulated. */
 int trl_read_stage_times(trl_ctx_t* c, float* h_ms) {
   if (!c || !h_ms) return TRL_E_INVALID;
   for (int i = 0; i < TRL_NUM_STAGES; ++i) h_ms[i] = 0.f;
-  int calls = 0;
-  for (auto& ev : c->prof_events) {
-    // marks: [0] start, [1] after memset, then one per stage
-    if ((int)ev.size() == TRL_NUM_STAGES + 2) {
-      for (int i = 0; i < TRL_NUM_STAGES; ++i) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ev[i + 1], ev[i + 2]) == cudaSuccess) h_ms[i] += ms;
-      }
-      ++calls;
-    }
-    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  int n = 0;
+  for (auto& r : c->prof_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && r.stage >= 0 && r.stage < TRL_NUM_STAGES) h_ms[r.stage] += ms;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+    ++n;
   }
   c->prof_events.clear();
-  return calls;
+  return n;
 }
 
 int trl_check_capacity(trl_ctx_t* c, int* h_detail) {

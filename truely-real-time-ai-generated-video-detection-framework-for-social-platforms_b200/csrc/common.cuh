@@ -47,7 +47,8 @@ struct PyrParams {
   float scale[TRL_MAX_SCALES];
   long long off[TRL_MAX_SCALES];       // float offset (already multiplied by B) of level k
   int blk_start[TRL_MAX_SCALES + 1];   // prefix of work blocks per level (kernel specific)
-  int grp[TRL_MAX_SCALES];             // lanes cooperating per output pixel (pyramid kernel)
+  int grp[TRL_MAX_SCALES];             // log2(lanes cooperating per output pixel) (pyramid kernel)
+  int tab_off[TRL_MAX_SCALES];         // offset of level k's window tables
 };
 
 namespace nms {
@@ -88,6 +89,9 @@ struct trl_ctx {
   int ws_B = 0, ws_H = 0, ws_W = 0;
   PyramidGeom geom{};
   float* d_pyr = nullptr;
+  int* d_pyr_tab = nullptr;      // adaptive-average window tables of the current frame shape
+  int pyr_tab_H = 0, pyr_tab_W = 0;
+  int pyr_tab_off[TRL_MAX_SCALES] = {0};
   Cand* d_cand1 = nullptr;       // [B][n_scales][cand_cap_scale]   P-Net candidates
   int* d_cnt1 = nullptr;         // [B][n_scales]
   Cand* d_cand2 = nullptr;       // [B][cand_cap_frame]             after per-scale NMS
@@ -113,7 +117,8 @@ struct trl_ctx {
   CapFlag* d_cap = nullptr;      // device alias of h_cap
 
   bool profiling = false;
-  std::vector<std::vector<cudaEvent_t>> prof_events;   // one vector of marks per trl_process call
+  struct ProfRec { int stage; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_events;
 
   // scratch for the stand-alone trl_nms entry point
   Cand* d_nms_tmp = nullptr; int nms_tmp_cap = 0;

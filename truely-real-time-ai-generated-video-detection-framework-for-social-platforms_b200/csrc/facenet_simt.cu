@@ -111,8 +111,8 @@ int launch_maxpool(trl_ctx* c, const PoolOp& op, int n, cudaStream_t s) {
 }
 
 // ----------------------------------------------------------------------------- head
-// 8 crops per CTA, 512 threads = 512 embedding dims.  w_t: [1792][512] fp32 (last_linear * last_bn scale, transposed).
-constexpr int HEAD_G = 8;
+// HEAD_G crops per CTA, 512 threads = 512 embedding dims.  w_t: [1792][512] fp32 (last_linear * last_bn scale, transposed).
+constexpr int HEAD_G = 2;
 __global__ void __launch_bounds__(512) head_kernel(const bf16* __restrict__ feat, int n, int hw, const float* __restrict__ w_t,
                                                   const float* __restrict__ bias, float* __restrict__ emb) {
   extern __shared__ __align__(16) float x_s[];   // [HEAD_G][1792]

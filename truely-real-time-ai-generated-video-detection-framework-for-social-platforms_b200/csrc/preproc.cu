@@ -35,49 +35,89 @@ __device__ __forceinline__ float area_norm(int s, int kh, int kw) {
 
 // ----------------------------------------------------------------------------- K1 pyramid
 
-// grid.x = work blocks over all levels (PyrParams::blk_start), grid.y = frame.  256 threads.
+// Window tables (host computed once per frame shape): for level k, tab + tab_off[k] holds
+// x0[ws], x1[ws], y0[hs], y1[hs]  -- no integer division on the device.
+// One block = (level, tile of PYR_ROWS output rows, tile of 256/grp output columns); grid.y = frame.
+// `grp` lanes (1..32, a power of two chosen from the window width) cooperate on one output pixel, so both the
+// 2x2 windows of the finest level and the ~100x100 windows of the coarsest one stay coalesced.
+constexpr int PYR_ROWS = 8;
+
 __global__ void __launch_bounds__(256) pyramid_kernel(const uint8_t* __restrict__ frames, int H, int W, PyrParams p,
-                                                     float* __restrict__ out) {
+                                                     const int* __restrict__ tab, float* __restrict__ out) {
   int lvl = 0;
   while (lvl + 1 < p.n && (int)blockIdx.x >= p.blk_start[lvl + 1]) ++lvl;
-  const int hs = p.hs[lvl], ws = p.ws[lvl], grp = p.grp[lvl];
+  const int hs = p.hs[lvl], ws = p.ws[lvl];
+  const int gsh = p.grp[lvl];                        // log2(lanes per pixel)
+  const int grp = 1 << gsh;
+  const int px_per_blk = 256 >> gsh;
+  const int col_tiles = (ws + px_per_blk - 1) / px_per_blk;
+  const int local = (int)blockIdx.x - p.blk_start[lvl];
+  const int rt = local / col_tiles, ct = local - rt * col_tiles;
   const int b = blockIdx.y;
-  const int px_per_blk = 256 / grp;
-  const int pix = ((int)blockIdx.x - p.blk_start[lvl]) * px_per_blk + (int)threadIdx.x / grp;
-  const int sub = threadIdx.x % grp;
-  const bool valid = pix < hs * ws;
-  int s0 = 0, s1 = 0, s2 = 0, kh = 1, kw = 1, oy = 0, ox = 0;
-  if (valid) {
-    oy = pix / ws;
-    ox = pix - oy * ws;
-    const int y0 = (int)(((long long)oy * H) / hs), y1 = (int)(((long long)(oy + 1) * H + hs - 1) / hs);
-    const int x0 = (int)(((long long)ox * W) / ws), x1 = (int)(((long long)(ox + 1) * W + ws - 1) / ws);
-    kh = y1 - y0;
-    kw = x1 - x0;
-    window_sum(frames + (size_t)b * H * W * 3, W, y0, y1, x0, x1, sub, grp, s0, s1, s2);
-  }
-  for (int o = grp >> 1; o > 0; o >>= 1) {   // grp divides 32: groups never straddle a warp
-    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  }
-  if (valid && sub == 0) {
-    float* o = out + p.off[lvl] + ((size_t)b * 3) * hs * ws + (size_t)oy * ws + ox;
-    o[0] = area_norm(s0, kh, kw);
-    o[(size_t)hs * ws] = area_norm(s1, kh, kw);
-    o[(size_t)2 * hs * ws] = area_norm(s2, kh, kw);
+  const int ox = ct * px_per_blk + ((int)threadIdx.x >> gsh);
+  const int sub = threadIdx.x & (grp - 1);
+  const int* t = tab + p.tab_off[lvl];
+  const bool vx = ox < ws;
+  int x0 = 0, x1 = 0;
+  if (vx) { x0 = __ldg(t + ox); x1 = __ldg(t + ws + ox); }
+  const int kw = x1 - x0;
+  const uint8_t* frame = frames + (size_t)b * H * W * 3;
+  const size_t plane = (size_t)hs * ws;
+  float* obase = out + p.off[lvl] + (size_t)b * 3 * plane;
+  const int oy_end = min(hs, (rt + 1) * PYR_ROWS);
+  for (int oy = rt * PYR_ROWS; oy < oy_end; ++oy) {
+    const int y0 = __ldg(t + 2 * ws + oy), y1 = __ldg(t + 2 * ws + hs + oy);
+    int s0 = 0, s1 = 0, s2 = 0;
+    if (vx) window_sum(frame, W, y0, y1, x0, x1, sub, grp, s0, s1, s2);
+    for (int o = grp >> 1; o > 0; o >>= 1) {   // grp divides 32: groups never straddle a warp
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (vx && sub == 0) {
+      float* o = obase + (size_t)oy * ws + ox;
+      const int kh = y1 - y0;
+      o[0] = area_norm(s0, kh, kw);
+      o[plane] = area_norm(s1, kh, kw);
+      o[2 * plane] = area_norm(s2, kh, kw);
+    }
   }
 }
 
-static int pick_group(int in_extent, int out_extent) {
+static int pick_group_log2(int in_extent, int out_extent) {
   int kw = (in_extent + out_extent - 1) / out_extent + 1;   // upper bound of the window width
-  int g = 1;
-  while (g < 32 && g * 2 <= kw) g <<= 1;
+  int g = 0;
+  while (g < 5 && (2 << g) <= kw) ++g;
   return g;
+}
+
+// adaptive_avg_pool2d windows: [floor(i*In/Out), ceil((i+1)*In/Out))
+static void window_table(int In, int Out, std::vector<int>& v) {
+  const size_t base = v.size();
+  v.resize(base + 2 * (size_t)Out);
+  for (int i = 0; i < Out; ++i) {
+    v[base + i] = (int)(((long long)i * In) / Out);
+    v[base + Out + i] = (int)(((long long)(i + 1) * In + Out - 1) / Out);
+  }
 }
 
 int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const PyramidGeom& g, float* d_out,
                    cudaStream_t s) {
+  if (g.n == 0 || B == 0) return TRL_OK;
+  // tables are cached per frame shape
+  if (c->pyr_tab_H != H || c->pyr_tab_W != W || c->d_pyr_tab == nullptr) {
+    std::vector<int> tab;
+    for (int k = 0; k < g.n; ++k) {
+      c->pyr_tab_off[k] = (int)tab.size();
+      window_table(W, g.ws[k], tab);
+      window_table(H, g.hs[k], tab);
+    }
+    if (c->d_pyr_tab) { TRL_CUDA(c, cudaStreamSynchronize(s)); TRL_CUDA(c, cudaFree(c->d_pyr_tab)); c->d_pyr_tab = nullptr; }
+    TRL_CUDA(c, cudaMalloc(&c->d_pyr_tab, tab.size() * sizeof(int)));
+    TRL_CUDA(c, cudaMemcpy(c->d_pyr_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+    c->pyr_tab_H = H;
+    c->pyr_tab_W = W;
+  }
   PyrParams p{};
   p.n = g.n;
   int blocks = 0;
@@ -85,13 +125,13 @@ int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, con
     p.hs[k] = g.hs[k];
     p.ws[k] = g.ws[k];
     p.off[k] = g.off[k] * B;
-    p.grp[k] = pick_group(W, g.ws[k]);
+    p.grp[k] = pick_group_log2(W, g.ws[k]);
+    p.tab_off[k] = c->pyr_tab_off[k];
     p.blk_start[k] = blocks;
-    blocks += ceil_div(g.hs[k] * g.ws[k], 256 / p.grp[k]);
+    blocks += ceil_div(g.hs[k], PYR_ROWS) * ceil_div(g.ws[k], 256 >> p.grp[k]);
   }
   p.blk_start[g.n] = blocks;
-  if (blocks == 0 || B == 0) return TRL_OK;
-  pyramid_kernel<<<dim3(blocks, B), 256, 0, s>>>(d_frames, H, W, p, d_out);
+  pyramid_kernel<<<dim3(blocks, B), 256, 0, s>>>(d_frames, H, W, p, c->d_pyr_tab, d_out);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }

@@ -197,38 +197,59 @@ class Analyzer:
 
 
     # ------------------------------------------------------------------ clip-level API on staged frames
-    def analyze_resident(self, frames, chunk: int = 90, host_out=None, halo=None, h2d: bool = False, dev_frames=None):
-        """All processed frames of a clip in one go.
+    def analyze_resident(self, frames, chunk: int = 90, host_out=None, halo=None, h2d: bool = False, dev_frames=None,
+                         thr: float = THRESHOLD_FACE_SIMILARITY):
+        """All processed frames of a clip (or of this rank's range) in one go.
 
         ``frames``: uint8 [N,H,W,3] tensor, either on the device (``h2d=False``) or in pinned host memory
-        (``h2d=True``: each chunk is copied to the device inside this call, into ``dev_frames`` [chunk,H,W,3]).
-        Chunks are chained through the device-side halo embedding, so nothing synchronises until the end.
+        (``h2d=True``: chunks are copied to the device inside this call on a copy stream, double buffered in
+        ``dev_frames`` [2,chunk,H,W,3], so the copy of chunk k+1 overlaps the cascade on chunk k).
+        The MTCNN cascade + crop-align run chunk by chunk (bounded workspace); all N crops are then embedded by ONE
+        FaceNet call (large-M GEMMs) and compared by one consistency call.  Nothing synchronises with the host.
         Returns the dict of device outputs [N, ...]; if ``host_out`` (pinned tensors keyed like the outputs) is given,
-        the small per-frame results are copied back asynchronously as well.
+        those per-frame results are copied back asynchronously as well.
         """
         t = self.torch
-        N = frames.shape[0]
+        N, H, Wd, _ = frames.shape
+        S = self.crop_size
+        dev = f"cuda:{self.device}"
         out = getattr(self, "_res_out", None)
         if out is None or out["valid"].shape[0] < N:
             out = self.alloc_outputs(N)
-            out["halo_emb"] = [t.zeros(L.EMB_DIM, dtype=t.float32, device=f"cuda:{self.device}") for _ in range(2)]
-            out["halo_valid"] = [t.zeros(1, dtype=t.uint8, device=f"cuda:{self.device}") for _ in range(2)]
+            out["crops"] = t.empty((N, S, S, 3), dtype=t.uint8, device=dev)
             self._res_out = out
-        with t.cuda.stream(self.stream):
-            k = 0
-            for a in range(0, N, chunk):
-                b = min(N, a + chunk)
+        if h2d and getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = t.cuda.Stream(device=self.device)
+        he, hv = (halo if halo is not None else (None, None))
+        chunks = [(a, min(N, a + chunk)) for a in range(0, N, chunk)]
+        if h2d:
+            cs = self._copy_stream
+            copied = [t.cuda.Event() for _ in chunks]
+            consumed = [t.cuda.Event() for _ in chunks]
+            cs.wait_stream(self.stream)
+        for k, (a, b) in enumerate(chunks):
+            if h2d:
+                with t.cuda.stream(cs):
+                    if k >= 2:
+                        cs.wait_event(consumed[k - 2])          # staging buffer k&1 is free again
+                    dev_frames[k & 1, : b - a].copy_(frames[a:b], non_blocking=True)
+                    copied[k].record(cs)
+                d = dev_frames[k & 1, : b - a]
+            else:
+                d = frames[a:b]
+            with t.cuda.stream(self.stream):
                 if h2d:
-                    d = dev_frames[: b - a]
-                    d.copy_(frames[a:b], non_blocking=True)
-                else:
-                    d = frames[a:b]
-                view = {key: out[key][a:b] for key in ("nfaces", "box", "valid", "emb", "sim", "below", "has_sim")}
-                view["last_emb"], view["last_valid"] = out["halo_emb"][k & 1], out["halo_valid"][k & 1]
-                self.process_device(d, view, halo)
-                halo = (view["last_emb"], view["last_valid"])
-                k += 1
-            out["last_emb"], out["last_valid"] = halo
+                    self.stream.wait_event(copied[k])
+                self._check(self.lib.trl_detect_align(
+                    self.ctx, _vp(d), b - a, H, Wd, _vp(out["box"][a:b]), _vp(out["valid"][a:b]), _vp(out["nfaces"][a:b]),
+                    _vp(out["crops"][a:b]), self._sptr()))
+                if h2d:
+                    consumed[k].record(self.stream)
+        with t.cuda.stream(self.stream):
+            self._check(self.lib.trl_facenet(self.ctx, _vp(out["crops"]), N, S, _vp(out["emb"]), self._sptr()))
+            self._check(self.lib.trl_consistency(
+                self.ctx, _vp(out["emb"]), _vp(out["valid"]), N, _vp(he), _vp(hv), thr, _vp(out["sim"]), _vp(out["below"]),
+                _vp(out["has_sim"]), _vp(out["last_emb"]), _vp(out["last_valid"]), self._sptr()))
             if host_out is not None:
                 for key, h in host_out.items():
                     h[:N].copy_(out[key][:N], non_blocking=True)
