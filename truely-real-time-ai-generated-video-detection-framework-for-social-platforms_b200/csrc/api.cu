@@ -75,6 +75,7 @@ void trl_destroy(trl_ctx_t* c) {
   if (c->d_onet) cudaFree(c->d_onet);
   if (c->d_nms_tmp) cudaFree(c->d_nms_tmp);
   if (c->d_pyr_tab) cudaFree(c->d_pyr_tab);
+  if (c->d_bgrx) cudaFree(c->d_bgrx);
   if (c->h_cap) cudaFreeHost(c->h_cap);
   delete c;
 }
@@ -310,8 +311,9 @@ int trl_process(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, cons
                 float* d_last_emb, uint8_t* d_last_valid, void* stream) {
   if (!c || !d_frames || !d_box_int || !d_valid || !d_emb || !d_sim || !d_below || !d_has_sim || B <= 0) return TRL_E_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = trl_detect_align(c, d_frames, B, H, W, d_box_int, d_valid, d_nfaces, c->d_crops, stream);
+  int rc = ensure_workspace(c, B, H, W);       // before c->d_crops is read: the workspace may be (re)allocated here
   if (rc != TRL_OK) return rc;
+  if ((rc = trl_detect_align(c, d_frames, B, H, W, d_box_int, d_valid, d_nfaces, c->d_crops, stream)) != TRL_OK) return rc;
   // FaceNet runs on all B crops (faceless frames carry a zero crop; their embeddings are never compared):
   // this keeps the whole batch free of host synchronisation.
   TIMED(11, facenet_forward(c, c->d_crops, B, c->cfg.crop_size, d_emb, s));

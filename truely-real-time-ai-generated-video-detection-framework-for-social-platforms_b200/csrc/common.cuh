@@ -89,6 +89,8 @@ struct trl_ctx {
   int ws_B = 0, ws_H = 0, ws_W = 0;
   PyramidGeom geom{};
   float* d_pyr = nullptr;
+  uint32_t* d_bgrx = nullptr;    // BGRx (4 B / pixel) copy of the current batch, read by the pyramid kernel
+  size_t bgrx_cap = 0;
   int* d_pyr_tab = nullptr;      // adaptive-average window tables of the current frame shape
   int pyr_tab_H = 0, pyr_tab_W = 0;
   int pyr_tab_off[TRL_MAX_SCALES] = {0};

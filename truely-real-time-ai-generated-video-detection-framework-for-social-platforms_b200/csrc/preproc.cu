@@ -28,6 +28,45 @@ __device__ __forceinline__ void window_sum(const uint8_t* __restrict__ frame, in
   }
 }
 
+// Same sum over a BGRx (4 bytes / pixel) copy of the frame: one aligned 32-bit load per pixel instead of three byte
+// loads (the LSU issue rate, not bandwidth, bounds these kernels), channels accumulated two at a time in 16-bit lanes.
+// A lane adds at most ceil(kw/grp) <= 5 pixels per row, far below the 257 that would overflow a 16-bit lane.
+__device__ __forceinline__ void window_sum_x(const uint32_t* __restrict__ frame, int W, int y0, int y1, int x0, int x1,
+                                             int sub, int grp, int& s0, int& s1, int& s2) {
+  s0 = s1 = s2 = 0;
+  for (int y = y0; y < y1; ++y) {
+    const uint32_t* row = frame + (size_t)y * W;
+    uint32_t a = 0, b = 0;
+    for (int x = x0 + sub; x < x1; x += grp) {
+      const uint32_t w = __ldg(row + x);
+      a += w & 0x00FF00FFu;          // B | R<<16
+      b += (w >> 8) & 0x00FF00FFu;   // G | x<<16
+    }
+    s0 += (int)(a & 0xFFFFu);
+    s2 += (int)(a >> 16);
+    s1 += (int)(b & 0xFFFFu);
+  }
+}
+
+// flat [n_px] BGR bytes -> BGRx words, 4 pixels (12 B in, 16 B out) per thread
+__global__ void __launch_bounds__(256) bgr_to_bgrx_kernel(const uint8_t* __restrict__ in, uint32_t* __restrict__ out, size_t n_px) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t p = i * 4;
+  if (p + 3 < n_px) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(in + p * 3);
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    uint4 o;
+    o.x = w0 & 0x00FFFFFFu;
+    o.y = ((w0 >> 24) | (w1 << 8)) & 0x00FFFFFFu;
+    o.z = ((w1 >> 16) | (w2 << 16)) & 0x00FFFFFFu;
+    o.w = w2 >> 8;
+    *reinterpret_cast<uint4*>(out + p) = o;
+  } else {
+    for (size_t q = p; q < n_px; ++q)
+      out[q] = (uint32_t)in[q * 3] | ((uint32_t)in[q * 3 + 1] << 8) | ((uint32_t)in[q * 3 + 2] << 16);
+  }
+}
+
 __device__ __forceinline__ float area_norm(int s, int kh, int kw) {
   float v = __fdiv_rn(__fdiv_rn((float)s, (float)kh), (float)kw);
   return __fmul_rn(__fsub_rn(v, 127.5f), 0.0078125f);
@@ -42,7 +81,7 @@ __device__ __forceinline__ float area_norm(int s, int kh, int kw) {
 // 2x2 windows of the finest level and the ~100x100 windows of the coarsest one stay coalesced.
 constexpr int PYR_ROWS = 8;
 
-__global__ void __launch_bounds__(256) pyramid_kernel(const uint8_t* __restrict__ frames, int H, int W, PyrParams p,
+__global__ void __launch_bounds__(256) pyramid_kernel(const uint32_t* __restrict__ frames, int H, int W, PyrParams p,
                                                      const int* __restrict__ tab, float* __restrict__ out) {
   int lvl = 0;
   while (lvl + 1 < p.n && (int)blockIdx.x >= p.blk_start[lvl + 1]) ++lvl;
@@ -61,14 +100,14 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const uint8_t* __restrict_
   int x0 = 0, x1 = 0;
   if (vx) { x0 = __ldg(t + ox); x1 = __ldg(t + ws + ox); }
   const int kw = x1 - x0;
-  const uint8_t* frame = frames + (size_t)b * H * W * 3;
+  const uint32_t* frame = frames + (size_t)b * H * W;
   const size_t plane = (size_t)hs * ws;
   float* obase = out + p.off[lvl] + (size_t)b * 3 * plane;
   const int oy_end = min(hs, (rt + 1) * PYR_ROWS);
   for (int oy = rt * PYR_ROWS; oy < oy_end; ++oy) {
     const int y0 = __ldg(t + 2 * ws + oy), y1 = __ldg(t + 2 * ws + hs + oy);
     int s0 = 0, s1 = 0, s2 = 0;
-    if (vx) window_sum(frame, W, y0, y1, x0, x1, sub, grp, s0, s1, s2);
+    if (vx) window_sum_x(frame, W, y0, y1, x0, x1, sub, grp, s0, s1, s2);
     for (int o = grp >> 1; o > 0; o >>= 1) {   // grp divides 32: groups never straddle a warp
       s0 += __shfl_xor_sync(0xffffffffu, s0, o);
       s1 += __shfl_xor_sync(0xffffffffu, s1, o);
@@ -131,7 +170,19 @@ int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, con
     blocks += ceil_div(g.hs[k], PYR_ROWS) * ceil_div(g.ws[k], 256 >> p.grp[k]);
   }
   p.blk_start[g.n] = blocks;
-  pyramid_kernel<<<dim3(blocks, B), 256, 0, s>>>(d_frames, H, W, p, c->d_pyr_tab, d_out);
+  // BGR -> BGRx staging copy (grown on demand; frames are addressed flat, so any H*W*3 alignment works as long as
+  // the batch base pointer is 4-byte aligned -- otherwise fall back to an aligned bounce is not needed: cudaMalloc /
+  // torch allocations are 256-byte aligned and trl_* documents the requirement)
+  const size_t n_px = (size_t)B * H * W;
+  if ((reinterpret_cast<uintptr_t>(d_frames) & 3) != 0) TRL_FAIL(c, TRL_E_INVALID, "frames pointer must be 4-byte aligned");
+  if (c->bgrx_cap < n_px) {
+    if (c->d_bgrx) { TRL_CUDA(c, cudaFree(c->d_bgrx)); c->d_bgrx = nullptr; }
+    TRL_CUDA(c, cudaMalloc(&c->d_bgrx, n_px * sizeof(uint32_t)));
+    c->bgrx_cap = n_px;
+  }
+  bgr_to_bgrx_kernel<<<(unsigned)((n_px / 4 + 1 + 255) / 256), 256, 0, s>>>(d_frames, c->d_bgrx, n_px);
+  TRL_LAUNCH_CHECK(c);
+  pyramid_kernel<<<dim3(blocks, B), 256, 0, s>>>(c->d_bgrx, H, W, p, c->d_pyr_tab, d_out);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
