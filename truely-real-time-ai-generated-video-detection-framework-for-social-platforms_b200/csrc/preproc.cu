@@ -8,6 +8,8 @@
 //  * cv2.resize(INTER_LINEAR, uint8): 11-bit fixed-point coefficients, horizontal pass in int32,
 //    vertical pass ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2; x coefficients are clamped at the
 //    borders, y rows are clipped instead (coefficients kept) -- bit exact with OpenCV.
+#include <algorithm>
+
 #include "common.cuh"
 
 // ----------------------------------------------------------------------------- shared device helpers
@@ -82,8 +84,8 @@ __device__ __forceinline__ float area_norm(int s, int kh, int kw) {
 constexpr int PYR_ROWS = 8;
 
 __global__ void __launch_bounds__(256) pyramid_kernel(const uint32_t* __restrict__ frames, int H, int W, PyrParams p,
-                                                     const int* __restrict__ tab, float* __restrict__ out) {
-  int lvl = 0;
+                                                     int lvl_first, const int* __restrict__ tab, float* __restrict__ out) {
+  int lvl = lvl_first;
   while (lvl + 1 < p.n && (int)blockIdx.x >= p.blk_start[lvl + 1]) ++lvl;
   const int hs = p.hs[lvl], ws = p.ws[lvl];
   const int gsh = p.grp[lvl];                        // log2(lanes per pixel)
@@ -123,6 +125,56 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const uint32_t* __restrict
   }
 }
 
+
+// Fine levels (window at most WMAX x WMAX): one thread per output pixel, fully unrolled predicated window, 32-bit
+// index arithmetic.  The generic lane-cooperative kernel above spends most of its instructions on loop control when
+// the windows are 2x2..8x8, and these levels hold > 95 % of the pyramid's pixels.
+template <int WMAX>
+__global__ void __launch_bounds__(256) pyramid_fine_kernel(const uint32_t* __restrict__ frames, int H, int W, PyrParams p,
+                                                          int lvl_first, int blk_first, const int* __restrict__ tab,
+                                                          float* __restrict__ out) {
+  int lvl = lvl_first;
+  const int bx = (int)blockIdx.x + blk_first;
+  while (lvl + 1 < p.n && bx >= p.blk_start[lvl + 1]) ++lvl;
+  const int hs = p.hs[lvl], ws = p.ws[lvl];
+  const int col_tiles = (ws + 255) >> 8;
+  const int local = bx - p.blk_start[lvl];
+  const int rt = local / col_tiles, ct = local - rt * col_tiles;
+  const int ox = ct * 256 + (int)threadIdx.x;
+  if (ox >= ws) return;
+  const int* t = tab + p.tab_off[lvl];
+  const int x0 = __ldg(t + ox), kw = __ldg(t + ws + ox) - x0;
+  const uint32_t* frame = frames + (size_t)blockIdx.y * H * W;
+  const int plane = hs * ws;
+  float* obase = out + p.off[lvl] + (size_t)blockIdx.y * 3 * plane + ox;
+  const float fkw = (float)kw;
+  const int oy_end = min(hs, (rt + 1) * PYR_ROWS);
+  for (int oy = rt * PYR_ROWS; oy < oy_end; ++oy) {
+    const int y0 = __ldg(t + 2 * ws + oy), kh = __ldg(t + 2 * ws + hs + oy) - y0;
+    const uint32_t* wp = frame + (y0 * W + x0);
+    uint32_t a = 0, b = 0;
+#pragma unroll
+    for (int dy = 0; dy < WMAX; ++dy) {
+      if (dy < kh) {
+#pragma unroll
+        for (int dx = 0; dx < WMAX; ++dx) {
+          if (dx < kw) {
+            const uint32_t w = __ldg(wp + dy * W + dx);
+            a += w & 0x00FF00FFu;
+            b += (w >> 8) & 0x00FF00FFu;
+          }
+        }
+      }
+    }
+    // WMAX*WMAX <= 64 pixels: the 16-bit lanes cannot overflow
+    const float fkh = (float)kh;
+    float* o = obase + oy * ws;
+    o[0] = __fmul_rn(__fsub_rn(__fdiv_rn(__fdiv_rn((float)(a & 0xFFFFu), fkh), fkw), 127.5f), 0.0078125f);
+    o[plane] = __fmul_rn(__fsub_rn(__fdiv_rn(__fdiv_rn((float)(b & 0xFFFFu), fkh), fkw), 127.5f), 0.0078125f);
+    o[2 * plane] = __fmul_rn(__fsub_rn(__fdiv_rn(__fdiv_rn((float)(a >> 16), fkh), fkw), 127.5f), 0.0078125f);
+  }
+}
+
 static int pick_group_log2(int in_extent, int out_extent) {
   int kw = (in_extent + out_extent - 1) / out_extent + 1;   // upper bound of the window width
   int g = 0;
@@ -157,22 +209,22 @@ int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, con
     c->pyr_tab_H = H;
     c->pyr_tab_W = W;
   }
+  // Levels are launched by class: fine levels (max window <= 3 / 4 / 6 / 8) with the unrolled one-thread-per-pixel
+  // kernel, the coarse rest with the lane-cooperative kernel.  blk_start is a prefix over the levels of one class.
   PyrParams p{};
   p.n = g.n;
-  int blocks = 0;
+  int cls[TRL_MAX_SCALES];
   for (int k = 0; k < g.n; ++k) {
     p.hs[k] = g.hs[k];
     p.ws[k] = g.ws[k];
     p.off[k] = g.off[k] * B;
     p.grp[k] = pick_group_log2(W, g.ws[k]);
     p.tab_off[k] = c->pyr_tab_off[k];
-    p.blk_start[k] = blocks;
-    blocks += ceil_div(g.hs[k], PYR_ROWS) * ceil_div(g.ws[k], 256 >> p.grp[k]);
+    const int wmax = std::max((W + g.ws[k] - 1) / g.ws[k], (H + g.hs[k] - 1) / g.hs[k]) + 1;
+    cls[k] = wmax <= 3 ? 3 : wmax <= 4 ? 4 : wmax <= 6 ? 6 : wmax <= 8 ? 8 : 0;
   }
-  p.blk_start[g.n] = blocks;
-  // BGR -> BGRx staging copy (grown on demand; frames are addressed flat, so any H*W*3 alignment works as long as
-  // the batch base pointer is 4-byte aligned -- otherwise fall back to an aligned bounce is not needed: cudaMalloc /
-  // torch allocations are 256-byte aligned and trl_* documents the requirement)
+  // BGR -> BGRx staging copy (frames are addressed flat, so any H*W*3 works as long as the batch base pointer is
+  // 4-byte aligned; cudaMalloc / torch allocations are 256-byte aligned)
   const size_t n_px = (size_t)B * H * W;
   if ((reinterpret_cast<uintptr_t>(d_frames) & 3) != 0) TRL_FAIL(c, TRL_E_INVALID, "frames pointer must be 4-byte aligned");
   if (c->bgrx_cap < n_px) {
@@ -182,8 +234,33 @@ int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, con
   }
   bgr_to_bgrx_kernel<<<(unsigned)((n_px / 4 + 1 + 255) / 256), 256, 0, s>>>(d_frames, c->d_bgrx, n_px);
   TRL_LAUNCH_CHECK(c);
-  pyramid_kernel<<<dim3(blocks, B), 256, 0, s>>>(c->d_bgrx, H, W, p, c->d_pyr_tab, d_out);
-  TRL_LAUNCH_CHECK(c);
+  // levels are ordered fine -> coarse, so each class is a contiguous run of levels
+  int k = 0;
+  while (k < g.n) {
+    const int cl = cls[k];
+    int k1 = k;
+    int blocks = 0;
+    while (k1 < g.n && cls[k1] == cl) {
+      p.blk_start[k1] = blocks;
+      blocks += cl ? ceil_div(g.hs[k1], PYR_ROWS) * ceil_div(g.ws[k1], 256)
+                   : ceil_div(g.hs[k1], PYR_ROWS) * ceil_div(g.ws[k1], 256 >> p.grp[k1]);
+      ++k1;
+    }
+    for (int q = k1; q <= g.n; ++q) p.blk_start[q] = blocks;      // sentinel for the level search
+    PyrParams pc = p;
+    // the level search in the kernels walks from the first level of the class: hide the finer ones
+    for (int q = 0; q < k; ++q) pc.blk_start[q] = -1;
+    dim3 grid(blocks, B);
+    switch (cl) {
+      case 3: pyramid_fine_kernel<3><<<grid, 256, 0, s>>>(c->d_bgrx, H, W, pc, k, 0, c->d_pyr_tab, d_out); break;
+      case 4: pyramid_fine_kernel<4><<<grid, 256, 0, s>>>(c->d_bgrx, H, W, pc, k, 0, c->d_pyr_tab, d_out); break;
+      case 6: pyramid_fine_kernel<6><<<grid, 256, 0, s>>>(c->d_bgrx, H, W, pc, k, 0, c->d_pyr_tab, d_out); break;
+      case 8: pyramid_fine_kernel<8><<<grid, 256, 0, s>>>(c->d_bgrx, H, W, pc, k, 0, c->d_pyr_tab, d_out); break;
+      default: pyramid_kernel<<<grid, 256, 0, s>>>(c->d_bgrx, H, W, pc, k, c->d_pyr_tab, d_out); break;
+    }
+    TRL_LAUNCH_CHECK(c);
+    k = k1;
+  }
   return TRL_OK;
 }
 
