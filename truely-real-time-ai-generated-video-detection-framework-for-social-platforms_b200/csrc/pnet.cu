@@ -4,8 +4,16 @@
 //
 // upstream: models/mtcnn.py PNet.forward, models/utils/detect_face.py generateBoundingBox.
 //
-// Thread tiles are register blocked (4 px x 4|8 channels) with weights broadcast from shared memory by
-// LDS.128, so the inner loops issue ~90 % FFMA.  FLOP roof, not HBM, binds this kernel.
+// conv1/conv2 run on the FP32 FMA pipe: thread tiles are register blocked (4 px x 4 channels) with weights broadcast
+// from shared memory by LDS.128.  conv3 (63 % of the FLOPs) runs on the tensor pipe as an implicit GEMM
+// (M = 16 pixels of one output row, N = 8 channels, K = 8 = one filter tap x 8 input channels) with
+// mma.sync.m16n8k8 TF32 and the 3xTF32 split (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulate), which keeps
+// fp32-level accuracy (measured max |err| 1e-5 on |sum| ~ 4.5 over K = 144, experiments/umma_probe.cu) so the
+// cascade sees the same candidates as the fp32 reference.  tcgen05 was measured and rejected for this layer: with
+// N = 32 output channels an SS-mode UMMA is bound by re-reading the A tile from shared memory (~73 cycles per
+// M128 x N32 x K8 step, experiments/umma_probe.cu), no faster than mma.sync once the 3x split is paid.
+// The two CTAs of an SM overlap one CTA's FMA-pipe stages with the other's tensor-pipe stage.
+// FLOP roof, not HBM, binds this kernel.
 #include "common.cuh"
 
 namespace pnet {
@@ -25,7 +33,7 @@ constexpr int A1 = B1 + 12;           // [12]
 constexpr int W2 = A1 + 12;           // [90][16]
 constexpr int B2 = W2 + 90 * 16;
 constexpr int A2 = B2 + 16;
-constexpr int W3 = A2 + 16;           // [144][32]
+constexpr int W3 = A2 + 16;           // mma B fragments: [18 k-steps][2][32 lanes][4 n-tiles], k = tap*16 + ci
 constexpr int B3 = W3 + 144 * 32;
 constexpr int A3 = B3 + 32;
 constexpr int WH = A3 + 32;           // [32][8]: cols 0,1 conv4_1; 2..5 conv4_2
@@ -62,6 +70,19 @@ struct Params {
 
 __device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : v * a; }
 
+// x = hi + lo with hi exactly representable in TF32 (round to nearest, ties away; two integer ops instead of the
+// five-instruction NaN-safe expansion of cvt.rna.tf32.f32 -- activations and weights are finite).  The tensor core
+// drops lo's low 13 bits, an error of 2^-21 |x|.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ wpacked, const __grid_constant__ Params p) {
   extern __shared__ __align__(16) float smem[];
   float* w_s = smem;
@@ -78,21 +99,27 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
   const int oy0 = ty * TOY, ox0 = tx * TOX;
   const int hs = L.hs, ws = L.ws;
 
-  // ---- stage weights and the input tile
-  for (int i = tid; i < WTOTAL / 4; i += 256)
-    reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(wpacked) + i);
+  // ---- stage weights and the input tile with cp.async (LDGSTS): every copy of a thread is in flight at once, so
+  // the tile costs one L2 round trip instead of one per unrolled load group; out-of-image elements are zero filled
+  // (src-size 0).
   {
+    const uint32_t w_dst = (uint32_t)__cvta_generic_to_shared(w_s);
+    for (int i = tid; i < WTOTAL / 4; i += 256)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(w_dst + 16u * i), "l"(wpacked + 4 * i) : "memory");
     const float* src = L.in + (size_t)b * 3 * hs * ws;
     const int iy0 = 2 * oy0, ix0 = 2 * ox0;
+    const uint32_t a_dst = (uint32_t)__cvta_generic_to_shared(a_s);
     for (int i = tid; i < 3 * INH * INW; i += 256) {
       const int ci = i / (INH * INW);
       const int r = (i - ci * INH * INW) / INW;
       const int cx = i - ci * INH * INW - r * INW;
       const int gy = iy0 + r, gx = ix0 + cx;
-      float v = 0.f;
-      if (gy < hs && gx < ws) v = __ldg(src + ((size_t)ci * hs + gy) * ws + gx);
-      a_s[(ci * INH + r) * INP + cx] = v;
+      const bool ok = gy < hs && gx < ws;
+      const float* gp = ok ? src + ((size_t)ci * hs + gy) * ws + gx : src;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
+                   ::"r"(a_dst + 4u * ((ci * INH + r) * INP + cx)), "l"(gp), "r"(ok ? 4 : 0) : "memory");
     }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
 
@@ -205,106 +232,139 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
   }
   __syncthreads();
 
-  // ---- conv3 (16->32, 3x3) + PReLU + heads.  thread = (4 px, 16 channels); halves are warp uniform.
-  const int pgi = tid & 127, half = tid >> 7;
-  const int row = pgi >> 3, pg = pgi & 7;
-  float hp[4][6];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 6; ++j) hp[i][j] = 0.f;
+  // ---- conv3 (16->32, 3x3) on the tensor pipe + PReLU + heads.
+  // warp w owns output rows 2w, 2w+1; one pass = one row = two 16-pixel M tiles x four 8-channel N tiles.
+  // fragment coordinates (PTX m16n8k8): g = lane/4, t = lane%4
+  //   A: a0 (px g, k t)  a1 (px g+8, k t)  a2 (px g, k t+4)  a3 (px g+8, k t+4)
+  //   B: b0 (k t, n g)   b1 (k t+4, n g)          C: c0 (px g, n 2t) c1 (px g, n 2t+1) c2/c3 (px g+8, ..)
+  // conv2 planes are 18*36 = 648 floats apart (= 8 mod 32 banks), so the 32 lanes of an A load hit 32 banks.
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
 #pragma unroll 1
-  for (int sub = 0; sub < 2; ++sub) {
-    const int c0 = (half * 2 + sub) * 8;
-    float acc[4][8];
+    for (int pass = 0; pass < 2; ++pass) {
+      const int row = 2 * warp + pass;
+      const float* arow = a_s + (t * C2H + row) * C2P + g;
+      const float4* wf = reinterpret_cast<const float4*>(w_s + W3) + lane;
+      float acc[2][4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int m = 0; m < 2; ++m)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll 2
-    for (int ci = 0; ci < 16; ++ci)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
+          for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
+#pragma unroll 1
       for (int ky = 0; ky < 3; ++ky) {
-        const float* ir = &a_s[(ci * C2H + row + ky) * C2P + 4 * pg];
-        const float4 i0 = *reinterpret_cast<const float4*>(ir);
-        const float2 i1 = *reinterpret_cast<const float2*>(ir + 4);
-        const float in[6] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y};
+        // 6 k-steps per filter row: (kx, channel half); unrolled so the offsets are immediates, the outer loop
+        // stays rolled to bound the number of live shared-memory loads (no spills at 128 registers)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const float* wr = &w_s[W3 + ((ci * 3 + ky) * 3 + kx) * 32 + c0];
-          const float4 wa = *reinterpret_cast<const float4*>(wr);
-          const float4 wb = *reinterpret_cast<const float4*>(wr + 4);
-          const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        for (int s6 = 0; s6 < 6; ++s6) {
+          const int kx = s6 >> 1;
+          const int koff = ((s6 & 1) * 8 * C2H) * C2P + kx;
+          const float4 w0 = wf[(2 * s6) * 32], w1 = wf[(2 * s6 + 1) * 32];
+          const float bw[2][4] = {{w0.x, w0.y, w0.z, w0.w}, {w1.x, w1.y, w1.z, w1.w}};
+          uint32_t bh[2][4], bl[2][4];
 #pragma unroll
-          for (int px = 0; px < 4; ++px)
+          for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(in[px + kx], w[j], acc[px][j]);
+            for (int j = 0; j < 4; ++j) split_tf32(bw[i][j], bh[i][j], bl[i][j]);
+          uint32_t ah[2][4], al[2][4];
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            const float* ap = arow + koff + 16 * m;
+            split_tf32(ap[0], ah[m][0], al[m][0]);
+            split_tf32(ap[8], ah[m][1], al[m][1]);
+            split_tf32(ap[4 * C2H * C2P], ah[m][2], al[m][2]);
+            split_tf32(ap[4 * C2H * C2P + 8], ah[m][3], al[m][3]);
+          }
+          // the three terms of one accumulator are dependent: issue the 8 independent accumulators between them
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_tf32(acc[m][j], al[m], bh[0][j], bh[1][j]);
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_tf32(acc[m][j], ah[m], bl[0][j], bl[1][j]);
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_tf32(acc[m][j], ah[m], bh[0][j], bh[1][j]);
         }
+        arow += C2P;
+        wf += 12 * 32;
       }
+      // epilogue: bias + PReLU, heads (6 outputs over 32 channels; this thread holds 8 channels of 2 pixels per tile)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int co = c0 + j;
-      const float bias = w_s[B3 + co], al = w_s[A3 + co];
-      const float4 ha = *reinterpret_cast<const float4*>(&w_s[WH + co * 8]);
-      const float2 hb = *reinterpret_cast<const float2*>(&w_s[WH + co * 8 + 4]);
+      for (int m = 0; m < 2; ++m) {
+        float hp[2][6];
 #pragma unroll
-      for (int px = 0; px < 4; ++px) {
-        const float v = prelu(acc[px][j] + bias, al);
-        hp[px][0] = fmaf(v, ha.x, hp[px][0]);
-        hp[px][1] = fmaf(v, ha.y, hp[px][1]);
-        hp[px][2] = fmaf(v, ha.z, hp[px][2]);
-        hp[px][3] = fmaf(v, ha.w, hp[px][3]);
-        hp[px][4] = fmaf(v, hb.x, hp[px][4]);
-        hp[px][5] = fmaf(v, hb.y, hp[px][5]);
-      }
-    }
-  }
-  // combine the two channel halves through shared memory (pooled conv1 tile is dead)
-  __syncthreads();
-  if (half == 1) {
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int px = 0; px < 4; ++px)
+          for (int q = 0; q < 6; ++q) hp[i][q] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 6; ++j) p1_s[(px * 6 + j) * 128 + pgi] = hp[px][j];
-  }
-  __syncthreads();
-  if (half == 0) {
-    const int oy = oy0 + row;
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int px = 0; px < 4; ++px) {
-      const int ox = ox0 + 4 * pg + px;
-      float h[6];
+          for (int e = 0; e < 2; ++e) {
+            const int co = 8 * j + 2 * t + e;
+            const float bias = w_s[B3 + co], al = w_s[A3 + co];
+            const float4 ha = *reinterpret_cast<const float4*>(&w_s[WH + co * 8]);
+            const float2 hb = *reinterpret_cast<const float2*>(&w_s[WH + co * 8 + 4]);
 #pragma unroll
-      for (int j = 0; j < 6; ++j) h[j] = hp[px][j] + p1_s[(px * 6 + j) * 128 + pgi] + w_s[BH + j];
-      if (oy < L.oh && ox < L.ow) {
-        // softmax over (h0, h1), class 1 -- same form as ATen's softmax (subtract max, exp, normalise)
-        const float mx = fmaxf(h[0], h[1]);
-        const float e0 = expf(h[0] - mx), e1 = expf(h[1] - mx);
-        const float prob = __fdiv_rn(e1, e0 + e1);
-        const size_t cell = (size_t)oy * L.ow + ox;
-        if (L.prob) {
-          const size_t plane = (size_t)L.oh * L.ow;
-          L.prob[(size_t)b * plane + cell] = prob;
-          float* rg = L.reg + (size_t)b * 4 * plane + cell;
-          rg[0] = h[2]; rg[plane] = h[3]; rg[2 * plane] = h[4]; rg[3 * plane] = h[5];
-        }
-        if (L.cand && prob >= p.thr) {
-          // generateBoundingBox: q1 = floor((2*c + 1)/scale), q2 = floor((2*c + 12)/scale)  (fp32, true division)
-          const int slotbase = b * p.n_levels + lvl;
-          const int slot = atomicAdd(&L.cnt[slotbase], 1);
-          if (slot < p.cap) {
-            Cand cd;
-            cd.x1 = floorf(__fdiv_rn((float)(2 * ox + 1), L.scale));
-            cd.y1 = floorf(__fdiv_rn((float)(2 * oy + 1), L.scale));
-            cd.x2 = floorf(__fdiv_rn((float)(2 * ox + 12), L.scale));
-            cd.y2 = floorf(__fdiv_rn((float)(2 * oy + 12), L.scale));
-            cd.score = prob;
-            cd.r0 = h[2]; cd.r1 = h[3]; cd.r2 = h[4]; cd.r3 = h[5];
-            cd.key = (uint32_t)cell;
-            L.cand[(size_t)slotbase * p.cap + slot] = cd;
-          } else if (p.capflag) {
-            p.capflag->overflow = 1; p.capflag->stage = 1; p.capflag->frame = b;
-            p.capflag->count = slot + 1; p.capflag->capacity = p.cap;
+            for (int i = 0; i < 2; ++i) {
+              const float v = prelu(acc[m][j][2 * i + e] + bias, al);
+              hp[i][0] = fmaf(v, ha.x, hp[i][0]);
+              hp[i][1] = fmaf(v, ha.y, hp[i][1]);
+              hp[i][2] = fmaf(v, ha.z, hp[i][2]);
+              hp[i][3] = fmaf(v, ha.w, hp[i][3]);
+              hp[i][4] = fmaf(v, hb.x, hp[i][4]);
+              hp[i][5] = fmaf(v, hb.y, hp[i][5]);
+            }
+          }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            hp[i][q] += __shfl_xor_sync(0xffffffffu, hp[i][q], 1);
+            hp[i][q] += __shfl_xor_sync(0xffffffffu, hp[i][q], 2);
+          }
+        // lanes t = 0 / 1 finish pixels g / g+8 of this tile
+        if (t < 2) {
+          float h[6];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) h[q] = (t == 0 ? hp[0][q] : hp[1][q]) + w_s[BH + q];
+          const int oy = oy0 + row, ox = ox0 + 16 * m + g + 8 * t;
+          if (oy < L.oh && ox < L.ow) {
+            // softmax over (h0, h1), class 1 -- same form as ATen's softmax (subtract max, exp, normalise)
+            const float mx = fmaxf(h[0], h[1]);
+            const float e0 = expf(h[0] - mx), e1 = expf(h[1] - mx);
+            const float prob = __fdiv_rn(e1, e0 + e1);
+            const size_t cell = (size_t)oy * L.ow + ox;
+            if (L.prob) {
+              const size_t plane = (size_t)L.oh * L.ow;
+              L.prob[(size_t)b * plane + cell] = prob;
+              float* rg = L.reg + (size_t)b * 4 * plane + cell;
+              rg[0] = h[2]; rg[plane] = h[3]; rg[2 * plane] = h[4]; rg[3 * plane] = h[5];
+            }
+            if (L.cand && prob >= p.thr) {
+              // generateBoundingBox: q1 = floor((2*c + 1)/scale), q2 = floor((2*c + 12)/scale)  (fp32, true division)
+              const int slotbase = b * p.n_levels + lvl;
+              const int slot = atomicAdd(&L.cnt[slotbase], 1);
+              if (slot < p.cap) {
+                Cand cd;
+                cd.x1 = floorf(__fdiv_rn((float)(2 * ox + 1), L.scale));
+                cd.y1 = floorf(__fdiv_rn((float)(2 * oy + 1), L.scale));
+                cd.x2 = floorf(__fdiv_rn((float)(2 * ox + 12), L.scale));
+                cd.y2 = floorf(__fdiv_rn((float)(2 * oy + 12), L.scale));
+                cd.score = prob;
+                cd.r0 = h[2]; cd.r1 = h[3]; cd.r2 = h[4]; cd.r3 = h[5];
+                cd.key = (uint32_t)cell;
+                L.cand[(size_t)slotbase * p.cap + slot] = cd;
+              } else if (p.capflag) {
+                p.capflag->overflow = 1; p.capflag->stage = 1; p.capflag->frame = b;
+                p.capflag->count = slot + 1; p.capflag->capacity = p.cap;
+              }
+            }
           }
         }
       }
@@ -338,8 +398,15 @@ int pnet_pack_weights(trl_ctx* c, const float* h, size_t len) {
   for (int co = 0; co < 16; ++co)
     for (int k = 0; k < 90; ++k) pk[W2 + k * 16 + co] = w2[co * 90 + k];
   for (int co = 0; co < 16; ++co) { pk[B2 + co] = b2[co]; pk[A2 + co] = a2[co]; }
-  for (int co = 0; co < 32; ++co)
-    for (int k = 0; k < 144; ++k) pk[W3 + k * 32 + co] = w3[co * 144 + k];
+  // conv3 as mma.m16n8k8 B fragments: k-step s = (tap, channel half), k = 8s + t (+4) -> ci = (s&1)*8 + t (+4)
+  for (int s = 0; s < 18; ++s)
+    for (int i = 0; i < 2; ++i)
+      for (int lane = 0; lane < 32; ++lane)
+        for (int j = 0; j < 4; ++j) {
+          const int g = lane >> 2, t = lane & 3;
+          const int tap = s >> 1, ci = (s & 1) * 8 + t + 4 * i, co = 8 * j + g;
+          pk[W3 + ((2 * s + i) * 32 + lane) * 4 + j] = w3[co * 144 + ci * 9 + tap];
+        }
   for (int co = 0; co < 32; ++co) { pk[B3 + co] = b3[co]; pk[A3 + co] = a3[co]; }
   for (int ci = 0; ci < 32; ++ci) {
     pk[WH + ci * 8 + 0] = w41[0 * 32 + ci];
