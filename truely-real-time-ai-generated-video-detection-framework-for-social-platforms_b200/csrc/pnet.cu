@@ -15,13 +15,16 @@
 // The two CTAs of an SM overlap one CTA's FMA-pipe stages with the other's tensor-pipe stage.
 // FLOP roof, not HBM, binds this kernel.
 #include "common.cuh"
+#include <string.h>
 
 namespace pnet {
 
 constexpr int TOY = 16, TOX = 32;            // output cells per CTA
 constexpr int P1H = TOY + 4, P1W = TOX + 4;  // pooled conv1 tile (20 x 36)
-constexpr int P1P = 40;                      // pitch (conv2 over-reads to col 37)
-constexpr int C2H = TOY + 2, C2W = 36;       // conv2 tile rows x computed cols (34 valid + 2 slack)
+constexpr int P1P = 40;                      // pitch (conv2's last 8-pixel segment over-reads to col 41 = next row)
+constexpr int P1PLANE = P1H * P1P + 8;       // 808 = 8 mod 32: four channels of one tap land in four bank octets
+constexpr int C2H = TOY + 2, C2W = 36;       // conv2 tile rows x stored cols (34 valid + 2 slack)
+constexpr int C2SEG = 5;                     // conv2 row = five 8-pixel segments (40 computed columns)
 constexpr int C2P = 36;
 constexpr int INH = 2 * TOY + 10, INW = 2 * TOX + 10;   // 42 x 74 input tile
 constexpr int INP = 76;
@@ -30,21 +33,22 @@ constexpr int INP = 76;
 constexpr int W1 = 0;                 // [27][12]
 constexpr int B1 = W1 + 27 * 12;      // [12]
 constexpr int A1 = B1 + 12;           // [12]
-constexpr int W2 = A1 + 12;           // [90][16]
-constexpr int B2 = W2 + 90 * 16;
+constexpr int W2 = A1 + 12;           // mma B fragments: [12 k-steps][32 lanes][b0 n0, b0 n1, b1 n0, b1 n1]
+constexpr int T2 = W2 + 12 * 32 * 4;  // int[96]: pooled-tile offset of k index 8s + t (+4), see conv2_k()
+constexpr int B2 = T2 + 96;
 constexpr int A2 = B2 + 16;
 constexpr int W3 = A2 + 16;           // mma B fragments: [18 k-steps][2][32 lanes][4 n-tiles], k = tap*16 + ci
 constexpr int B3 = W3 + 144 * 32;
 constexpr int A3 = B3 + 32;
 constexpr int WH = A3 + 32;           // [32][8]: cols 0,1 conv4_1; 2..5 conv4_2
 constexpr int BH = WH + 32 * 8;       // [8]
-constexpr int WTOTAL = BH + 8;        // 6756 floats
+constexpr int WTOTAL = BH + 8;        // 6948 floats
 static_assert(WTOTAL % 4 == 0, "float4 copy");
 
 constexpr int SM_IN = 3 * INH * INP;          // 9576
 constexpr int SM_C2 = 16 * C2H * C2P;         // 10368   (aliases the input tile)
 constexpr int SM_A = SM_C2 > SM_IN ? SM_C2 : SM_IN;
-constexpr int SM_P1 = 10 * P1H * P1P;         // 8000    (later: head partial sums, 24*128)
+constexpr int SM_P1 = 10 * P1PLANE;           // 8080
 constexpr int SMEM_FLOATS = WTOTAL + SM_A + SM_P1;
 constexpr int SMEM_BYTES = SMEM_FLOATS * 4;   // ~100 KB -> 2 CTAs / SM
 
@@ -68,6 +72,9 @@ struct Params {
   CapFlag* capflag;
 };
 
+#ifdef PNET_TIMING
+__device__ unsigned long long g_pnet_phase[8];
+#endif
 __device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : v * a; }
 
 // x = hi + lo with hi exactly representable in TF32 (round to nearest, ties away; two integer ops instead of the
@@ -89,6 +96,9 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
   float* a_s = smem + WTOTAL;          // input tile, later conv2 output
   float* p1_s = a_s + SM_A;            // pooled conv1, later head partials
   const int tid = threadIdx.x;
+#ifdef PNET_TIMING
+  long long tph[5]; tph[0] = clock64();
+#endif
 
   int lvl = 0;
   while (lvl + 1 < p.n_levels && (int)blockIdx.x >= p.blk_start[lvl + 1]) ++lvl;
@@ -122,6 +132,9 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
+#ifdef PNET_TIMING
+  tph[1] = clock64();
+#endif
 
   // ---- conv1 (3->10, 3x3) + PReLU + maxpool(2,2,ceil): one pooled pixel x 10 channels per item
   {
@@ -171,7 +184,7 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
           const float v = prelu(acc[q][co] + bias, al);
           m = ok ? fmaxf(m, v) : m;
         }
-        p1_s[(co * P1H + py) * P1P + px] = (m == -INFINITY) ? 0.f : m;
+        p1_s[co * P1PLANE + py * P1P + px] = (m == -INFINITY) ? 0.f : m;
       }
     }
     // slack columns read by conv2's last pixel group
@@ -179,58 +192,94 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
       const int co = i / (P1H * (P1P - P1W));
       const int r = (i / (P1P - P1W)) % P1H;
       const int cx = P1W + i % (P1P - P1W);
-      p1_s[(co * P1H + r) * P1P + cx] = 0.f;
+      p1_s[co * P1PLANE + r * P1P + cx] = 0.f;
     }
   }
   __syncthreads();
+#ifdef PNET_TIMING
+  tph[2] = clock64();
+#endif
 
-  // ---- conv2 (10->16, 3x3) + PReLU: item = (4 channels, row, 4 px); output over the dead input tile
+  // ---- conv2 (10->16, 3x3) + PReLU on the tensor pipe (3xTF32), output over the dead input tile.
+  // M tile = two 8-pixel row segments (18 rows x 5 segments = 45 tiles), N = 2 x 8 channels, K = 96 (90 used):
+  // k index 8s + t (+4) -> (ci, ky, kx) by conv2_k(): the four k of one A load share kx and differ in (ci + ky) mod 4,
+  // so with planes 808 floats apart they read four different bank octets (conflict free); offsets come from T2.
   {
-    constexpr int PXG = C2W / 4;                   // 9
-    constexpr int ITEMS = 4 * C2H * PXG;           // 648
-    for (int item = tid; item < ITEMS; item += 256) {
-      const int cg = item / (C2H * PXG);
-      const int rem = item - cg * (C2H * PXG);
-      const int row = rem / PXG, pg = rem - row * PXG;
-      float acc[4][4];
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int* tab = reinterpret_cast<const int*>(w_s + T2);
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int mt0 = (pass * 8 + warp) * 3;
+      if (mt0 >= 45) break;                       // warp uniform
+      int pa[3][2], row[3][2], col[3][2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int q = 0; q < 3; ++q)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int h = 0; h < 2; ++h) {
+          const int seg = 2 * (mt0 + q) + h;
+          row[q][h] = seg / C2SEG;
+          col[q][h] = 8 * (seg - row[q][h] * C2SEG) + g;
+          pa[q][h] = row[q][h] * P1P + col[q][h];
+        }
+      float acc[3][2][4];
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[q][j][e] = 0.f;
 #pragma unroll 2
-      for (int ci = 0; ci < 10; ++ci)
+      for (int s = 0; s < 12; ++s) {
+        const int o0 = tab[8 * s + t], o1 = tab[8 * s + t + 4];
+        const float4 w = *reinterpret_cast<const float4*>(&w_s[W2 + (s * 32 + lane) * 4]);
+        uint32_t bh[4], bl[4];
+        split_tf32(w.x, bh[0], bl[0]);
+        split_tf32(w.y, bh[1], bl[1]);
+        split_tf32(w.z, bh[2], bl[2]);
+        split_tf32(w.w, bh[3], bl[3]);
+        uint32_t ah[3][4], al[3][4];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const float* ir = &p1_s[(ci * P1H + row + ky) * P1P + 4 * pg];
-          const float4 i0 = *reinterpret_cast<const float4*>(ir);
-          const float2 i1 = *reinterpret_cast<const float2*>(ir + 4);
-          const float in[6] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y};
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const float4 w = *reinterpret_cast<const float4*>(&w_s[W2 + ((ci * 3 + ky) * 3 + kx) * 16 + cg * 4]);
-#pragma unroll
-            for (int px = 0; px < 4; ++px) {
-              acc[px][0] = fmaf(in[px + kx], w.x, acc[px][0]);
-              acc[px][1] = fmaf(in[px + kx], w.y, acc[px][1]);
-              acc[px][2] = fmaf(in[px + kx], w.z, acc[px][2]);
-              acc[px][3] = fmaf(in[px + kx], w.w, acc[px][3]);
-            }
-          }
+        for (int q = 0; q < 3; ++q) {
+          split_tf32(p1_s[pa[q][0] + o0], ah[q][0], al[q][0]);
+          split_tf32(p1_s[pa[q][1] + o0], ah[q][1], al[q][1]);
+          split_tf32(p1_s[pa[q][0] + o1], ah[q][2], al[q][2]);
+          split_tf32(p1_s[pa[q][1] + o1], ah[q][3], al[q][3]);
         }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int co = cg * 4 + j;
-        const float bias = w_s[B2 + co], al = w_s[A2 + co];
-        float4 o;
-        o.x = prelu(acc[0][j] + bias, al);
-        o.y = prelu(acc[1][j] + bias, al);
-        o.z = prelu(acc[2][j] + bias, al);
-        o.w = prelu(acc[3][j] + bias, al);
-        *reinterpret_cast<float4*>(&a_s[(co * C2H + row) * C2P + 4 * pg]) = o;
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) mma_tf32(acc[q][j], al[q], bh[j], bh[2 + j]);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) mma_tf32(acc[q][j], ah[q], bl[j], bl[2 + j]);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) mma_tf32(acc[q][j], ah[q], bh[j], bh[2 + j]);
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        if (mt0 + q >= 45) break;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int co = 8 * j + 2 * t + e;
+            const float bias = w_s[B2 + co], al2 = w_s[A2 + co];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              if (col[q][h] < C2W)
+                a_s[(co * C2H + row[q][h]) * C2P + col[q][h]] = prelu(acc[q][j][2 * h + e] + bias, al2);
+          }
       }
     }
   }
   __syncthreads();
+#ifdef PNET_TIMING
+  tph[3] = clock64();
+#endif
 
   // ---- conv3 (16->32, 3x3) on the tensor pipe + PReLU + heads.
   // warp w owns output rows 2w, 2w+1; one pass = one row = two 16-pixel M tiles x four 8-channel N tiles.
@@ -370,9 +419,43 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
       }
     }
   }
+#ifdef PNET_TIMING
+  tph[4] = clock64();
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) atomicAdd(&g_pnet_phase[i], (unsigned long long)(tph[i + 1] - tph[i]));
+    atomicAdd(&g_pnet_phase[4], 1ull);
+  }
+#endif
 }
 
 }  // namespace pnet
+#ifdef PNET_TIMING
+extern "C" void trl_debug_pnet_timing(unsigned long long* out) {
+  cudaMemcpyFromSymbol(out, pnet::g_pnet_phase, sizeof(unsigned long long) * 8);
+  unsigned long long z[8] = {0};
+  cudaMemcpyToSymbol(pnet::g_pnet_phase, z, sizeof(z));
+}
+#endif
+
+// conv2's K ordering: group G = 2*kstep + (0: a0/a1/b0, 1: a2/a3/b1), slot t = lane % 4.
+//   G < 18 : tap G/2, channels 4*(G%2) + t               (channels 0..7)
+//   G >= 18: kx = (G-18)/2; channels 8,9 x ky 0..2, two zero-weight pads
+// Every group has one kx and four distinct (ci + ky) mod 4 -> four bank octets.  Returns false for the pads.
+static bool conv2_k(int G, int t, int* ci, int* ky, int* kx) {
+  if (G < 18) {
+    const int tap = G / 2;
+    *ci = 4 * (G % 2) + t; *ky = tap / 3; *kx = tap % 3;
+    return true;
+  }
+  *kx = (G - 18) / 2;
+  if ((G - 18) % 2 == 0) {
+    *ci = 8 + (t & 1); *ky = (t < 2) ? 0 : 2;            // (8,0) (9,0) (8,2) (9,2): octets 0,1,2,3
+    return true;
+  }
+  if (t < 2) { *ci = 8 + t; *ky = 1; return true; }       // (8,1) (9,1): octets 1,2
+  *ci = (t == 2) ? 0 : 3; *ky = 0;                        // pads (zero weights): octets 0,3
+  return false;
+}
 
 // upstream layouts -> packed shared-memory image
 int pnet_pack_weights(trl_ctx* c, const float* h, size_t len) {
@@ -395,8 +478,21 @@ int pnet_pack_weights(trl_ctx* c, const float* h, size_t len) {
   for (int co = 0; co < 10; ++co)
     for (int k = 0; k < 27; ++k) pk[W1 + k * 12 + co] = w1[co * 27 + k];
   for (int co = 0; co < 10; ++co) { pk[B1 + co] = b1[co]; pk[A1 + co] = a1[co]; }
-  for (int co = 0; co < 16; ++co)
-    for (int k = 0; k < 90; ++k) pk[W2 + k * 16 + co] = w2[co * 90 + k];
+  // conv2 as mma.m16n8k8 B fragments + the k -> pooled-tile offset table
+  for (int s = 0; s < 12; ++s)
+    for (int lane = 0; lane < 32; ++lane) {
+      const int g = lane >> 2, t = lane & 3;
+      for (int i = 0; i < 2; ++i) {
+        int ci, ky, kx;
+        const bool used = conv2_k(2 * s + i, t, &ci, &ky, &kx);
+        for (int j = 0; j < 2; ++j)
+          pk[W2 + (s * 32 + lane) * 4 + 2 * i + j] = used ? w2[(8 * j + g) * 90 + ci * 9 + ky * 3 + kx] : 0.f;
+        if (g == 0) {
+          const int off = ci * P1PLANE + ky * P1P + kx;
+          memcpy(&pk[T2 + 8 * s + 4 * i + t], &off, sizeof(int));
+        }
+      }
+    }
   for (int co = 0; co < 16; ++co) { pk[B2 + co] = b2[co]; pk[A2 + co] = a2[co]; }
   // conv3 as mma.m16n8k8 B fragments: k-step s = (tap, channel half), k = 8s + t (+4) -> ci = (s&1)*8 + t (+4)
   for (int s = 0; s < 18; ++s)
