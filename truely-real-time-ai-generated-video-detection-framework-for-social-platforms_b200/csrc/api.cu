@@ -75,7 +75,6 @@ void trl_destroy(trl_ctx_t* c) {
   if (c->d_onet) cudaFree(c->d_onet);
   if (c->d_nms_tmp) cudaFree(c->d_nms_tmp);
   if (c->d_pyr_tab) cudaFree(c->d_pyr_tab);
-  if (c->d_bgrx) cudaFree(c->d_bgrx);
   if (c->h_cap) cudaFreeHost(c->h_cap);
   delete c;
 }
@@ -138,7 +137,7 @@ int trl_pyramid(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, floa
   PyramidGeom g;
   int rc = compute_geometry(c->cfg, H, W, &g);
   if (rc != TRL_OK) TRL_FAIL(c, rc, "trl_pyramid: bad geometry %dx%d", H, W);
-  return launch_pyramid(c, d_frames, B, H, W, g, d_out, (cudaStream_t)stream);
+  return launch_pyramid(c, d_frames, B, H, W, g, d_out, false, (cudaStream_t)stream);
 }
 
 int trl_pnet(trl_ctx_t* c, const float* d_in, int B, int hs, int ws, float* d_prob, float* d_reg, void* stream) {
@@ -188,7 +187,7 @@ static int ensure_workspace(trl_ctx* c, int B, int H, int W) {
   const PyramidGeom& g = c->geom;
   const size_t c1 = c->cfg.cand_cap_scale, c2 = c->cfg.cand_cap_frame, c4 = c->cfg.box_cap_frame;
   const int S = c->cfg.crop_size;
-  WS_ALLOC(c->d_pyr, (size_t)Bc * g.px_total * 3 * sizeof(float));
+  WS_ALLOC(c->d_pyr, (size_t)Bc * g.floats_total * sizeof(float));
   WS_ALLOC(c->d_cand1, (size_t)Bc * g.n * c1 * sizeof(Cand));
   WS_ALLOC(c->d_cnt1, (size_t)Bc * (g.n + 3) * sizeof(int));     // cnt1 [B][n] then cnt2 [B], cnt3 [B], cnt4 [B]
   c->d_cnt2 = nullptr;
@@ -223,7 +222,7 @@ static int detect_impl(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W,
   int* cnt3 = cnt2 + B;
   int* cnt4 = cnt3 + B;
   TRL_CUDA(c, cudaMemsetAsync(cnt1, 0, (size_t)B * (g.n + 3) * sizeof(int), s));
-  TIMED(0, launch_pyramid(c, d_frames, B, H, W, g, c->d_pyr, s));
+  TIMED(0, launch_pyramid(c, d_frames, B, H, W, g, c->d_pyr, true, s));
   TIMED(1, launch_pnet_candidates(c, c->d_pyr, B, g, c->cfg.thresholds[0], c->d_cand1, cnt1, c1, s));
 
   nms::StageParams p{};

@@ -34,9 +34,11 @@ struct PyramidGeom {
   double scale[TRL_MAX_SCALES];
   float scale_f[TRL_MAX_SCALES];
   int hs[TRL_MAX_SCALES], ws[TRL_MAX_SCALES];   // resampled image size
+  int pitch[TRL_MAX_SCALES];                    // row pitch (floats) of level k in the cascade's pyramid buffer: ws rounded up to 4
   int oh[TRL_MAX_SCALES], ow[TRL_MAX_SCALES];   // P-Net output map size
   long long off[TRL_MAX_SCALES];                // float offset of level k in the pyramid buffer, per frame count B: off*B
   long long px_total;                           // sum hs*ws
+  long long floats_total;                       // floats per frame of the padded pyramid buffer: sum 3*hs*pitch
 };
 
 // kernel-parameter view of the pyramid (passed by value)
@@ -47,7 +49,8 @@ struct PyrParams {
   float scale[TRL_MAX_SCALES];
   long long off[TRL_MAX_SCALES];       // float offset (already multiplied by B) of level k
   int blk_start[TRL_MAX_SCALES + 1];   // prefix of work blocks per level (kernel specific)
-  int grp[TRL_MAX_SCALES];             // log2(lanes cooperating per output pixel) (pyramid kernel)
+  int pitch[TRL_MAX_SCALES];           // output row pitch in floats (pyramid kernel)
+  int rows[TRL_MAX_SCALES];            // output rows per CTA (pyramid kernel)
   int tab_off[TRL_MAX_SCALES];         // offset of level k's window tables
 };
 
@@ -89,8 +92,7 @@ struct trl_ctx {
   int ws_B = 0, ws_H = 0, ws_W = 0;
   PyramidGeom geom{};
   float* d_pyr = nullptr;
-  uint32_t* d_bgrx = nullptr;    // BGRx (4 B / pixel) copy of the current batch, read by the pyramid kernel
-  size_t bgrx_cap = 0;
+  size_t pyr_smem_set = 0;       // dynamic shared memory the pyramid kernel has been opted in to
   int* d_pyr_tab = nullptr;      // adaptive-average window tables of the current frame shape
   int pyr_tab_H = 0, pyr_tab_W = 0;
   int pyr_tab_off[TRL_MAX_SCALES] = {0};
@@ -153,7 +155,7 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 int compute_geometry(const trl_config_t& cfg, int H, int W, PyramidGeom* g);
 
 int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const PyramidGeom& g, float* d_out,
-                   cudaStream_t s);
+                   bool padded, cudaStream_t s);
 int launch_crop_resample(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const int* d_pad, const int* d_img,
                          const int* d_count, int n_max, int size, float* d_out, cudaStream_t s);
 int launch_crop_align(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,

@@ -53,8 +53,8 @@ constexpr int SMEM_FLOATS = WTOTAL + SM_A + SM_P1;
 constexpr int SMEM_BYTES = SMEM_FLOATS * 4;   // ~100 KB -> 2 CTAs / SM
 
 struct Level {
-  const float* in;     // [B][3][hs][ws]
-  int hs, ws, oh, ow;
+  const float* in;     // [B][3][hs][pitch]
+  int hs, ws, pitch, oh, ow;
   int tiles_x, tiles;  // tiles per frame
   float scale;
   float* prob;         // optional maps
@@ -116,18 +116,33 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
     const uint32_t w_dst = (uint32_t)__cvta_generic_to_shared(w_s);
     for (int i = tid; i < WTOTAL / 4; i += 256)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(w_dst + 16u * i), "l"(wpacked + 4 * i) : "memory");
-    const float* src = L.in + (size_t)b * 3 * hs * ws;
+    const int pitch = L.pitch;
+    const float* src = L.in + (size_t)b * 3 * hs * pitch;
     const int iy0 = 2 * oy0, ix0 = 2 * ox0;
     const uint32_t a_dst = (uint32_t)__cvta_generic_to_shared(a_s);
-    for (int i = tid; i < 3 * INH * INW; i += 256) {
-      const int ci = i / (INH * INW);
-      const int r = (i - ci * INH * INW) / INW;
-      const int cx = i - ci * INH * INW - r * INW;
-      const int gy = iy0 + r, gx = ix0 + cx;
-      const bool ok = gy < hs && gx < ws;
-      const float* gp = ok ? src + ((size_t)ci * hs + gy) * ws + gx : src;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
-                   ::"r"(a_dst + 4u * ((ci * INH + r) * INP + cx)), "l"(gp), "r"(ok ? 4 : 0) : "memory");
+    if ((pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(L.in) & 15) == 0) {
+      // 16-byte rows (the cascade's padded pyramid): 19 chunks per tile row, partial chunks zero filled by src-size
+      constexpr int CH = INP / 4;
+      for (int i = tid; i < 3 * INH * CH; i += 256) {
+        const int rr = i / CH, j = i - rr * CH;          // rr = ci * INH + r
+        const int ci = rr / INH, r = rr - ci * INH;
+        const int gy = iy0 + r, gx = ix0 + 4 * j;
+        const int nb = gy < hs ? min(max(ws - gx, 0), 4) * 4 : 0;
+        const float* gp = nb ? src + ((size_t)ci * hs + gy) * pitch + gx : src;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                     ::"r"(a_dst + 16u * (uint32_t)i), "l"(gp), "r"(nb) : "memory");
+      }
+    } else {
+      for (int i = tid; i < 3 * INH * INW; i += 256) {
+        const int ci = i / (INH * INW);
+        const int r = (i - ci * INH * INW) / INW;
+        const int cx = i - ci * INH * INW - r * INW;
+        const int gy = iy0 + r, gx = ix0 + cx;
+        const bool ok = gy < hs && gx < ws;
+        const float* gp = ok ? src + ((size_t)ci * hs + gy) * pitch + gx : src;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
+                     ::"r"(a_dst + 4u * ((ci * INH + r) * INP + cx)), "l"(gp), "r"(ok ? 4 : 0) : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   }
@@ -522,7 +537,7 @@ int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float
   Params p{};
   p.n_levels = 1;
   Level& L = p.lv[0];
-  L.in = d_in; L.hs = hs; L.ws = ws;
+  L.in = d_in; L.hs = hs; L.ws = ws; L.pitch = ws;
   L.oh = (hs - 2 + 1) / 2 - 4; L.ow = (ws - 2 + 1) / 2 - 4;
   if (L.oh <= 0 || L.ow <= 0) TRL_FAIL(c, TRL_E_INVALID, "pnet input %dx%d too small", hs, ws);
   L.tiles_x = ceil_div(L.ow, TOX);
@@ -544,7 +559,7 @@ int launch_pnet_candidates(trl_ctx* c, const float* d_pyr, int B, const PyramidG
   for (int k = 0; k < g.n; ++k) {
     Level& L = p.lv[k];
     L.in = d_pyr + g.off[k] * B;
-    L.hs = g.hs[k]; L.ws = g.ws[k]; L.oh = g.oh[k]; L.ow = g.ow[k];
+    L.hs = g.hs[k]; L.ws = g.ws[k]; L.pitch = g.pitch[k]; L.oh = g.oh[k]; L.ow = g.ow[k];
     L.tiles_x = ceil_div(L.ow, TOX);
     L.tiles = L.tiles_x * ceil_div(L.oh, TOY);
     L.scale = g.scale_f[k];

@@ -30,45 +30,6 @@ __device__ __forceinline__ void window_sum(const uint8_t* __restrict__ frame, in
   }
 }
 
-// Same sum over a BGRx (4 bytes / pixel) copy of the frame: one aligned 32-bit load per pixel instead of three byte
-// loads (the LSU issue rate, not bandwidth, bounds these kernels), channels accumulated two at a time in 16-bit lanes.
-// A lane adds at most ceil(kw/grp) <= 5 pixels per row, far below the 257 that would overflow a 16-bit lane.
-__device__ __forceinline__ void window_sum_x(const uint32_t* __restrict__ frame, int W, int y0, int y1, int x0, int x1,
-                                             int sub, int grp, int& s0, int& s1, int& s2) {
-  s0 = s1 = s2 = 0;
-  for (int y = y0; y < y1; ++y) {
-    const uint32_t* row = frame + (size_t)y * W;
-    uint32_t a = 0, b = 0;
-    for (int x = x0 + sub; x < x1; x += grp) {
-      const uint32_t w = __ldg(row + x);
-      a += w & 0x00FF00FFu;          // B | R<<16
-      b += (w >> 8) & 0x00FF00FFu;   // G | x<<16
-    }
-    s0 += (int)(a & 0xFFFFu);
-    s2 += (int)(a >> 16);
-    s1 += (int)(b & 0xFFFFu);
-  }
-}
-
-// flat [n_px] BGR bytes -> BGRx words, 4 pixels (12 B in, 16 B out) per thread
-__global__ void __launch_bounds__(256) bgr_to_bgrx_kernel(const uint8_t* __restrict__ in, uint32_t* __restrict__ out, size_t n_px) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t p = i * 4;
-  if (p + 3 < n_px) {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(in + p * 3);
-    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
-    uint4 o;
-    o.x = w0 & 0x00FFFFFFu;
-    o.y = ((w0 >> 24) | (w1 << 8)) & 0x00FFFFFFu;
-    o.z = ((w1 >> 16) | (w2 << 16)) & 0x00FFFFFFu;
-    o.w = w2 >> 8;
-    *reinterpret_cast<uint4*>(out + p) = o;
-  } else {
-    for (size_t q = p; q < n_px; ++q)
-      out[q] = (uint32_t)in[q * 3] | ((uint32_t)in[q * 3 + 1] << 8) | ((uint32_t)in[q * 3 + 2] << 16);
-  }
-}
-
 __device__ __forceinline__ float area_norm(int s, int kh, int kw) {
   float v = __fdiv_rn(__fdiv_rn((float)s, (float)kh), (float)kw);
   return __fmul_rn(__fsub_rn(v, 127.5f), 0.0078125f);
@@ -76,110 +37,102 @@ __device__ __forceinline__ float area_norm(int s, int kh, int kw) {
 
 // ----------------------------------------------------------------------------- K1 pyramid
 
-// Window tables (host computed once per frame shape): for level k, tab + tab_off[k] holds
-// x0[ws], x1[ws], y0[hs], y1[hs]  -- no integer division on the device.
-// One block = (level, tile of PYR_ROWS output rows, tile of 256/grp output columns); grid.y = frame.
-// `grp` lanes (1..32, a power of two chosen from the window width) cooperate on one output pixel, so both the
-// 2x2 windows of the finest level and the ~100x100 windows of the coarsest one stay coalesced.
-constexpr int PYR_ROWS = 8;
+// Separable exact area resample.  Window tables (host computed once per frame shape): for level k,
+// tab + tab_off[k] holds x0[ws], x1[ws], y0[hs], y1[hs] -- no integer division on the device.
+//
+// One CTA = (frame, level, R consecutive output rows).
+//  pass 1 (vertical): the source rows are read as a flat array of 32-bit words straight from the packed BGR bytes
+//    (no BGRx staging copy): a thread owns word columns q, q+256, ... and adds the bytes of rows [y0, y1) in two
+//    registers of 2 x 16-bit lanes (even / odd bytes).  Integer sums are exact in any order.  The column sums go to
+//    shared memory as a u16 array indexed by byte column.  Coalesced 128 B per warp per row, 4 rows in flight.
+//  pass 2 (horizontal): one thread per output pixel adds its kw column sums per channel, divides (s / kh) / kw exactly
+//    like ATen's adaptive_avg_pool2d, normalises and stores planar fp32 (coalesced along x).
+// A 16-bit lane holds at most 255 * kh, so kh <= 257 (frames up to ~4000 px on the short side with minsize 20).
+constexpr int PYR_MAX_KH = 257;
 
-__global__ void __launch_bounds__(256) pyramid_kernel(const uint32_t* __restrict__ frames, int H, int W, PyrParams p,
-                                                     int lvl_first, const int* __restrict__ tab, float* __restrict__ out) {
-  int lvl = lvl_first;
+template <bool ALIGNED>
+__device__ __forceinline__ uint32_t load_word(const uint8_t* __restrict__ frames, size_t byte_off, size_t total_bytes) {
+  if (ALIGNED) return __ldg(reinterpret_cast<const uint32_t*>(frames + byte_off));
+  // frames is 4-byte aligned; the word may straddle two aligned words and the batch may end inside it
+  const size_t a = byte_off & ~(size_t)3;
+  const uint32_t sh = (uint32_t)(byte_off & 3) * 8u;
+  if (a + 8 <= total_bytes) {
+    const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(frames + a));
+    const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(frames + a + 4));
+    return __funnelshift_r(w0, w1, sh);
+  }
+  uint32_t v = 0;
+  for (int i = 0; i < 4; ++i)
+    if (byte_off + i < total_bytes) v |= (uint32_t)__ldg(frames + byte_off + i) << (8 * i);
+  return v;
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restrict__ frames, int H, int W, size_t total_bytes,
+                                                         const __grid_constant__ PyrParams p, const int* __restrict__ tab,
+                                                         float* __restrict__ out) {
+  extern __shared__ __align__(16) uint32_t vs[];      // [R][nw] x 2 words = u16 column sums [R][4*nw]
+  int lvl = 0;
   while (lvl + 1 < p.n && (int)blockIdx.x >= p.blk_start[lvl + 1]) ++lvl;
-  const int hs = p.hs[lvl], ws = p.ws[lvl];
-  const int gsh = p.grp[lvl];                        // log2(lanes per pixel)
-  const int grp = 1 << gsh;
-  const int px_per_blk = 256 >> gsh;
-  const int col_tiles = (ws + px_per_blk - 1) / px_per_blk;
-  const int local = (int)blockIdx.x - p.blk_start[lvl];
-  const int rt = local / col_tiles, ct = local - rt * col_tiles;
+  const int hs = p.hs[lvl], ws = p.ws[lvl], R = p.rows[lvl];
+  const int j0 = ((int)blockIdx.x - p.blk_start[lvl]) * R;
+  const int nrows = min(R, hs - j0);
   const int b = blockIdx.y;
-  const int ox = ct * px_per_blk + ((int)threadIdx.x >> gsh);
-  const int sub = threadIdx.x & (grp - 1);
+  const int rowbytes = 3 * W;
+  const int nw = (rowbytes + 3) >> 2;
   const int* t = tab + p.tab_off[lvl];
-  const bool vx = ox < ws;
-  int x0 = 0, x1 = 0;
-  if (vx) { x0 = __ldg(t + ox); x1 = __ldg(t + ws + ox); }
-  const int kw = x1 - x0;
-  const uint32_t* frame = frames + (size_t)b * H * W;
-  const size_t plane = (size_t)hs * ws;
-  float* obase = out + p.off[lvl] + (size_t)b * 3 * plane;
-  const int oy_end = min(hs, (rt + 1) * PYR_ROWS);
-  for (int oy = rt * PYR_ROWS; oy < oy_end; ++oy) {
-    const int y0 = __ldg(t + 2 * ws + oy), y1 = __ldg(t + 2 * ws + hs + oy);
-    int s0 = 0, s1 = 0, s2 = 0;
-    if (vx) window_sum_x(frame, W, y0, y1, x0, x1, sub, grp, s0, s1, s2);
-    for (int o = grp >> 1; o > 0; o >>= 1) {   // grp divides 32: groups never straddle a warp
-      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (vx && sub == 0) {
-      float* o = obase + (size_t)oy * ws + ox;
-      const int kh = y1 - y0;
-      o[0] = area_norm(s0, kh, kw);
-      o[plane] = area_norm(s1, kh, kw);
-      o[2 * plane] = area_norm(s2, kh, kw);
-    }
-  }
-}
+  const int* ty0 = t + 2 * ws;
+  const int* ty1 = ty0 + hs;
+  const size_t fbase = (size_t)b * H * rowbytes;
+  const int tid = threadIdx.x;
 
-
-// Fine levels (window at most WMAX x WMAX): one thread per output pixel, fully unrolled predicated window, 32-bit
-// index arithmetic.  The generic lane-cooperative kernel above spends most of its instructions on loop control when
-// the windows are 2x2..8x8, and these levels hold > 95 % of the pyramid's pixels.
-template <int WMAX>
-__global__ void __launch_bounds__(256) pyramid_fine_kernel(const uint32_t* __restrict__ frames, int H, int W, PyrParams p,
-                                                          int lvl_first, int blk_first, const int* __restrict__ tab,
-                                                          float* __restrict__ out) {
-  int lvl = lvl_first;
-  const int bx = (int)blockIdx.x + blk_first;
-  while (lvl + 1 < p.n && bx >= p.blk_start[lvl + 1]) ++lvl;
-  const int hs = p.hs[lvl], ws = p.ws[lvl];
-  const int col_tiles = (ws + 255) >> 8;
-  const int local = bx - p.blk_start[lvl];
-  const int rt = local / col_tiles, ct = local - rt * col_tiles;
-  const int ox = ct * 256 + (int)threadIdx.x;
-  if (ox >= ws) return;
-  const int* t = tab + p.tab_off[lvl];
-  const int x0 = __ldg(t + ox), kw = __ldg(t + ws + ox) - x0;
-  const uint32_t* frame = frames + (size_t)blockIdx.y * H * W;
-  const int plane = hs * ws;
-  float* obase = out + p.off[lvl] + (size_t)blockIdx.y * 3 * plane + ox;
-  const float fkw = (float)kw;
-  const int oy_end = min(hs, (rt + 1) * PYR_ROWS);
-  for (int oy = rt * PYR_ROWS; oy < oy_end; ++oy) {
-    const int y0 = __ldg(t + 2 * ws + oy), kh = __ldg(t + 2 * ws + hs + oy) - y0;
-    const uint32_t* wp = frame + (y0 * W + x0);
-    uint32_t a = 0, b = 0;
-#pragma unroll
-    for (int dy = 0; dy < WMAX; ++dy) {
-      if (dy < kh) {
-#pragma unroll
-        for (int dx = 0; dx < WMAX; ++dx) {
-          if (dx < kw) {
-            const uint32_t w = __ldg(wp + dy * W + dx);
-            a += w & 0x00FF00FFu;
-            b += (w >> 8) & 0x00FF00FFu;
-          }
-        }
+  for (int jj = 0; jj < nrows; ++jj) {
+    const int y0 = __ldg(ty0 + j0 + jj), y1 = __ldg(ty1 + j0 + jj);
+    uint2* vrow = reinterpret_cast<uint2*>(vs) + (size_t)jj * nw;
+    for (int q = tid; q < nw; q += 256) {
+      uint32_t ae = 0, ao = 0;
+      size_t off = fbase + (size_t)y0 * rowbytes + 4 * (size_t)q;
+      int y = y0;
+      for (; y + 4 <= y1; y += 4) {
+        const uint32_t w0 = load_word<ALIGNED>(frames, off, total_bytes);
+        const uint32_t w1 = load_word<ALIGNED>(frames, off + rowbytes, total_bytes);
+        const uint32_t w2 = load_word<ALIGNED>(frames, off + 2 * (size_t)rowbytes, total_bytes);
+        const uint32_t w3 = load_word<ALIGNED>(frames, off + 3 * (size_t)rowbytes, total_bytes);
+        ae += (w0 & 0x00FF00FFu) + (w1 & 0x00FF00FFu) + (w2 & 0x00FF00FFu) + (w3 & 0x00FF00FFu);
+        ao += __byte_perm(w0, 0, 0x4341) + __byte_perm(w1, 0, 0x4341) + __byte_perm(w2, 0, 0x4341) + __byte_perm(w3, 0, 0x4341);
+        off += 4 * (size_t)rowbytes;
       }
+      for (; y < y1; ++y) {
+        const uint32_t w0 = load_word<ALIGNED>(frames, off, total_bytes);
+        ae += w0 & 0x00FF00FFu;
+        ao += __byte_perm(w0, 0, 0x4341);
+        off += rowbytes;
+      }
+      // bytes (0,2) live in ae, (1,3) in ao -> u16 sums in byte order
+      vrow[q] = make_uint2(__byte_perm(ae, ao, 0x5410), __byte_perm(ae, ao, 0x7632));
     }
-    // WMAX*WMAX <= 64 pixels: the 16-bit lanes cannot overflow
-    const float fkh = (float)kh;
-    float* o = obase + oy * ws;
-    o[0] = __fmul_rn(__fsub_rn(__fdiv_rn(__fdiv_rn((float)(a & 0xFFFFu), fkh), fkw), 127.5f), 0.0078125f);
-    o[plane] = __fmul_rn(__fsub_rn(__fdiv_rn(__fdiv_rn((float)(b & 0xFFFFu), fkh), fkw), 127.5f), 0.0078125f);
-    o[2 * plane] = __fmul_rn(__fsub_rn(__fdiv_rn(__fdiv_rn((float)(a >> 16), fkh), fkw), 127.5f), 0.0078125f);
   }
-}
+  __syncthreads();
 
-static int pick_group_log2(int in_extent, int out_extent) {
-  int kw = (in_extent + out_extent - 1) / out_extent + 1;   // upper bound of the window width
-  int g = 0;
-  while (g < 5 && (2 << g) <= kw) ++g;
-  return g;
+  const uint16_t* v16 = reinterpret_cast<const uint16_t*>(vs);
+  const int pitch = p.pitch[lvl];
+  const size_t plane = (size_t)hs * pitch;
+  float* obase = out + p.off[lvl] + (size_t)b * 3 * plane;
+  const int items = nrows * ws;
+  for (int item = tid; item < items; item += 256) {
+    const int jj = item / ws, i = item - jj * ws;
+    const int x0 = __ldg(t + i), x1 = __ldg(t + ws + i);
+    const int kh = __ldg(ty1 + j0 + jj) - __ldg(ty0 + j0 + jj);
+    const uint16_t* vp = v16 + (size_t)jj * (4 * nw) + 3 * x0;
+    int s0 = 0, s1 = 0, s2 = 0;
+    for (int x = x0; x < x1; ++x, vp += 3) { s0 += vp[0]; s1 += vp[1]; s2 += vp[2]; }
+    float* o = obase + (size_t)(j0 + jj) * pitch + i;
+    const int kw = x1 - x0;
+    o[0] = area_norm(s0, kh, kw);
+    o[plane] = area_norm(s1, kh, kw);
+    o[2 * plane] = area_norm(s2, kh, kw);
+  }
+  // pad columns [ws, pitch) stay untouched: readers clip at ws
 }
 
 // adaptive_avg_pool2d windows: [floor(i*In/Out), ceil((i+1)*In/Out))
@@ -192,8 +145,10 @@ static void window_table(int In, int Out, std::vector<int>& v) {
   }
 }
 
+// `padded`: rows at g.pitch[k] floats and levels at g.off[k]*B (the cascade's internal layout, 16-byte aligned rows
+// for P-Net's cp.async staging); otherwise the compact layout of the trl_pyramid stage entry point.
 int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const PyramidGeom& g, float* d_out,
-                   cudaStream_t s) {
+                   bool padded, cudaStream_t s) {
   if (g.n == 0 || B == 0) return TRL_OK;
   // tables are cached per frame shape
   if (c->pyr_tab_H != H || c->pyr_tab_W != W || c->d_pyr_tab == nullptr) {
@@ -209,58 +164,44 @@ int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, con
     c->pyr_tab_H = H;
     c->pyr_tab_W = W;
   }
-  // Levels are launched by class: fine levels (max window <= 3 / 4 / 6 / 8) with the unrolled one-thread-per-pixel
-  // kernel, the coarse rest with the lane-cooperative kernel.  blk_start is a prefix over the levels of one class.
+  if ((reinterpret_cast<uintptr_t>(d_frames) & 3) != 0) TRL_FAIL(c, TRL_E_INVALID, "frames pointer must be 4-byte aligned");
+  const int nw = (3 * W + 3) / 4;
   PyrParams p{};
   p.n = g.n;
-  int cls[TRL_MAX_SCALES];
+  int blocks = 0, rmax = 1;
+  long long off = 0;
   for (int k = 0; k < g.n; ++k) {
+    const int kh = (H + g.hs[k] - 1) / g.hs[k] + 1;
+    if (kh > PYR_MAX_KH) TRL_FAIL(c, TRL_E_INVALID, "pyramid window of %d rows exceeds %d (frame %dx%d)", kh, PYR_MAX_KH, H, W);
     p.hs[k] = g.hs[k];
     p.ws[k] = g.ws[k];
-    p.off[k] = g.off[k] * B;
-    p.grp[k] = pick_group_log2(W, g.ws[k]);
+    p.pitch[k] = padded ? g.pitch[k] : g.ws[k];
+    p.off[k] = padded ? g.off[k] * B : off * B;
+    off += 3LL * g.hs[k] * g.ws[k];
     p.tab_off[k] = c->pyr_tab_off[k];
-    const int wmax = std::max((W + g.ws[k] - 1) / g.ws[k], (H + g.hs[k] - 1) / g.hs[k]) + 1;
-    cls[k] = wmax <= 3 ? 3 : wmax <= 4 ? 4 : wmax <= 6 ? 6 : wmax <= 8 ? 8 : 0;
+    // rows per CTA: about 8-12 source rows of work, bounded by 64 KB of column sums
+    int R = (int)(8.0 * g.hs[k] / H);
+    R = std::max(1, std::min(R, 4));
+    while (R > 1 && (size_t)R * nw * 8 > 64 * 1024) --R;
+    p.rows[k] = R;
+    rmax = std::max(rmax, R);
+    p.blk_start[k] = blocks;
+    blocks += ceil_div(g.hs[k], R);
   }
-  // BGR -> BGRx staging copy (frames are addressed flat, so any H*W*3 works as long as the batch base pointer is
-  // 4-byte aligned; cudaMalloc / torch allocations are 256-byte aligned)
-  const size_t n_px = (size_t)B * H * W;
-  if ((reinterpret_cast<uintptr_t>(d_frames) & 3) != 0) TRL_FAIL(c, TRL_E_INVALID, "frames pointer must be 4-byte aligned");
-  if (c->bgrx_cap < n_px) {
-    if (c->d_bgrx) { TRL_CUDA(c, cudaFree(c->d_bgrx)); c->d_bgrx = nullptr; }
-    TRL_CUDA(c, cudaMalloc(&c->d_bgrx, n_px * sizeof(uint32_t)));
-    c->bgrx_cap = n_px;
+  for (int q = g.n; q <= TRL_MAX_SCALES; ++q) p.blk_start[q] = blocks;
+  const size_t smem = (size_t)rmax * nw * 8;
+  if (smem > 200 * 1024) TRL_FAIL(c, TRL_E_INVALID, "frame width %d too large for the pyramid kernel", W);
+  const size_t total = (size_t)B * H * W * 3;
+  const bool aligned = (3 * W) % 4 == 0;
+  if (smem > c->pyr_smem_set) {
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    c->pyr_smem_set = smem;
   }
-  bgr_to_bgrx_kernel<<<(unsigned)((n_px / 4 + 1 + 255) / 256), 256, 0, s>>>(d_frames, c->d_bgrx, n_px);
+  dim3 grid(blocks, B);
+  if (aligned) pyramid_sep_kernel<true><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out);
+  else pyramid_sep_kernel<false><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out);
   TRL_LAUNCH_CHECK(c);
-  // levels are ordered fine -> coarse, so each class is a contiguous run of levels
-  int k = 0;
-  while (k < g.n) {
-    const int cl = cls[k];
-    int k1 = k;
-    int blocks = 0;
-    while (k1 < g.n && cls[k1] == cl) {
-      p.blk_start[k1] = blocks;
-      blocks += cl ? ceil_div(g.hs[k1], PYR_ROWS) * ceil_div(g.ws[k1], 256)
-                   : ceil_div(g.hs[k1], PYR_ROWS) * ceil_div(g.ws[k1], 256 >> p.grp[k1]);
-      ++k1;
-    }
-    for (int q = k1; q <= g.n; ++q) p.blk_start[q] = blocks;      // sentinel for the level search
-    PyrParams pc = p;
-    // the level search in the kernels walks from the first level of the class: hide the finer ones
-    for (int q = 0; q < k; ++q) pc.blk_start[q] = -1;
-    dim3 grid(blocks, B);
-    switch (cl) {
-      case 3: pyramid_fine_kernel<3><<<grid, 256, 0, s>>>(c->d_bgrx, H, W, pc, k, 0, c->d_pyr_tab, d_out); break;
-      case 4: pyramid_fine_kernel<4><<<grid, 256, 0, s>>>(c->d_bgrx, H, W, pc, k, 0, c->d_pyr_tab, d_out); break;
-      case 6: pyramid_fine_kernel<6><<<grid, 256, 0, s>>>(c->d_bgrx, H, W, pc, k, 0, c->d_pyr_tab, d_out); break;
-      case 8: pyramid_fine_kernel<8><<<grid, 256, 0, s>>>(c->d_bgrx, H, W, pc, k, 0, c->d_pyr_tab, d_out); break;
-      default: pyramid_kernel<<<grid, 256, 0, s>>>(c->d_bgrx, H, W, pc, k, c->d_pyr_tab, d_out); break;
-    }
-    TRL_LAUNCH_CHECK(c);
-    k = k1;
-  }
   return TRL_OK;
 }
 
@@ -430,6 +371,7 @@ int launch_crop_align(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, 
 int compute_geometry(const trl_config_t& cfg, int H, int W, PyramidGeom* g) {
   g->n = 0;
   g->px_total = 0;
+  g->floats_total = 0;
   if (H <= 0 || W <= 0 || cfg.min_face_size <= 0) return TRL_E_INVALID;
   const double m = 12.0 / (double)cfg.min_face_size;
   double minl = (double)(H < W ? H : W) * m;
@@ -444,9 +386,11 @@ int compute_geometry(const trl_config_t& cfg, int H, int W, PyramidGeom* g) {
     g->ws[k] = (int)((double)W * scale_i + 1.0);
     g->oh[k] = (g->hs[k] - 2 + 1) / 2 - 4;
     g->ow[k] = (g->ws[k] - 2 + 1) / 2 - 4;
+    g->pitch[k] = (g->ws[k] + 3) & ~3;               // rows padded to 16 bytes (internal cascade layout)
     g->off[k] = off;
-    off += 3LL * g->hs[k] * g->ws[k];
+    off += 3LL * g->hs[k] * g->pitch[k];
     g->px_total += (long long)g->hs[k] * g->ws[k];
+    g->floats_total = off;
     scale_i = scale_i * cfg.factor;
     minl = minl * cfg.factor;
   }
