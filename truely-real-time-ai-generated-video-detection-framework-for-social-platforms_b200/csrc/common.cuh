@@ -51,6 +51,7 @@ struct PyrParams {
   int blk_start[TRL_MAX_SCALES + 1];   // prefix of work blocks per level (kernel specific)
   int pitch[TRL_MAX_SCALES];           // output row pitch in floats (pyramid kernel)
   int rows[TRL_MAX_SCALES];            // output rows per CTA (pyramid kernel)
+  int fastdiv[TRL_MAX_SCALES];         // 1: the verified 3-instruction division may be used for this level
   int tab_off[TRL_MAX_SCALES];         // offset of level k's window tables
 };
 
@@ -96,6 +97,7 @@ struct trl_ctx {
   int* d_pyr_tab = nullptr;      // adaptive-average window tables of the current frame shape
   int pyr_tab_H = 0, pyr_tab_W = 0;
   int pyr_tab_off[TRL_MAX_SCALES] = {0};
+  int pyr_fastdiv[TRL_MAX_SCALES] = {0};
   Cand* d_cand1 = nullptr;       // [B][n_scales][cand_cap_scale]   P-Net candidates
   int* d_cnt1 = nullptr;         // [B][n_scales]
   Cand* d_cand2 = nullptr;       // [B][cand_cap_frame]             after per-scale NMS

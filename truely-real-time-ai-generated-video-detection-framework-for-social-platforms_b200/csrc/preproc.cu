@@ -9,6 +9,7 @@
 //    vertical pass ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2; x coefficients are clamped at the
 //    borders, y rows are clipped instead (coefficients kept) -- bit exact with OpenCV.
 #include <algorithm>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -38,17 +39,45 @@ __device__ __forceinline__ float area_norm(int s, int kh, int kw) {
 // ----------------------------------------------------------------------------- K1 pyramid
 
 // Separable exact area resample.  Window tables (host computed once per frame shape): for level k,
-// tab + tab_off[k] holds x0[ws], x1[ws], y0[hs], y1[hs] -- no integer division on the device.
+// tab + tab_off[k] holds xw[ws] = x0 | kw << 16, rkw[ws] = bits of RN(1 / kw), y0[hs], y1[hs] -- no integer
+// division on the device.
 //
 // One CTA = (frame, level, R consecutive output rows).
 //  pass 1 (vertical): the source rows are read as a flat array of 32-bit words straight from the packed BGR bytes
-//    (no BGRx staging copy): a thread owns word columns q, q+256, ... and adds the bytes of rows [y0, y1) in two
-//    registers of 2 x 16-bit lanes (even / odd bytes).  Integer sums are exact in any order.  The column sums go to
-//    shared memory as a u16 array indexed by byte column.  Coalesced 128 B per warp per row, 4 rows in flight.
+//    (no BGRx staging copy): a thread owns word columns tid, tid+256, tid+512, tid+768 of a 1024-word chunk and adds
+//    the bytes of rows [y0, y1) in two registers of 2 x 16-bit lanes each (even / odd bytes); the four loads of a row
+//    are independent.  Integer sums are exact in any order.  The column sums go to shared memory as a u16 array indexed
+//    by byte column.  Coalesced 128 B per warp and row.
 //  pass 2 (horizontal): one thread per output pixel adds its kw column sums per channel, divides (s / kh) / kw exactly
 //    like ATen's adaptive_avg_pool2d, normalises and stores planar fp32 (coalesced along x).
 // A 16-bit lane holds at most 255 * kh, so kh <= 257 (frames up to ~4000 px on the short side with minsize 20).
+//
+// Division: a / b with b a small integer, r = RN(1/b): q0 = RN(a r), e = a - q0 b (exact, FMA), q = RN(q0 + e r)
+// (Markstein's correction step, 3 instructions).  It equals the IEEE quotient for every operand this kernel can see:
+// div_verify_kernel checks all s in [0, 255 kh kw] for every (kh, kw) pair of a level against __fdiv_rn when the
+// tables are built, and a level that failed would use __fdiv_rn instead (p.fastdiv).
 constexpr int PYR_MAX_KH = 257;
+
+__device__ __forceinline__ float div_small(float a, float b, float r) {
+  const float q0 = __fmul_rn(a, r);
+  const float e = __fmaf_rn(-q0, b, a);
+  return __fmaf_rn(e, r, q0);
+}
+
+// pairs: int2 (kh, kw); bad[pair] set when the fast division differs from IEEE for some window sum
+__global__ void __launch_bounds__(256) div_verify_kernel(const int2* __restrict__ pairs, int* __restrict__ bad) {
+  const int2 k = pairs[blockIdx.y];
+  const float fkh = (float)k.x, fkw = (float)k.y;
+  const float rkh = __frcp_rn(fkh), rkw = __frcp_rn(fkw);
+  const int n = 255 * k.x * k.y;
+  bool ok = true;
+  for (int s = blockIdx.x * 256 + threadIdx.x; s <= n; s += gridDim.x * 256) {
+    const float ref = __fdiv_rn(__fdiv_rn((float)s, fkh), fkw);
+    const float got = div_small(div_small((float)s, fkh, rkh), fkw, rkw);
+    ok = ok && (__float_as_uint(ref) == __float_as_uint(got));
+  }
+  if (!ok) bad[blockIdx.y] = 1;
+}
 
 template <bool ALIGNED>
 __device__ __forceinline__ uint32_t load_word(const uint8_t* __restrict__ frames, size_t byte_off, size_t total_bytes) {
@@ -81,68 +110,150 @@ __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restr
   const int rowbytes = 3 * W;
   const int nw = (rowbytes + 3) >> 2;
   const int* t = tab + p.tab_off[lvl];
-  const int* ty0 = t + 2 * ws;
+  const int* ty0 = t + 2 * ws + j0;
   const int* ty1 = ty0 + hs;
   const size_t fbase = (size_t)b * H * rowbytes;
   const int tid = threadIdx.x;
 
-  for (int jj = 0; jj < nrows; ++jj) {
-    const int y0 = __ldg(ty0 + j0 + jj), y1 = __ldg(ty1 + j0 + jj);
-    uint2* vrow = reinterpret_cast<uint2*>(vs) + (size_t)jj * nw;
-    for (int q = tid; q < nw; q += 256) {
-      uint32_t ae = 0, ao = 0;
-      size_t off = fbase + (size_t)y0 * rowbytes + 4 * (size_t)q;
-      int y = y0;
-      for (; y + 4 <= y1; y += 4) {
-        const uint32_t w0 = load_word<ALIGNED>(frames, off, total_bytes);
-        const uint32_t w1 = load_word<ALIGNED>(frames, off + rowbytes, total_bytes);
-        const uint32_t w2 = load_word<ALIGNED>(frames, off + 2 * (size_t)rowbytes, total_bytes);
-        const uint32_t w3 = load_word<ALIGNED>(frames, off + 3 * (size_t)rowbytes, total_bytes);
-        ae += (w0 & 0x00FF00FFu) + (w1 & 0x00FF00FFu) + (w2 & 0x00FF00FFu) + (w3 & 0x00FF00FFu);
-        ao += __byte_perm(w0, 0, 0x4341) + __byte_perm(w1, 0, 0x4341) + __byte_perm(w2, 0, 0x4341) + __byte_perm(w3, 0, 0x4341);
-        off += 4 * (size_t)rowbytes;
-      }
-      for (; y < y1; ++y) {
-        const uint32_t w0 = load_word<ALIGNED>(frames, off, total_bytes);
-        ae += w0 & 0x00FF00FFu;
-        ao += __byte_perm(w0, 0, 0x4341);
-        off += rowbytes;
+  for (int c0 = 0; c0 < nw; c0 += 1024) {
+    const int q = c0 + tid;
+    const bool v0 = q < nw, v1 = q + 256 < nw, v2 = q + 512 < nw, v3 = q + 768 < nw;
+    for (int jj = 0; jj < nrows; ++jj) {
+      const int y0 = __ldg(ty0 + jj), y1 = __ldg(ty1 + jj);
+      uint32_t ae0 = 0, ao0 = 0, ae1 = 0, ao1 = 0, ae2 = 0, ao2 = 0, ae3 = 0, ao3 = 0;
+      if (ALIGNED) {
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(frames + fbase) + (size_t)y0 * (rowbytes >> 2) + q;
+        for (int y = y0; y < y1; ++y, row += rowbytes >> 2) {
+          const uint32_t w0 = v0 ? __ldg(row) : 0u;
+          const uint32_t w1 = v1 ? __ldg(row + 256) : 0u;
+          const uint32_t w2 = v2 ? __ldg(row + 512) : 0u;
+          const uint32_t w3 = v3 ? __ldg(row + 768) : 0u;
+          ae0 += w0 & 0x00FF00FFu; ao0 += __byte_perm(w0, 0, 0x4341);
+          ae1 += w1 & 0x00FF00FFu; ao1 += __byte_perm(w1, 0, 0x4341);
+          ae2 += w2 & 0x00FF00FFu; ao2 += __byte_perm(w2, 0, 0x4341);
+          ae3 += w3 & 0x00FF00FFu; ao3 += __byte_perm(w3, 0, 0x4341);
+        }
+      } else {
+        size_t off = fbase + (size_t)y0 * rowbytes + 4 * (size_t)q;
+        for (int y = y0; y < y1; ++y, off += rowbytes) {
+          const uint32_t w0 = v0 ? load_word<false>(frames, off, total_bytes) : 0u;
+          const uint32_t w1 = v1 ? load_word<false>(frames, off + 1024, total_bytes) : 0u;
+          const uint32_t w2 = v2 ? load_word<false>(frames, off + 2048, total_bytes) : 0u;
+          const uint32_t w3 = v3 ? load_word<false>(frames, off + 3072, total_bytes) : 0u;
+          ae0 += w0 & 0x00FF00FFu; ao0 += __byte_perm(w0, 0, 0x4341);
+          ae1 += w1 & 0x00FF00FFu; ao1 += __byte_perm(w1, 0, 0x4341);
+          ae2 += w2 & 0x00FF00FFu; ao2 += __byte_perm(w2, 0, 0x4341);
+          ae3 += w3 & 0x00FF00FFu; ao3 += __byte_perm(w3, 0, 0x4341);
+        }
       }
       // bytes (0,2) live in ae, (1,3) in ao -> u16 sums in byte order
-      vrow[q] = make_uint2(__byte_perm(ae, ao, 0x5410), __byte_perm(ae, ao, 0x7632));
+      uint2* vrow = reinterpret_cast<uint2*>(vs) + jj * nw + q;
+      if (v0) vrow[0] = make_uint2(__byte_perm(ae0, ao0, 0x5410), __byte_perm(ae0, ao0, 0x7632));
+      if (v1) vrow[256] = make_uint2(__byte_perm(ae1, ao1, 0x5410), __byte_perm(ae1, ao1, 0x7632));
+      if (v2) vrow[512] = make_uint2(__byte_perm(ae2, ao2, 0x5410), __byte_perm(ae2, ao2, 0x7632));
+      if (v3) vrow[768] = make_uint2(__byte_perm(ae3, ao3, 0x5410), __byte_perm(ae3, ao3, 0x7632));
     }
   }
   __syncthreads();
 
   const uint16_t* v16 = reinterpret_cast<const uint16_t*>(vs);
   const int pitch = p.pitch[lvl];
-  const size_t plane = (size_t)hs * pitch;
-  float* obase = out + p.off[lvl] + (size_t)b * 3 * plane;
-  const int items = nrows * ws;
-  for (int item = tid; item < items; item += 256) {
-    const int jj = item / ws, i = item - jj * ws;
-    const int x0 = __ldg(t + i), x1 = __ldg(t + ws + i);
-    const int kh = __ldg(ty1 + j0 + jj) - __ldg(ty0 + j0 + jj);
-    const uint16_t* vp = v16 + (size_t)jj * (4 * nw) + 3 * x0;
-    int s0 = 0, s1 = 0, s2 = 0;
-    for (int x = x0; x < x1; ++x, vp += 3) { s0 += vp[0]; s1 += vp[1]; s2 += vp[2]; }
-    float* o = obase + (size_t)(j0 + jj) * pitch + i;
-    const int kw = x1 - x0;
-    o[0] = area_norm(s0, kh, kw);
-    o[plane] = area_norm(s1, kh, kw);
-    o[2 * plane] = area_norm(s2, kh, kw);
+  const int plane = hs * pitch;
+  float* obase = out + p.off[lvl] + (size_t)b * 3 * plane + (size_t)j0 * pitch;
+  const bool fast = p.fastdiv[lvl] != 0;
+  for (int jj = 0; jj < nrows; ++jj) {
+    const int kh = __ldg(ty1 + jj) - __ldg(ty0 + jj);
+    const float fkh = (float)kh, rkh = __frcp_rn(fkh);
+    const uint16_t* vr = v16 + jj * (4 * nw);
+    float* orow = obase + jj * pitch;
+    for (int i = tid; i < ws; i += 256) {
+      const int xw = __ldg(t + i);
+      const float rkw = __int_as_float(__ldg(t + ws + i));
+      const int kw = xw >> 16;
+      const uint16_t* vp = vr + 3 * (xw & 0xFFFF);
+      int s0 = 0, s1 = 0, s2 = 0;
+      for (int x = 0; x < kw; ++x, vp += 3) { s0 += vp[0]; s1 += vp[1]; s2 += vp[2]; }
+      const float fkw = (float)kw;
+      float a0, a1, a2;
+      if (fast) {
+        a0 = div_small(div_small((float)s0, fkh, rkh), fkw, rkw);
+        a1 = div_small(div_small((float)s1, fkh, rkh), fkw, rkw);
+        a2 = div_small(div_small((float)s2, fkh, rkh), fkw, rkw);
+      } else {
+        a0 = __fdiv_rn(__fdiv_rn((float)s0, fkh), fkw);
+        a1 = __fdiv_rn(__fdiv_rn((float)s1, fkh), fkw);
+        a2 = __fdiv_rn(__fdiv_rn((float)s2, fkh), fkw);
+      }
+      orow[i] = __fmul_rn(__fsub_rn(a0, 127.5f), 0.0078125f);
+      orow[plane + i] = __fmul_rn(__fsub_rn(a1, 127.5f), 0.0078125f);
+      orow[2 * plane + i] = __fmul_rn(__fsub_rn(a2, 127.5f), 0.0078125f);
+    }
   }
   // pad columns [ws, pitch) stay untouched: readers clip at ws
 }
 
 // adaptive_avg_pool2d windows: [floor(i*In/Out), ceil((i+1)*In/Out))
-static void window_table(int In, int Out, std::vector<int>& v) {
-  const size_t base = v.size();
-  v.resize(base + 2 * (size_t)Out);
+static void window_table(int In, int Out, std::vector<int>& lo, std::vector<int>& hi) {
+  lo.resize(Out);
+  hi.resize(Out);
   for (int i = 0; i < Out; ++i) {
-    v[base + i] = (int)(((long long)i * In) / Out);
-    v[base + Out + i] = (int)(((long long)(i + 1) * In + Out - 1) / Out);
+    lo[i] = (int)(((long long)i * In) / Out);
+    hi[i] = (int)(((long long)(i + 1) * In + Out - 1) / Out);
   }
+}
+
+// Builds (and caches per frame shape) the window tables and verifies the fast division for every (kh, kw) pair.
+static int build_pyramid_tables(trl_ctx* c, int H, int W, const PyramidGeom& g, cudaStream_t s) {
+  if (c->pyr_tab_H == H && c->pyr_tab_W == W && c->d_pyr_tab != nullptr) return TRL_OK;
+  if (W > 65535) TRL_FAIL(c, TRL_E_INVALID, "frame width %d too large", W);
+  std::vector<int> tab;
+  std::vector<int2> pairs;
+  std::vector<int> pair_level;
+  for (int k = 0; k < g.n; ++k) {
+    c->pyr_tab_off[k] = (int)tab.size();
+    std::vector<int> x0, x1, y0, y1;
+    window_table(W, g.ws[k], x0, x1);
+    window_table(H, g.hs[k], y0, y1);
+    for (int i = 0; i < g.ws[k]; ++i) tab.push_back(x0[i] | ((x1[i] - x0[i]) << 16));
+    for (int i = 0; i < g.ws[k]; ++i) {
+      const float r = 1.0f / (float)(x1[i] - x0[i]);     // IEEE: correctly rounded reciprocal
+      int bits;
+      memcpy(&bits, &r, 4);
+      tab.push_back(bits);
+    }
+    tab.insert(tab.end(), y0.begin(), y0.end());
+    tab.insert(tab.end(), y1.begin(), y1.end());
+    std::vector<int> khs, kws;
+    for (int i = 0; i < g.hs[k]; ++i) khs.push_back(y1[i] - y0[i]);
+    for (int i = 0; i < g.ws[k]; ++i) kws.push_back(x1[i] - x0[i]);
+    std::sort(khs.begin(), khs.end()); khs.erase(std::unique(khs.begin(), khs.end()), khs.end());
+    std::sort(kws.begin(), kws.end()); kws.erase(std::unique(kws.begin(), kws.end()), kws.end());
+    for (int a : khs)
+      for (int b : kws) { pairs.push_back(make_int2(a, b)); pair_level.push_back(k); }
+  }
+  if (c->d_pyr_tab) { TRL_CUDA(c, cudaStreamSynchronize(s)); TRL_CUDA(c, cudaFree(c->d_pyr_tab)); c->d_pyr_tab = nullptr; }
+  TRL_CUDA(c, cudaMalloc(&c->d_pyr_tab, tab.size() * sizeof(int)));
+  TRL_CUDA(c, cudaMemcpy(c->d_pyr_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // exhaustive check of the 3-instruction division on this shape's windows (a few million quotients, once per shape)
+  int2* d_pairs = nullptr;
+  int* d_bad = nullptr;
+  TRL_CUDA(c, cudaMalloc(&d_pairs, pairs.size() * sizeof(int2)));
+  TRL_CUDA(c, cudaMalloc(&d_bad, pairs.size() * sizeof(int)));
+  TRL_CUDA(c, cudaMemcpy(d_pairs, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  TRL_CUDA(c, cudaMemset(d_bad, 0, pairs.size() * sizeof(int)));
+  div_verify_kernel<<<dim3(64, (unsigned)pairs.size()), 256, 0, s>>>(d_pairs, d_bad);
+  TRL_LAUNCH_CHECK(c);
+  std::vector<int> bad(pairs.size());
+  TRL_CUDA(c, cudaMemcpyAsync(bad.data(), d_bad, pairs.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+  TRL_CUDA(c, cudaStreamSynchronize(s));
+  cudaFree(d_pairs);
+  cudaFree(d_bad);
+  for (int k = 0; k < g.n; ++k) c->pyr_fastdiv[k] = 1;
+  for (size_t i = 0; i < pairs.size(); ++i)
+    if (bad[i]) c->pyr_fastdiv[pair_level[i]] = 0;
+  c->pyr_tab_H = H;
+  c->pyr_tab_W = W;
+  return TRL_OK;
 }
 
 // `padded`: rows at g.pitch[k] floats and levels at g.off[k]*B (the cascade's internal layout, 16-byte aligned rows
@@ -150,20 +261,8 @@ static void window_table(int In, int Out, std::vector<int>& v) {
 int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const PyramidGeom& g, float* d_out,
                    bool padded, cudaStream_t s) {
   if (g.n == 0 || B == 0) return TRL_OK;
-  // tables are cached per frame shape
-  if (c->pyr_tab_H != H || c->pyr_tab_W != W || c->d_pyr_tab == nullptr) {
-    std::vector<int> tab;
-    for (int k = 0; k < g.n; ++k) {
-      c->pyr_tab_off[k] = (int)tab.size();
-      window_table(W, g.ws[k], tab);
-      window_table(H, g.hs[k], tab);
-    }
-    if (c->d_pyr_tab) { TRL_CUDA(c, cudaStreamSynchronize(s)); TRL_CUDA(c, cudaFree(c->d_pyr_tab)); c->d_pyr_tab = nullptr; }
-    TRL_CUDA(c, cudaMalloc(&c->d_pyr_tab, tab.size() * sizeof(int)));
-    TRL_CUDA(c, cudaMemcpy(c->d_pyr_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
-    c->pyr_tab_H = H;
-    c->pyr_tab_W = W;
-  }
+  int rc = build_pyramid_tables(c, H, W, g, s);
+  if (rc != TRL_OK) return rc;
   if ((reinterpret_cast<uintptr_t>(d_frames) & 3) != 0) TRL_FAIL(c, TRL_E_INVALID, "frames pointer must be 4-byte aligned");
   const int nw = (3 * W + 3) / 4;
   PyrParams p{};
@@ -179,6 +278,7 @@ int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, con
     p.off[k] = padded ? g.off[k] * B : off * B;
     off += 3LL * g.hs[k] * g.ws[k];
     p.tab_off[k] = c->pyr_tab_off[k];
+    p.fastdiv[k] = c->pyr_fastdiv[k];
     // rows per CTA: about 8-12 source rows of work, bounded by 64 KB of column sums
     int R = (int)(8.0 * g.hs[k] / H);
     R = std::max(1, std::min(R, 4));
