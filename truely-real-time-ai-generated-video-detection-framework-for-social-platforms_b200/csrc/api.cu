@@ -354,8 +354,12 @@ int trl_check_capacity(trl_ctx_t* c, int* h_detail) {
   if (!c) return TRL_E_INVALID;
   if (c->h_cap->overflow) {
     if (h_detail) { h_detail[0] = c->h_cap->stage; h_detail[1] = c->h_cap->frame; h_detail[2] = c->h_cap->count; h_detail[3] = c->h_cap->capacity; }
-    c->err = "candidate buffer overflow at stage " + std::to_string(c->h_cap->stage) + " (frame " + std::to_string(c->h_cap->frame) +
-             ": " + std::to_string(c->h_cap->count) + " > capacity " + std::to_string(c->h_cap->capacity) + ")";
+    if (c->h_cap->stage == 5)
+      c->err = "P-Net activation beyond +-" + std::to_string(c->h_cap->capacity) + " (frame " + std::to_string(c->h_cap->frame) +
+               "): outside the range of the scaled fp16 operand split (pnet.cu)";
+    else
+      c->err = "candidate buffer overflow at stage " + std::to_string(c->h_cap->stage) + " (frame " + std::to_string(c->h_cap->frame) +
+               ": " + std::to_string(c->h_cap->count) + " > capacity " + std::to_string(c->h_cap->capacity) + ")";
     memset(c->h_cap, 0, sizeof(CapFlag));
     return TRL_E_CAPACITY;
   }

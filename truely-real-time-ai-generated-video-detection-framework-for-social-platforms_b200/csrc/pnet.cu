@@ -1,56 +1,68 @@
 // K2 + K3: fused P-Net (conv1+PReLU+maxpool, conv2+PReLU, conv3+PReLU, conv4_1 -> softmax, conv4_2) and
-// generateBoundingBox, fp32 on the FMA pipe.  One CTA computes a 16x32 tile of output cells; every intermediate
-// lives in shared memory, the only HBM traffic is the input tile and the (rare) candidates.
+// generateBoundingBox.  One CTA computes a 16x32 tile of output cells; every intermediate lives in shared memory, the
+// only HBM traffic is the input tile and the (rare) candidates.
 //
 // upstream: models/mtcnn.py PNet.forward, models/utils/detect_face.py generateBoundingBox.
 //
-// conv1/conv2 run on the FP32 FMA pipe: thread tiles are register blocked (4 px x 4 channels) with weights broadcast
-// from shared memory by LDS.128.  conv3 (63 % of the FLOPs) runs on the tensor pipe as an implicit GEMM
-// (M = 16 pixels of one output row, N = 8 channels, K = 8 = one filter tap x 8 input channels) with
-// mma.sync.m16n8k8 TF32 and the 3xTF32 split (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulate), which keeps
-// fp32-level accuracy (measured max |err| 1e-5 on |sum| ~ 4.5 over K = 144, experiments/umma_probe.cu) so the
-// cascade sees the same candidates as the fp32 reference.  tcgen05 was measured and rejected for this layer: with
-// N = 32 output channels an SS-mode UMMA is bound by re-reading the A tile from shared memory (~73 cycles per
-// M128 x N32 x K8 step, experiments/umma_probe.cu), no faster than mma.sync once the 3x split is paid.
-// The two CTAs of an SM overlap one CTA's FMA-pipe stages with the other's tensor-pipe stage.
+// conv1 (15 % of the MACs) runs on the FP32 FMA pipe with register-blocked thread tiles.  conv2 and conv3 (85 %) run
+// on the tensor pipe as implicit GEMMs with mma.sync.m16n8k16 and a 3-term fp16 split that keeps fp32-level
+// accuracy: every operand x is scaled by a power of two S and stored as hi = fp16(S x), lo = fp16(S x - hi);
+//     S_a S_w sum(a w) ~= sum(a_hi w_hi) + sum(a_lo w_hi) + sum(a_hi w_lo)          (fp32 accumulate)
+// drops only a_lo w_lo (2^-22 relative) and lo's own rounding (2^-22 relative; the scale keeps lo out of fp16's
+// subnormal range for |x| >= 2^-9, below that the absolute error is < 1e-9).  The result is unscaled exactly in the
+// epilogue.  Against the fp32 oracle the maps agree to ~1e-6 (tests/test_gpu_stages.py bar: 2e-5), so the cascade
+// sees the same candidates.  k16 fp16 MMAs need half the tensor-pipe cycles of the 3xTF32 (k8) form of the same
+// product, and the operands are split once where they are produced (weights on the host, activations in the
+// producing layer's epilogue), not in the MMA loop.  Activations beyond +-1000 would overflow the scaled fp16 hi part:
+// the kernel raises the capacity flag (stage 5) instead of continuing silently.
+// tcgen05 was measured and rejected for these layers: with N = 16/32 output channels an SS-mode UMMA is bound by
+// re-reading the A tile from shared memory (~73 cycles per M128 x N32 x K8 step, experiments/umma_probe.cu).
+// The two CTAs of an SM overlap one CTA's FMA-pipe stage with the other's tensor-pipe stages.
 // FLOP roof, not HBM, binds this kernel.
 #include "common.cuh"
+#include <cuda_fp16.h>
+#include <math.h>
 #include <string.h>
 
 namespace pnet {
 
 constexpr int TOY = 16, TOX = 32;            // output cells per CTA
-constexpr int P1H = TOY + 4, P1W = TOX + 4;  // pooled conv1 tile (20 x 36)
-constexpr int P1P = 40;                      // pitch (conv2's last 8-pixel segment over-reads to col 41 = next row)
-constexpr int P1PLANE = P1H * P1P + 8;       // 808 = 8 mod 32: four channels of one tap land in four bank octets
-constexpr int C2H = TOY + 2, C2W = 36;       // conv2 tile rows x stored cols (34 valid + 2 slack)
-constexpr int C2SEG = 5;                     // conv2 row = five 8-pixel segments (40 computed columns)
-constexpr int C2P = 36;
+constexpr int P1H = TOY + 4, P1W = TOX + 4;  // pooled conv1 tile (20 x 36), flat pixel index n = row * 36 + col
+constexpr int P1PX = 736;                    // 720 pixels + slack read by conv2's last (partial) M tile
+constexpr int P1WORDS = 5;                   // 10 channels = 5 half2 words per pixel (hi plane, lo plane)
+constexpr int C2H = TOY + 2, C2P = 36;       // conv2 tile: 18 rows at the same pitch as its input (flat indexing)
+constexpr int C2PX = C2H * C2P;              // 648 pixels (columns 34, 35 of a row are never read)
+constexpr int C2WORDS = 8;                   // 16 channels = 8 half2 words per pixel
+constexpr int C2TILES = (C2PX + 15) / 16;    // 41 M tiles of two 8-pixel segments
 constexpr int INH = 2 * TOY + 10, INW = 2 * TOX + 10;   // 42 x 74 input tile
 constexpr int INP = 76;
 
-// packed weights (floats), k = (ci*3+ky)*3+kx
-constexpr int W1 = 0;                 // [27][12]
+constexpr float SA = 64.f;                   // activation scale (p1 and c2 tiles)
+constexpr float ACT_MAX = 1000.f;            // |activation| bound for the fp16 hi part (64 * 1000 < 65504)
+
+// packed weights (32-bit words)
+constexpr int W1 = 0;                 // fp32 [27][12]
 constexpr int B1 = W1 + 27 * 12;      // [12]
 constexpr int A1 = B1 + 12;           // [12]
-constexpr int W2 = A1 + 12;           // mma B fragments: [12 k-steps][32 lanes][b0 n0, b0 n1, b1 n0, b1 n1]
-constexpr int T2 = W2 + 12 * 32 * 4;  // int[96]: pooled-tile offset of k index 8s + t (+4), see conv2_k()
-constexpr int B2 = T2 + 96;
-constexpr int A2 = B2 + 16;
-constexpr int W3 = A2 + 16;           // mma B fragments: [18 k-steps][2][32 lanes][4 n-tiles], k = tap*16 + ci
-constexpr int B3 = W3 + 144 * 32;
+constexpr int W2 = A1 + 12;           // half2 B fragments: [6 k-steps][hi, lo][32 lanes][n0 b0, n0 b1, n1 b0, n1 b1]
+constexpr int T2 = W2 + 6 * 2 * 32 * 4;   // int[48]: p1 word offset of channel pair P (see conv2_pair())
+constexpr int B2 = T2 + 48;           // [16]
+constexpr int A2 = B2 + 16;           // [16]
+constexpr int W3 = A2 + 16;           // half2 B fragments: [9 taps][hi, lo][2 n-tile pairs][32 lanes][4]
+constexpr int B3 = W3 + 9 * 2 * 2 * 32 * 4;
 constexpr int A3 = B3 + 32;
-constexpr int WH = A3 + 32;           // [32][8]: cols 0,1 conv4_1; 2..5 conv4_2
+constexpr int WH = A3 + 32;           // fp32 [32][8]: cols 0,1 conv4_1; 2..5 conv4_2
 constexpr int BH = WH + 32 * 8;       // [8]
-constexpr int WTOTAL = BH + 8;        // 6948 floats
-static_assert(WTOTAL % 4 == 0, "float4 copy");
+constexpr int SC = BH + 8;            // [4]: 1 / (SA * S_w2), 1 / (SA * S_w3)
+constexpr int WTOTAL = SC + 4;
+static_assert(WTOTAL % 4 == 0 && W2 % 4 == 0 && W3 % 4 == 0, "16-byte alignment of the fragment arrays");
 
-constexpr int SM_IN = 3 * INH * INP;          // 9576
-constexpr int SM_C2 = 16 * C2H * C2P;         // 10368   (aliases the input tile)
+constexpr int SM_IN = 3 * INH * INP;                 // 9576 words
+constexpr int SM_C2 = 2 * C2PX * C2WORDS;            // 10368 words (aliases the input tile)
 constexpr int SM_A = SM_C2 > SM_IN ? SM_C2 : SM_IN;
-constexpr int SM_P1 = 10 * P1PLANE;           // 8080
-constexpr int SMEM_FLOATS = WTOTAL + SM_A + SM_P1;
-constexpr int SMEM_BYTES = SMEM_FLOATS * 4;   // ~100 KB -> 2 CTAs / SM
+constexpr int SM_P1 = 2 * P1PX * P1WORDS;            // 7360 words
+constexpr int SMEM_WORDS = WTOTAL + SM_A + SM_P1;
+constexpr int SMEM_BYTES = SMEM_WORDS * 4;           // ~97 KB -> 2 CTAs / SM
 
 struct Level {
   const float* in;     // [B][3][hs][pitch]
@@ -77,25 +89,32 @@ __device__ unsigned long long g_pnet_phase[8];
 #endif
 __device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : v * a; }
 
-// x = hi + lo with hi exactly representable in TF32 (round to nearest, ties away; two integer ops instead of the
-// five-instruction NaN-safe expansion of cvt.rna.tf32.f32 -- activations and weights are finite).  The tensor core
-// drops lo's low 13 bits, an error of 2^-21 |x|.
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
+// (x0, x1), already scaled -> packed fp16 hi and lo = fp16(x - hi)
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+__device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                        uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ wpacked, const __grid_constant__ Params p) {
   extern __shared__ __align__(16) float smem[];
   float* w_s = smem;
-  float* a_s = smem + WTOTAL;          // input tile, later conv2 output
-  float* p1_s = a_s + SM_A;            // pooled conv1, later head partials
+  float* a_s = smem + WTOTAL;                                        // fp32 input tile, later the conv2 output
+  uint32_t* c2_s = reinterpret_cast<uint32_t*>(a_s);                 // [hi, lo][C2PX][8]
+  uint32_t* p1_s = reinterpret_cast<uint32_t*>(a_s + SM_A);          // [hi, lo][P1PX][5]
+  const uint32_t* wu = reinterpret_cast<const uint32_t*>(w_s);
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  bool range_bad = false;
 #ifdef PNET_TIMING
   long long tph[5]; tph[0] = clock64();
 #endif
@@ -151,10 +170,13 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
   tph[1] = clock64();
 #endif
 
-  // ---- conv1 (3->10, 3x3) + PReLU + maxpool(2,2,ceil): one pooled pixel x 10 channels per item
+  // ---- conv1 (3->10, 3x3) + PReLU + maxpool(2,2,ceil): one pooled pixel x 10 channels per item, written as
+  // scaled fp16 hi / lo channel pairs
   {
     const int c1h = hs - 2, c1w = ws - 2;     // valid conv1 extent (ceil-mode pooling clips to it)
+#pragma unroll 1
     for (int item = tid; item < P1H * P1W; item += 256) {
+      asm volatile("" ::: "memory");          // keep the weight loads inside the loop (hoisted, they spill)
       const int py = item / P1W, px = item - py * P1W;
       float patch[3][4][4];
 #pragma unroll
@@ -189,25 +211,32 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
             }
           }
       const int gy = 2 * (oy0 + py), gx = 2 * (ox0 + px);
+      float m[10];
 #pragma unroll
       for (int co = 0; co < 10; ++co) {
         const float bias = w_s[B1 + co], al = w_s[A1 + co];
-        float m = -INFINITY;
+        float mm = -INFINITY;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const bool ok = (gy + (q >> 1) < c1h) && (gx + (q & 1) < c1w);
           const float v = prelu(acc[q][co] + bias, al);
-          m = ok ? fmaxf(m, v) : m;
+          mm = ok ? fmaxf(mm, v) : mm;
         }
-        p1_s[co * P1PLANE + py * P1P + px] = (m == -INFINITY) ? 0.f : m;
+        m[co] = (mm == -INFINITY) ? 0.f : mm;
+        range_bad |= fabsf(m[co]) > ACT_MAX;
+      }
+#pragma unroll
+      for (int cp = 0; cp < 5; ++cp) {
+        uint32_t hi, lo;
+        split_h2(m[2 * cp] * SA, m[2 * cp + 1] * SA, hi, lo);
+        p1_s[item * P1WORDS + cp] = hi;
+        p1_s[P1PX * P1WORDS + item * P1WORDS + cp] = lo;
       }
     }
-    // slack columns read by conv2's last pixel group
-    for (int i = tid; i < 10 * P1H * (P1P - P1W); i += 256) {
-      const int co = i / (P1H * (P1P - P1W));
-      const int r = (i / (P1P - P1W)) % P1H;
-      const int cx = P1W + i % (P1P - P1W);
-      p1_s[co * P1PLANE + r * P1P + cx] = 0.f;
+    // slack pixels read by conv2's last M tile (their outputs are never used, but they must be finite)
+    for (int i = tid; i < (P1PX - P1H * P1W) * P1WORDS; i += 256) {
+      p1_s[P1H * P1W * P1WORDS + i] = 0u;
+      p1_s[P1PX * P1WORDS + P1H * P1W * P1WORDS + i] = 0u;
     }
   }
   __syncthreads();
@@ -215,28 +244,25 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
   tph[2] = clock64();
 #endif
 
-  // ---- conv2 (10->16, 3x3) + PReLU on the tensor pipe (3xTF32), output over the dead input tile.
-  // M tile = two 8-pixel row segments (18 rows x 5 segments = 45 tiles), N = 2 x 8 channels, K = 96 (90 used):
-  // k index 8s + t (+4) -> (ci, ky, kx) by conv2_k(): the four k of one A load share kx and differ in (ci + ky) mod 4,
-  // so with planes 808 floats apart they read four different bank octets (conflict free); offsets come from T2.
+  // ---- conv2 (10->16, 3x3) + PReLU on the tensor pipe, output over the dead input tile.
+  // Flat implicit GEMM: output pixel n = row * 36 + col reads input pixels n + ky * 36 + kx, so an M tile is any
+  // two 8-pixel runs of the flat index (41 tiles cover the 18 x 36 tile, columns 34/35 are computed but unused).
+  // K = 90 as 45 channel pairs P = ky*15 + kx*5 + cp (+3 zero-weight pads) = 6 k16 steps; the word offset of pair P
+  // relative to the pixel comes from T2.  Fragment coordinates (PTX m16n8k16): g = lane/4, t = lane%4
+  //   A: a0 (px g, pair t)  a1 (px g+8, pair t)  a2 (px g, pair t+4)  a3 (px g+8, pair t+4)
+  //   B: b0 (pair t, n g)   b1 (pair t+4, n g)        C: c0,c1 (px g, n 2t, 2t+1)  c2,c3 (px g+8, ..)
   {
-    const int lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
     const int* tab = reinterpret_cast<const int*>(w_s + T2);
+    const uint32_t* p1h = p1_s;
+    const uint32_t* p1l = p1_s + P1PX * P1WORDS;
+    const float inv = w_s[SC + 0];
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-      const int mt0 = (pass * 8 + warp) * 3;
-      if (mt0 >= 45) break;                       // warp uniform
-      int pa[3][2], row[3][2], col[3][2];
+      // tiles warp + 8 i, i = 3 pass .. 3 pass + 2 (tile 40 exists for warp 0 only)
+      const int mt0 = warp + 24 * pass;
+      int base[3];
 #pragma unroll
-      for (int q = 0; q < 3; ++q)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int seg = 2 * (mt0 + q) + h;
-          row[q][h] = seg / C2SEG;
-          col[q][h] = 8 * (seg - row[q][h] * C2SEG) + g;
-          pa[q][h] = row[q][h] * P1P + col[q][h];
-        }
+      for (int q = 0; q < 3; ++q) base[q] = min(mt0 + 8 * q, C2TILES - 1) * 16 * P1WORDS + g * P1WORDS;
       float acc[3][2][4];
 #pragma unroll
       for (int q = 0; q < 3; ++q)
@@ -244,50 +270,60 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
         for (int j = 0; j < 2; ++j)
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[q][j][e] = 0.f;
-#pragma unroll 2
-      for (int s = 0; s < 12; ++s) {
+#pragma unroll
+      for (int s = 0; s < 6; ++s) {
         const int o0 = tab[8 * s + t], o1 = tab[8 * s + t + 4];
-        const float4 w = *reinterpret_cast<const float4*>(&w_s[W2 + (s * 32 + lane) * 4]);
-        uint32_t bh[4], bl[4];
-        split_tf32(w.x, bh[0], bl[0]);
-        split_tf32(w.y, bh[1], bl[1]);
-        split_tf32(w.z, bh[2], bl[2]);
-        split_tf32(w.w, bh[3], bl[3]);
+        const uint4 bh = *reinterpret_cast<const uint4*>(&wu[W2 + ((2 * s + 0) * 32 + lane) * 4]);
+        const uint4 bl = *reinterpret_cast<const uint4*>(&wu[W2 + ((2 * s + 1) * 32 + lane) * 4]);
         uint32_t ah[3][4], al[3][4];
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          split_tf32(p1_s[pa[q][0] + o0], ah[q][0], al[q][0]);
-          split_tf32(p1_s[pa[q][1] + o0], ah[q][1], al[q][1]);
-          split_tf32(p1_s[pa[q][0] + o1], ah[q][2], al[q][2]);
-          split_tf32(p1_s[pa[q][1] + o1], ah[q][3], al[q][3]);
+          ah[q][0] = p1h[base[q] + o0];                  al[q][0] = p1l[base[q] + o0];
+          ah[q][1] = p1h[base[q] + 8 * P1WORDS + o0];    al[q][1] = p1l[base[q] + 8 * P1WORDS + o0];
+          ah[q][2] = p1h[base[q] + o1];                  al[q][2] = p1l[base[q] + o1];
+          ah[q][3] = p1h[base[q] + 8 * P1WORDS + o1];    al[q][3] = p1l[base[q] + 8 * P1WORDS + o1];
+        }
+        // the three terms of one accumulator are dependent: issue the 6 independent accumulators between them
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          mma_f16(acc[q][0], al[q][0], al[q][1], al[q][2], al[q][3], bh.x, bh.y);
+          mma_f16(acc[q][1], al[q][0], al[q][1], al[q][2], al[q][3], bh.z, bh.w);
         }
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
+        for (int q = 0; q < 3; ++q) {
+          mma_f16(acc[q][0], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bl.x, bl.y);
+          mma_f16(acc[q][1], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bl.z, bl.w);
+        }
 #pragma unroll
-          for (int j = 0; j < 2; ++j) mma_tf32(acc[q][j], al[q], bh[j], bh[2 + j]);
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) mma_tf32(acc[q][j], ah[q], bl[j], bl[2 + j]);
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) mma_tf32(acc[q][j], ah[q], bh[j], bh[2 + j]);
+        for (int q = 0; q < 3; ++q) {
+          mma_f16(acc[q][0], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bh.x, bh.y);
+          mma_f16(acc[q][1], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bh.z, bh.w);
+        }
       }
+      // epilogue: unscale, bias, PReLU, split; lane holds channels (2t, 2t+1) + 8 j of pixels g and g + 8.
+      // conv3 wants the pair words of a pixel in the order (0,4,1,5,2,6,3,7): pair 4 j + t sits at word 2 t + j.
+      const float bias0 = w_s[B2 + 2 * t], bias1 = w_s[B2 + 2 * t + 1], bias2 = w_s[B2 + 8 + 2 * t], bias3 = w_s[B2 + 9 + 2 * t];
+      const float al0 = w_s[A2 + 2 * t], al1 = w_s[A2 + 2 * t + 1], al2 = w_s[A2 + 8 + 2 * t], al3 = w_s[A2 + 9 + 2 * t];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        if (mt0 + q >= 45) break;
+        const int mt = mt0 + 8 * q;
+        if (mt >= C2TILES) break;                 // warp uniform
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int co = 8 * j + 2 * t + e;
-            const float bias = w_s[B2 + co], al2 = w_s[A2 + co];
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-              if (col[q][h] < C2W)
-                a_s[(co * C2H + row[q][h]) * C2P + col[q][h]] = prelu(acc[q][j][2 * h + e] + bias, al2);
+        for (int h = 0; h < 2; ++h) {
+          const int n = mt * 16 + 8 * h + g;
+          if (n < C2PX) {
+            const float v0 = prelu(fmaf(acc[q][0][2 * h], inv, bias0), al0);
+            const float v1 = prelu(fmaf(acc[q][0][2 * h + 1], inv, bias1), al1);
+            const float v2 = prelu(fmaf(acc[q][1][2 * h], inv, bias2), al2);
+            const float v3 = prelu(fmaf(acc[q][1][2 * h + 1], inv, bias3), al3);
+            range_bad |= fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3))) > ACT_MAX;
+            uint32_t h0, l0, h1, l1;
+            split_h2(v0 * SA, v1 * SA, h0, l0);
+            split_h2(v2 * SA, v3 * SA, h1, l1);
+            *reinterpret_cast<uint2*>(&c2_s[n * C2WORDS + 2 * t]) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(&c2_s[C2PX * C2WORDS + n * C2WORDS + 2 * t]) = make_uint2(l0, l1);
           }
+        }
       }
     }
   }
@@ -297,19 +333,16 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
 #endif
 
   // ---- conv3 (16->32, 3x3) on the tensor pipe + PReLU + heads.
-  // warp w owns output rows 2w, 2w+1; one pass = one row = two 16-pixel M tiles x four 8-channel N tiles.
-  // fragment coordinates (PTX m16n8k8): g = lane/4, t = lane%4
-  //   A: a0 (px g, k t)  a1 (px g+8, k t)  a2 (px g, k t+4)  a3 (px g+8, k t+4)
-  //   B: b0 (k t, n g)   b1 (k t+4, n g)          C: c0 (px g, n 2t) c1 (px g, n 2t+1) c2/c3 (px g+8, ..)
-  // conv2 planes are 18*36 = 648 floats apart (= 8 mod 32 banks), so the 32 lanes of an A load hit 32 banks.
+  // warp w owns output rows 2w, 2w+1; one pass = one row = two 16-pixel M tiles x four 8-channel N tiles; one k16 step
+  // = one filter tap x 16 channels.  The A words of a pixel are ordered so that (a0, a2) is one 64-bit load:
+  // a half-warp (g = 0..3) then reads 32 consecutive words, conflict free.
   {
-    const int lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
+    const uint32_t* c2h = c2_s;
+    const uint32_t* c2l = c2_s + C2PX * C2WORDS;
+    const float inv = w_s[SC + 1];
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       const int row = 2 * warp + pass;
-      const float* arow = a_s + (t * C2H + row) * C2P + g;
-      const float4* wf = reinterpret_cast<const float4*>(w_s + W3) + lane;
       float acc[2][4][4];
 #pragma unroll
       for (int m = 0; m < 2; ++m)
@@ -317,46 +350,44 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
-#pragma unroll 1
-      for (int ky = 0; ky < 3; ++ky) {
-        // 6 k-steps per filter row: (kx, channel half); unrolled so the offsets are immediates, the outer loop
-        // stays rolled to bound the number of live shared-memory loads (no spills at 128 registers)
+#pragma unroll 3
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap - 3 * ky;
+        const int abase = ((row + ky) * C2P + kx + g) * C2WORDS + 2 * t;
+        const uint32_t* wf = wu + W3 + tap * (2 * 2 * 32 * 4) + lane * 4;
+        const uint4 bh0 = *reinterpret_cast<const uint4*>(wf);              // n-tiles 0,1: (b0,b1),(b0,b1)
+        const uint4 bh1 = *reinterpret_cast<const uint4*>(wf + 128);        // n-tiles 2,3
+        const uint4 bl0 = *reinterpret_cast<const uint4*>(wf + 256);
+        const uint4 bl1 = *reinterpret_cast<const uint4*>(wf + 384);
+        uint2 ah[2][2], al[2][2];        // [m tile][pixel g / g+8] = (a0|a1, a2|a3)
 #pragma unroll
-        for (int s6 = 0; s6 < 6; ++s6) {
-          const int kx = s6 >> 1;
-          const int koff = ((s6 & 1) * 8 * C2H) * C2P + kx;
-          const float4 w0 = wf[(2 * s6) * 32], w1 = wf[(2 * s6 + 1) * 32];
-          const float bw[2][4] = {{w0.x, w0.y, w0.z, w0.w}, {w1.x, w1.y, w1.z, w1.w}};
-          uint32_t bh[2][4], bl[2][4];
+        for (int m = 0; m < 2; ++m)
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) split_tf32(bw[i][j], bh[i][j], bl[i][j]);
-          uint32_t ah[2][4], al[2][4];
-#pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            const float* ap = arow + koff + 16 * m;
-            split_tf32(ap[0], ah[m][0], al[m][0]);
-            split_tf32(ap[8], ah[m][1], al[m][1]);
-            split_tf32(ap[4 * C2H * C2P], ah[m][2], al[m][2]);
-            split_tf32(ap[4 * C2H * C2P + 8], ah[m][3], al[m][3]);
+          for (int h = 0; h < 2; ++h) {
+            ah[m][h] = *reinterpret_cast<const uint2*>(&c2h[abase + (16 * m + 8 * h) * C2WORDS]);
+            al[m][h] = *reinterpret_cast<const uint2*>(&c2l[abase + (16 * m + 8 * h) * C2WORDS]);
           }
-          // the three terms of one accumulator are dependent: issue the 8 independent accumulators between them
 #pragma unroll
-          for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mma_tf32(acc[m][j], al[m], bh[0][j], bh[1][j]);
-#pragma unroll
-          for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mma_tf32(acc[m][j], ah[m], bl[0][j], bl[1][j]);
-#pragma unroll
-          for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mma_tf32(acc[m][j], ah[m], bh[0][j], bh[1][j]);
+        for (int m = 0; m < 2; ++m) {
+          mma_f16(acc[m][0], al[m][0].x, al[m][1].x, al[m][0].y, al[m][1].y, bh0.x, bh0.y);
+          mma_f16(acc[m][1], al[m][0].x, al[m][1].x, al[m][0].y, al[m][1].y, bh0.z, bh0.w);
+          mma_f16(acc[m][2], al[m][0].x, al[m][1].x, al[m][0].y, al[m][1].y, bh1.x, bh1.y);
+          mma_f16(acc[m][3], al[m][0].x, al[m][1].x, al[m][0].y, al[m][1].y, bh1.z, bh1.w);
         }
-        arow += C2P;
-        wf += 12 * 32;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          mma_f16(acc[m][0], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bl0.x, bl0.y);
+          mma_f16(acc[m][1], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bl0.z, bl0.w);
+          mma_f16(acc[m][2], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bl1.x, bl1.y);
+          mma_f16(acc[m][3], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bl1.z, bl1.w);
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          mma_f16(acc[m][0], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bh0.x, bh0.y);
+          mma_f16(acc[m][1], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bh0.z, bh0.w);
+          mma_f16(acc[m][2], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bh1.x, bh1.y);
+          mma_f16(acc[m][3], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bh1.z, bh1.w);
+        }
       }
       // epilogue: bias + PReLU, heads (6 outputs over 32 channels; this thread holds 8 channels of 2 pixels per tile)
 #pragma unroll
@@ -371,12 +402,12 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int co = 8 * j + 2 * t + e;
-            const float bias = w_s[B3 + co], al = w_s[A3 + co];
+            const float bias = w_s[B3 + co], al3 = w_s[A3 + co];
             const float4 ha = *reinterpret_cast<const float4*>(&w_s[WH + co * 8]);
             const float2 hb = *reinterpret_cast<const float2*>(&w_s[WH + co * 8 + 4]);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              const float v = prelu(acc[m][j][2 * i + e] + bias, al);
+              const float v = prelu(fmaf(acc[m][j][2 * i + e], inv, bias), al3);
               hp[i][0] = fmaf(v, ha.x, hp[i][0]);
               hp[i][1] = fmaf(v, ha.y, hp[i][1]);
               hp[i][2] = fmaf(v, ha.z, hp[i][2]);
@@ -434,6 +465,10 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
       }
     }
   }
+  if (range_bad && p.capflag) {
+    p.capflag->overflow = 1; p.capflag->stage = 5; p.capflag->frame = b;
+    p.capflag->count = 0; p.capflag->capacity = (int)ACT_MAX;
+  }
 #ifdef PNET_TIMING
   tph[4] = clock64();
   if (tid == 0) {
@@ -452,24 +487,39 @@ extern "C" void trl_debug_pnet_timing(unsigned long long* out) {
 }
 #endif
 
-// conv2's K ordering: group G = 2*kstep + (0: a0/a1/b0, 1: a2/a3/b1), slot t = lane % 4.
-//   G < 18 : tap G/2, channels 4*(G%2) + t               (channels 0..7)
-//   G >= 18: kx = (G-18)/2; channels 8,9 x ky 0..2, two zero-weight pads
-// Every group has one kx and four distinct (ci + ky) mod 4 -> four bank octets.  Returns false for the pads.
-static bool conv2_k(int G, int t, int* ci, int* ky, int* kx) {
-  if (G < 18) {
-    const int tap = G / 2;
-    *ci = 4 * (G % 2) + t; *ky = tap / 3; *kx = tap % 3;
-    return true;
-  }
-  *kx = (G - 18) / 2;
-  if ((G - 18) % 2 == 0) {
-    *ci = 8 + (t & 1); *ky = (t < 2) ? 0 : 2;            // (8,0) (9,0) (8,2) (9,2): octets 0,1,2,3
-    return true;
-  }
-  if (t < 2) { *ci = 8 + t; *ky = 1; return true; }       // (8,1) (9,1): octets 1,2
-  *ci = (t == 2) ? 0 : 3; *ky = 0;                        // pads (zero weights): octets 0,3
-  return false;
+// ---- host-side packing
+
+// conv2's K ordering: channel pair P = ky*15 + kx*5 + cp holds channels (2cp, 2cp+1) of tap (ky, kx); P >= 45 are
+// zero-weight pads that read pair P - 45 (any finite word).
+static void conv2_pair(int P, int* ky, int* kx, int* cp, bool* used) {
+  *used = P < 45;
+  const int q = *used ? P : P - 45;
+  *ky = q / 15; *kx = (q % 15) / 5; *cp = q % 5;
+}
+
+// power-of-two scale that brings max|w| just below 2^14 (fp16 max is 65504): keeps w's lo part out of the subnormals
+static float weight_scale(const float* w, int n) {
+  float m = 0.f;
+  for (int i = 0; i < n; ++i) m = fmaxf(m, fabsf(w[i]));
+  if (!(m > 0.f) || !isfinite(m)) return 1.f;
+  int e;
+  frexpf(m, &e);                        // m = f * 2^e, f in [0.5, 1)
+  return ldexpf(1.f, 14 - e);
+}
+
+static uint32_t pack_h2(float x0, float x1) {
+  const __half a = __float2half_rn(x0), b = __float2half_rn(x1);
+  uint16_t ua, ub;
+  memcpy(&ua, &a, 2);
+  memcpy(&ub, &b, 2);
+  return (uint32_t)ua | ((uint32_t)ub << 16);
+}
+// scaled pair -> hi word and lo word
+static void split_pair(float x0, float x1, float scale, uint32_t* hi, uint32_t* lo) {
+  const float s0 = x0 * scale, s1 = x1 * scale;         // power-of-two scale: exact
+  const float h0 = __half2float(__float2half_rn(s0)), h1 = __half2float(__float2half_rn(s1));
+  *hi = pack_h2(s0, s1);
+  *lo = pack_h2(s0 - h0, s1 - h1);
 }
 
 // upstream layouts -> packed shared-memory image
@@ -477,6 +527,7 @@ int pnet_pack_weights(trl_ctx* c, const float* h, size_t len) {
   using namespace pnet;
   if (len != 6632) TRL_FAIL(c, TRL_E_INVALID, "pnet blob has %zu floats, expected 6632", len);
   std::vector<float> pk(WTOTAL, 0.f);
+  uint32_t* pu = reinterpret_cast<uint32_t*>(pk.data());
   const float* w1 = h;                   // [10][3][3][3]
   const float* b1 = w1 + 270;
   const float* a1 = b1 + 10;
@@ -493,31 +544,45 @@ int pnet_pack_weights(trl_ctx* c, const float* h, size_t len) {
   for (int co = 0; co < 10; ++co)
     for (int k = 0; k < 27; ++k) pk[W1 + k * 12 + co] = w1[co * 27 + k];
   for (int co = 0; co < 10; ++co) { pk[B1 + co] = b1[co]; pk[A1 + co] = a1[co]; }
-  // conv2 as mma.m16n8k8 B fragments + the k -> pooled-tile offset table
-  for (int s = 0; s < 12; ++s)
+  const float s2 = weight_scale(w2, 1440), s3 = weight_scale(w3, 4608);
+  // conv2 B fragments (m16n8k16: b0 = pair t, b1 = pair t + 4 of the k-step; n = g + 8 j) + the pair offset table
+  for (int s = 0; s < 6; ++s)
     for (int lane = 0; lane < 32; ++lane) {
       const int g = lane >> 2, t = lane & 3;
-      for (int i = 0; i < 2; ++i) {
-        int ci, ky, kx;
-        const bool used = conv2_k(2 * s + i, t, &ci, &ky, &kx);
-        for (int j = 0; j < 2; ++j)
-          pk[W2 + (s * 32 + lane) * 4 + 2 * i + j] = used ? w2[(8 * j + g) * 90 + ci * 9 + ky * 3 + kx] : 0.f;
+      for (int i = 0; i < 2; ++i) {        // b0 / b1
+        int ky, kx, cp;
+        bool used;
+        conv2_pair(8 * s + 4 * i + t, &ky, &kx, &cp, &used);
+        for (int j = 0; j < 2; ++j) {
+          const int co = 8 * j + g;
+          const float x0 = used ? w2[co * 90 + (2 * cp) * 9 + ky * 3 + kx] : 0.f;
+          const float x1 = used ? w2[co * 90 + (2 * cp + 1) * 9 + ky * 3 + kx] : 0.f;
+          uint32_t hi, lo;
+          split_pair(x0, x1, s2, &hi, &lo);
+          pu[W2 + ((2 * s + 0) * 32 + lane) * 4 + 2 * j + i] = hi;
+          pu[W2 + ((2 * s + 1) * 32 + lane) * 4 + 2 * j + i] = lo;
+        }
         if (g == 0) {
-          const int off = ci * P1PLANE + ky * P1P + kx;
+          const int off = (ky * P1W + kx) * P1WORDS + cp;
           memcpy(&pk[T2 + 8 * s + 4 * i + t], &off, sizeof(int));
         }
       }
     }
   for (int co = 0; co < 16; ++co) { pk[B2 + co] = b2[co]; pk[A2 + co] = a2[co]; }
-  // conv3 as mma.m16n8k8 B fragments: k-step s = (tap, channel half), k = 8s + t (+4) -> ci = (s&1)*8 + t (+4)
-  for (int s = 0; s < 18; ++s)
-    for (int i = 0; i < 2; ++i)
-      for (int lane = 0; lane < 32; ++lane)
-        for (int j = 0; j < 4; ++j) {
-          const int g = lane >> 2, t = lane & 3;
-          const int tap = s >> 1, ci = (s & 1) * 8 + t + 4 * i, co = 8 * j + g;
-          pk[W3 + ((2 * s + i) * 32 + lane) * 4 + j] = w3[co * 144 + ci * 9 + tap];
+  // conv3 B fragments: k16 step = tap, b0 = channels (2t, 2t+1), b1 = channels (2t+8, 2t+9); n = g + 8 j
+  for (int tap = 0; tap < 9; ++tap)
+    for (int lane = 0; lane < 32; ++lane) {
+      const int g = lane >> 2, t = lane & 3;
+      for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 2; ++i) {
+          const int co = 8 * j + g, ci = 2 * t + 8 * i;
+          uint32_t hi, lo;
+          split_pair(w3[co * 144 + ci * 9 + tap], w3[co * 144 + (ci + 1) * 9 + tap], s3, &hi, &lo);
+          const int word = ((j >> 1) * 32 + lane) * 4 + 2 * (j & 1) + i;
+          pu[W3 + tap * 512 + 0 * 256 + word] = hi;
+          pu[W3 + tap * 512 + 1 * 256 + word] = lo;
         }
+    }
   for (int co = 0; co < 32; ++co) { pk[B3 + co] = b3[co]; pk[A3 + co] = a3[co]; }
   for (int ci = 0; ci < 32; ++ci) {
     pk[WH + ci * 8 + 0] = w41[0 * 32 + ci];
@@ -526,6 +591,8 @@ int pnet_pack_weights(trl_ctx* c, const float* h, size_t len) {
   }
   pk[BH + 0] = b41[0]; pk[BH + 1] = b41[1];
   for (int j = 0; j < 4; ++j) pk[BH + 2 + j] = b42[j];
+  pk[SC + 0] = 1.f / (SA * s2);
+  pk[SC + 1] = 1.f / (SA * s3);
   TRL_CUDA(c, cudaMalloc(&c->d_pnet_packed, WTOTAL * sizeof(float)));
   TRL_CUDA(c, cudaMemcpy(c->d_pnet_packed, pk.data(), WTOTAL * sizeof(float), cudaMemcpyHostToDevice));
   TRL_CUDA(c, cudaFuncSetAttribute(pnet::pnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -544,7 +611,7 @@ int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float
   L.tiles = L.tiles_x * ceil_div(L.oh, TOY);
   L.scale = 1.f; L.prob = d_prob; L.reg = d_reg; L.cand = nullptr; L.cnt = nullptr;
   p.blk_start[0] = 0; p.blk_start[1] = L.tiles;
-  p.thr = 2.f; p.cap = 0; p.capflag = nullptr;
+  p.thr = 2.f; p.cap = 0; p.capflag = c->d_cap;
   pnet_kernel<<<dim3(L.tiles, B), 256, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
