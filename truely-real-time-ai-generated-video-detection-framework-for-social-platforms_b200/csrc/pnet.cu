@@ -88,6 +88,18 @@ struct Params {
 __device__ unsigned long long g_pnet_phase[8];
 #endif
 __device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : v * a; }
+// sm_100 packed fp32: two independent IEEE fmas per instruction (SASS FFMA2; a (v, v) pair becomes a scalar broadcast operand)
+__device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
 
 // (x0, x1), already scaled -> packed fp16 hi and lo = fp16(x - hi)
 __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
@@ -187,11 +199,12 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
           const float2 v1 = *reinterpret_cast<const float2*>(&a_s[(ci * INH + 2 * py + r) * INP + 2 * px + 2]);
           patch[ci][r][0] = v0.x; patch[ci][r][1] = v0.y; patch[ci][r][2] = v1.x; patch[ci][r][3] = v1.y;
         }
-      float acc[4][12];
+      // packed fp32 pairs: FFMA2 (fma.rn.f32x2) does two channels per issued instruction, same rounding as FFMA
+      unsigned long long acc[4][5];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int co = 0; co < 12; ++co) acc[q][co] = 0.f;
+        for (int cp = 0; cp < 5; ++cp) acc[q][cp] = 0ull;
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
@@ -201,16 +214,23 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
             const float* wr = &w_s[W1 + ((ci * 3 + ky) * 3 + kx) * 12];
             const float4 wa = *reinterpret_cast<const float4*>(wr);
             const float4 wb = *reinterpret_cast<const float4*>(wr + 4);
-            const float4 wc = *reinterpret_cast<const float4*>(wr + 8);
-            const float w[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
+            const float2 wc = *reinterpret_cast<const float2*>(wr + 8);
+            const unsigned long long w[5] = {pack_f32x2(wa.x, wa.y), pack_f32x2(wa.z, wa.w), pack_f32x2(wb.x, wb.y),
+                                             pack_f32x2(wb.z, wb.w), pack_f32x2(wc.x, wc.y)};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float v = patch[ci][(q >> 1) + ky][(q & 1) + kx];
+              const unsigned long long vv = pack_f32x2(v, v);
 #pragma unroll
-              for (int co = 0; co < 10; ++co) acc[q][co] = fmaf(v, w[co], acc[q][co]);
+              for (int cp = 0; cp < 5; ++cp) ffma2(acc[q][cp], vv, w[cp]);
             }
           }
       const int gy = 2 * (oy0 + py), gx = 2 * (ox0 + px);
+      float accf[4][10];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int cp = 0; cp < 5; ++cp) unpack_f32x2(acc[q][cp], accf[q][2 * cp], accf[q][2 * cp + 1]);
       float m[10];
 #pragma unroll
       for (int co = 0; co < 10; ++co) {
@@ -219,7 +239,7 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const bool ok = (gy + (q >> 1) < c1h) && (gx + (q & 1) < c1w);
-          const float v = prelu(acc[q][co] + bias, al);
+          const float v = prelu(accf[q][co] + bias, al);
           mm = ok ? fmaxf(mm, v) : mm;
         }
         m[co] = (mm == -INFINITY) ? 0.f : mm;
@@ -392,11 +412,11 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
       // epilogue: bias + PReLU, heads (6 outputs over 32 channels; this thread holds 8 channels of 2 pixels per tile)
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
-        float hp[2][6];
+        unsigned long long hp2[2][3];
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int q = 0; q < 6; ++q) hp[i][q] = 0.f;
+          for (int q = 0; q < 3; ++q) hp2[i][q] = 0ull;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -405,17 +425,21 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
             const float bias = w_s[B3 + co], al3 = w_s[A3 + co];
             const float4 ha = *reinterpret_cast<const float4*>(&w_s[WH + co * 8]);
             const float2 hb = *reinterpret_cast<const float2*>(&w_s[WH + co * 8 + 4]);
+            const unsigned long long h01 = pack_f32x2(ha.x, ha.y), h23 = pack_f32x2(ha.z, ha.w), h45 = pack_f32x2(hb.x, hb.y);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const float v = prelu(fmaf(acc[m][j][2 * i + e], inv, bias), al3);
-              hp[i][0] = fmaf(v, ha.x, hp[i][0]);
-              hp[i][1] = fmaf(v, ha.y, hp[i][1]);
-              hp[i][2] = fmaf(v, ha.z, hp[i][2]);
-              hp[i][3] = fmaf(v, ha.w, hp[i][3]);
-              hp[i][4] = fmaf(v, hb.x, hp[i][4]);
-              hp[i][5] = fmaf(v, hb.y, hp[i][5]);
+              const unsigned long long vv = pack_f32x2(v, v);
+              ffma2(hp2[i][0], vv, h01);
+              ffma2(hp2[i][1], vv, h23);
+              ffma2(hp2[i][2], vv, h45);
             }
           }
+        float hp[2][6];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) unpack_f32x2(hp2[i][q], hp[i][2 * q], hp[i][2 * q + 1]);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
