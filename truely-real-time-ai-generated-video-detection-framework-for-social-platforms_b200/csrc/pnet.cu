@@ -32,8 +32,13 @@ constexpr int P1PX = 736;                    // 720 pixels + slack read by conv2
 constexpr int P1WORDS = 5;                   // 10 channels = 5 half2 words per pixel (hi plane, lo plane)
 constexpr int C2H = TOY + 2, C2P = 36;       // conv2 tile: 18 rows at the same pitch as its input (flat indexing)
 constexpr int C2PX = C2H * C2P;              // 648 pixels (columns 34, 35 of a row are never read)
-constexpr int C2WORDS = 8;                   // 16 channels = 8 half2 words per pixel
 constexpr int C2TILES = (C2PX + 15) / 16;    // 41 M tiles of two 8-pixel segments
+// conv2 output = conv3's UMMA A operand: four planes [hi k0, hi k1, lo k0, lo k1] of [pixel][8 channels = 16 B]
+// (no-swizzle K-major core matrices: 8 consecutive pixels x 16 B; k-half stride = plane, 8-pixel stride = 128 B)
+constexpr int C2NP = 720;                    // pixels per plane: 648 computed + slack read by the last (partial) M tile
+constexpr int C2PLANE = C2NP * 4;            // words per plane
+constexpr int C3TILES = 5;                   // conv3 M tiles of 128 flat pixels (16 rows x pitch 36 = 576 = 4.5 tiles)
+constexpr int TMEM_COLS = 256;               // tiles 0-2: 64 columns each, tiles 3-4: 32 columns each
 constexpr int INH = 2 * TOY + 10, INW = 2 * TOX + 10;   // 42 x 74 input tile
 constexpr int INP = 76;
 
@@ -48,21 +53,19 @@ constexpr int W2 = A1 + 12;           // half2 B fragments: [6 k-steps][hi, lo][
 constexpr int T2 = W2 + 6 * 2 * 32 * 4;   // int[48]: p1 word offset of channel pair P (see conv2_pair())
 constexpr int B2 = T2 + 48;           // [16]
 constexpr int A2 = B2 + 16;           // [16]
-constexpr int W3 = A2 + 16;           // half2 B fragments: [9 taps][hi, lo][2 n-tile pairs][32 lanes][4]
-constexpr int B3 = W3 + 9 * 2 * 2 * 32 * 4;
-constexpr int A3 = B3 + 32;
-constexpr int WH = A3 + 32;           // fp32 [32][8]: cols 0,1 conv4_1; 2..5 conv4_2
+constexpr int W3 = A2 + 16;           // UMMA B operand: [9 taps][k-half][64 rows: w_hi[32], w_lo[32]][8 channels as fp16]
+constexpr int WH = W3 + 9 * 2 * 64 * 4;   // fp32 [32][8]: conv4_1 (2), conv4_2 (4), conv3 bias, conv3 PReLU slope
 constexpr int BH = WH + 32 * 8;       // [8]
 constexpr int SC = BH + 8;            // [4]: 1 / (SA * S_w2), 1 / (SA * S_w3)
 constexpr int WTOTAL = SC + 4;
-static_assert(WTOTAL % 4 == 0 && W2 % 4 == 0 && W3 % 4 == 0, "16-byte alignment of the fragment arrays");
+static_assert(WTOTAL % 4 == 0 && W2 % 4 == 0 && W3 % 4 == 0 && WH % 4 == 0, "16-byte alignment of the operand arrays");
 
 constexpr int SM_IN = 3 * INH * INP;                 // 9576 words
-constexpr int SM_C2 = 2 * C2PX * C2WORDS;            // 10368 words (aliases the input tile)
+constexpr int SM_C2 = 4 * C2PLANE;                   // 11520 words (aliases the input tile)
 constexpr int SM_A = SM_C2 > SM_IN ? SM_C2 : SM_IN;
 constexpr int SM_P1 = 2 * P1PX * P1WORDS;            // 7360 words
 constexpr int SMEM_WORDS = WTOTAL + SM_A + SM_P1;
-constexpr int SMEM_BYTES = SMEM_WORDS * 4;           // ~97 KB -> 2 CTAs / SM
+constexpr int SMEM_BYTES = SMEM_WORDS * 4;           // ~100 KB -> 2 CTAs / SM
 
 struct Level {
   const float* in;     // [B][3][hs][pitch]
@@ -109,6 +112,45 @@ __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint3
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// ---- tcgen05 (conv3): D[128 px x N] (TMEM, fp32) += A[128 px x 16 ch] (smem) * B[N x 16 ch] (smem), fp16 operands
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .pred px;\nelect.sync _|px, %1;\n@px mov.s32 %0, 1;\n}\n" : "+r"(pred) : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+// no-swizzle K-major descriptor: start >> 4 | (k-half stride >> 4) << 16 | (8-row stride >> 4) << 32 | version 1 << 46
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) __trap();        // ~2 s: a lost commit must not hang the device
+  }
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                         uint32_t b1) {
   asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -117,7 +159,9 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1,
 }
 
 __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ wpacked, const __grid_constant__ Params p) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t mma_bar[C3TILES];   // one single-use barrier per conv3 M tile (tcgen05.commit arrives)
+  __shared__ uint32_t tmem_slot;
   float* w_s = smem;
   float* a_s = smem + WTOTAL;                                        // fp32 input tile, later the conv2 output
   uint32_t* c2_s = reinterpret_cast<uint32_t*>(a_s);                 // [hi, lo][C2PX][8]
@@ -126,10 +170,23 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);        // warp-uniform copy (keeps the MMA issue path in uniform registers)
   bool range_bad = false;
 #ifdef PNET_TIMING
   long long tph[5]; tph[0] = clock64();
 #endif
+  // TMEM for the conv3 accumulators: allocated up front (the allocator may have to wait for the co-resident CTA's
+  // predecessor to release its columns), published through shared memory by the first __syncthreads below
+  if (warp_u == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < C3TILES; ++i)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mma_bar[i])), "r"(1u) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
 
   int lvl = 0;
   while (lvl + 1 < p.n_levels && (int)blockIdx.x >= p.blk_start[lvl + 1]) ++lvl;
@@ -177,7 +234,9 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #ifdef PNET_TIMING
   tph[1] = clock64();
 #endif
@@ -321,7 +380,6 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
         }
       }
       // epilogue: unscale, bias, PReLU, split; lane holds channels (2t, 2t+1) + 8 j of pixels g and g + 8.
-      // conv3 wants the pair words of a pixel in the order (0,4,1,5,2,6,3,7): pair 4 j + t sits at word 2 t + j.
       const float bias0 = w_s[B2 + 2 * t], bias1 = w_s[B2 + 2 * t + 1], bias2 = w_s[B2 + 8 + 2 * t], bias3 = w_s[B2 + 9 + 2 * t];
       const float al0 = w_s[A2 + 2 * t], al1 = w_s[A2 + 2 * t + 1], al2 = w_s[A2 + 8 + 2 * t], al3 = w_s[A2 + 9 + 2 * t];
 #pragma unroll
@@ -340,155 +398,144 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
             uint32_t h0, l0, h1, l1;
             split_h2(v0 * SA, v1 * SA, h0, l0);
             split_h2(v2 * SA, v3 * SA, h1, l1);
-            *reinterpret_cast<uint2*>(&c2_s[n * C2WORDS + 2 * t]) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(&c2_s[C2PX * C2WORDS + n * C2WORDS + 2 * t]) = make_uint2(l0, l1);
+            c2_s[0 * C2PLANE + n * 4 + t] = h0;      // hi, channels 0-7   (a warp writes 32 consecutive words)
+            c2_s[1 * C2PLANE + n * 4 + t] = h1;      // hi, channels 8-15
+            c2_s[2 * C2PLANE + n * 4 + t] = l0;
+            c2_s[3 * C2PLANE + n * 4 + t] = l1;
           }
         }
       }
     }
   }
+
+  // ---- conv3 (16->32, 3x3) as tcgen05 implicit GEMMs + PReLU + heads.
+  // Flat indexing again: output pixel n = row * 36 + col reads conv2 pixels n + ky * 36 + kx, so the A operand of
+  // filter tap (ky, kx) is the same shared-memory image with its start address moved by (ky * 36 + kx) * 16 bytes --
+  // no im2col copy.  One M tile = 128 flat pixels, one MMA = one tap x 16 channels (K = 16).  The 3-term split
+  //   a_hi w_hi + a_hi w_lo + a_lo w_hi
+  // costs two MMAs per tap on tiles 0-2 (B = [w_hi | w_lo] as N = 64, then a_lo x w_hi as N = 32 into the first 32
+  // columns; the epilogue adds the two column blocks) and three N = 32 MMAs per tap on tiles 3-4 (all into one
+  // 32-column block), so that the five accumulators fit the CTA's 256 TMEM columns (2 CTAs / SM).
+  // One elected thread issues everything; each tile's commit releases its epilogue (thread = pixel: 32 channels
+  // -> bias, PReLU, heads, softmax, candidate append; no cross-lane traffic).
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // c2 planes and weights -> visible to the UMMA proxy
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #ifdef PNET_TIMING
   tph[3] = clock64();
 #endif
-
-  // ---- conv3 (16->32, 3x3) on the tensor pipe + PReLU + heads.
-  // warp w owns output rows 2w, 2w+1; one pass = one row = two 16-pixel M tiles x four 8-channel N tiles; one k16 step
-  // = one filter tap x 16 channels.  The A words of a pixel are ordered so that (a0, a2) is one 64-bit load:
-  // a half-warp (g = 0..3) then reads 32 consecutive words, conflict free.
-  {
-    const uint32_t* c2h = c2_s;
-    const uint32_t* c2l = c2_s + C2PX * C2WORDS;
-    const float inv = w_s[SC + 1];
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const int row = 2 * warp + pass;
-      float acc[2][4][4];
+  const uint32_t tmem = tmem_slot;
+  if (warp_u == 0) {
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t a_base = __shfl_sync(0xffffffffu, smem_u32(c2_s), 0);
+    const uint32_t b_base = __shfl_sync(0xffffffffu, smem_u32(w_s + W3), 0);
+    constexpr uint32_t IDESC32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);   // f32 accumulate, f16 x f16, K-major
+    constexpr uint32_t IDESC64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t APL = C2PLANE * 4;                                                // plane stride in bytes
+    if (elect_one()) {
 #pragma unroll
-      for (int m = 0; m < 2; ++m)
+      for (int tile = 0; tile < C3TILES; ++tile) {
+        const uint32_t d = tm + (tile < 3 ? 64u * tile : 192u + 32u * (tile - 3));
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
-#pragma unroll 3
-      for (int tap = 0; tap < 9; ++tap) {
-        const int ky = tap / 3, kx = tap - 3 * ky;
-        const int abase = ((row + ky) * C2P + kx + g) * C2WORDS + 2 * t;
-        const uint32_t* wf = wu + W3 + tap * (2 * 2 * 32 * 4) + lane * 4;
-        const uint4 bh0 = *reinterpret_cast<const uint4*>(wf);              // n-tiles 0,1: (b0,b1),(b0,b1)
-        const uint4 bh1 = *reinterpret_cast<const uint4*>(wf + 128);        // n-tiles 2,3
-        const uint4 bl0 = *reinterpret_cast<const uint4*>(wf + 256);
-        const uint4 bl1 = *reinterpret_cast<const uint4*>(wf + 384);
-        uint2 ah[2][2], al[2][2];        // [m tile][pixel g / g+8] = (a0|a1, a2|a3)
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            ah[m][h] = *reinterpret_cast<const uint2*>(&c2h[abase + (16 * m + 8 * h) * C2WORDS]);
-            al[m][h] = *reinterpret_cast<const uint2*>(&c2l[abase + (16 * m + 8 * h) * C2WORDS]);
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t a_off = (uint32_t)(tile * 128 + (tap / 3) * C2P + (tap % 3)) * 16u;
+          const uint64_t a_hi = umma_desc(a_base + a_off, APL, 128u);
+          const uint64_t a_lo = umma_desc(a_base + 2u * APL + a_off, APL, 128u);
+          const uint64_t b_hl = umma_desc(b_base + (uint32_t)tap * 2048u, 1024u, 128u);            // rows 0-31 w_hi, 32-63 w_lo
+          if (tile < 3) {
+            umma_f16(d, a_hi, b_hl, IDESC64, tap > 0 ? 1u : 0u);
+            umma_f16(d, a_lo, b_hl, IDESC32, 1u);
+          } else {
+            const uint64_t b_lo = umma_desc(b_base + (uint32_t)tap * 2048u + 512u, 1024u, 128u);
+            umma_f16(d, a_hi, b_hl, IDESC32, tap > 0 ? 1u : 0u);
+            umma_f16(d, a_lo, b_hl, IDESC32, 1u);
+            umma_f16(d, a_hi, b_lo, IDESC32, 1u);
           }
+        }
+        umma_commit(&mma_bar[tile]);
+      }
+    }
+    __syncwarp();
+  }
+  {
+    const float inv = w_s[SC + 1];
+    const int lg = warp & 3;                      // TMEM lane group this warp may read
+    for (int tile = warp >> 2; tile < C3TILES; tile += 2) {
+      if (tile == 4 && lg >= 2) break;            // flat pixels >= 576 do not exist
+      mbar_wait(&mma_bar[tile], 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (tile < 3 ? 64u * tile : 192u + 32u * (tile - 3));
+      unsigned long long hp2[3] = {0ull, 0ull, 0ull};
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          mma_f16(acc[m][0], al[m][0].x, al[m][1].x, al[m][0].y, al[m][1].y, bh0.x, bh0.y);
-          mma_f16(acc[m][1], al[m][0].x, al[m][1].x, al[m][0].y, al[m][1].y, bh0.z, bh0.w);
-          mma_f16(acc[m][2], al[m][0].x, al[m][1].x, al[m][0].y, al[m][1].y, bh1.x, bh1.y);
-          mma_f16(acc[m][3], al[m][0].x, al[m][1].x, al[m][0].y, al[m][1].y, bh1.z, bh1.w);
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        float dh[16];
+        tmem_ld16(taddr + c0, dh);
+        if (tile < 3) {
+          float dl[16];
+          tmem_ld16(taddr + 32 + c0, dl);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dh[j] += dl[j];
+        } else {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         }
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          mma_f16(acc[m][0], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bl0.x, bl0.y);
-          mma_f16(acc[m][1], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bl0.z, bl0.w);
-          mma_f16(acc[m][2], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bl1.x, bl1.y);
-          mma_f16(acc[m][3], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bl1.z, bl1.w);
-        }
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          mma_f16(acc[m][0], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bh0.x, bh0.y);
-          mma_f16(acc[m][1], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bh0.z, bh0.w);
-          mma_f16(acc[m][2], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bh1.x, bh1.y);
-          mma_f16(acc[m][3], ah[m][0].x, ah[m][1].x, ah[m][0].y, ah[m][1].y, bh1.z, bh1.w);
+        for (int j = 0; j < 16; ++j) {
+          const float4 ha = *reinterpret_cast<const float4*>(&w_s[WH + (c0 + j) * 8]);      // h0..h3
+          const float4 hb = *reinterpret_cast<const float4*>(&w_s[WH + (c0 + j) * 8 + 4]);  // h4, h5, bias, slope
+          const float v = prelu(fmaf(dh[j], inv, hb.z), hb.w);
+          const unsigned long long vv = pack_f32x2(v, v);
+          ffma2(hp2[0], vv, pack_f32x2(ha.x, ha.y));
+          ffma2(hp2[1], vv, pack_f32x2(ha.z, ha.w));
+          ffma2(hp2[2], vv, pack_f32x2(hb.x, hb.y));
         }
       }
-      // epilogue: bias + PReLU, heads (6 outputs over 32 channels; this thread holds 8 channels of 2 pixels per tile)
+      float h[6];
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        unsigned long long hp2[2][3];
+      for (int q = 0; q < 3; ++q) unpack_f32x2(hp2[q], h[2 * q], h[2 * q + 1]);
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int q = 0; q < 3; ++q) hp2[i][q] = 0ull;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int co = 8 * j + 2 * t + e;
-            const float bias = w_s[B3 + co], al3 = w_s[A3 + co];
-            const float4 ha = *reinterpret_cast<const float4*>(&w_s[WH + co * 8]);
-            const float2 hb = *reinterpret_cast<const float2*>(&w_s[WH + co * 8 + 4]);
-            const unsigned long long h01 = pack_f32x2(ha.x, ha.y), h23 = pack_f32x2(ha.z, ha.w), h45 = pack_f32x2(hb.x, hb.y);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float v = prelu(fmaf(acc[m][j][2 * i + e], inv, bias), al3);
-              const unsigned long long vv = pack_f32x2(v, v);
-              ffma2(hp2[i][0], vv, h01);
-              ffma2(hp2[i][1], vv, h23);
-              ffma2(hp2[i][2], vv, h45);
-            }
-          }
-        float hp[2][6];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int q = 0; q < 3; ++q) unpack_f32x2(hp2[i][q], hp[i][2 * q], hp[i][2 * q + 1]);
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            hp[i][q] += __shfl_xor_sync(0xffffffffu, hp[i][q], 1);
-            hp[i][q] += __shfl_xor_sync(0xffffffffu, hp[i][q], 2);
-          }
-        // lanes t = 0 / 1 finish pixels g / g+8 of this tile
-        if (t < 2) {
-          float h[6];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) h[q] = (t == 0 ? hp[0][q] : hp[1][q]) + w_s[BH + q];
-          const int oy = oy0 + row, ox = ox0 + 16 * m + g + 8 * t;
-          if (oy < L.oh && ox < L.ow) {
-            // softmax over (h0, h1), class 1 -- same form as ATen's softmax (subtract max, exp, normalise)
-            const float mx = fmaxf(h[0], h[1]);
-            const float e0 = expf(h[0] - mx), e1 = expf(h[1] - mx);
-            const float prob = __fdiv_rn(e1, e0 + e1);
-            const size_t cell = (size_t)oy * L.ow + ox;
-            if (L.prob) {
-              const size_t plane = (size_t)L.oh * L.ow;
-              L.prob[(size_t)b * plane + cell] = prob;
-              float* rg = L.reg + (size_t)b * 4 * plane + cell;
-              rg[0] = h[2]; rg[plane] = h[3]; rg[2 * plane] = h[4]; rg[3 * plane] = h[5];
-            }
-            if (L.cand && prob >= p.thr) {
-              // generateBoundingBox: q1 = floor((2*c + 1)/scale), q2 = floor((2*c + 12)/scale)  (fp32, true division)
-              const int slotbase = b * p.n_levels + lvl;
-              const int slot = atomicAdd(&L.cnt[slotbase], 1);
-              if (slot < p.cap) {
-                Cand cd;
-                cd.x1 = floorf(__fdiv_rn((float)(2 * ox + 1), L.scale));
-                cd.y1 = floorf(__fdiv_rn((float)(2 * oy + 1), L.scale));
-                cd.x2 = floorf(__fdiv_rn((float)(2 * ox + 12), L.scale));
-                cd.y2 = floorf(__fdiv_rn((float)(2 * oy + 12), L.scale));
-                cd.score = prob;
-                cd.r0 = h[2]; cd.r1 = h[3]; cd.r2 = h[4]; cd.r3 = h[5];
-                cd.key = (uint32_t)cell;
-                L.cand[(size_t)slotbase * p.cap + slot] = cd;
-              } else if (p.capflag) {
-                p.capflag->overflow = 1; p.capflag->stage = 1; p.capflag->frame = b;
-                p.capflag->count = slot + 1; p.capflag->capacity = p.cap;
-              }
-            }
+      for (int q = 0; q < 6; ++q) h[q] += w_s[BH + q];
+      const int n = tile * 128 + lg * 32 + lane;
+      const int row = n / C2P, col = n - row * C2P;
+      const int oy = oy0 + row, ox = ox0 + col;
+      if (row < TOY && col < TOX && oy < L.oh && ox < L.ow) {
+        // softmax over (h0, h1), class 1 -- same form as ATen's softmax (subtract max, exp, normalise)
+        const float mx = fmaxf(h[0], h[1]);
+        const float e0 = expf(h[0] - mx), e1 = expf(h[1] - mx);
+        const float prob = __fdiv_rn(e1, e0 + e1);
+        const size_t cell = (size_t)oy * L.ow + ox;
+        if (L.prob) {
+          const size_t plane = (size_t)L.oh * L.ow;
+          L.prob[(size_t)b * plane + cell] = prob;
+          float* rg = L.reg + (size_t)b * 4 * plane + cell;
+          rg[0] = h[2]; rg[plane] = h[3]; rg[2 * plane] = h[4]; rg[3 * plane] = h[5];
+        }
+        if (L.cand && prob >= p.thr) {
+          // generateBoundingBox: q1 = floor((2*c + 1)/scale), q2 = floor((2*c + 12)/scale)  (fp32, true division)
+          const int slotbase = b * p.n_levels + lvl;
+          const int slot = atomicAdd(&L.cnt[slotbase], 1);
+          if (slot < p.cap) {
+            Cand cd;
+            cd.x1 = floorf(__fdiv_rn((float)(2 * ox + 1), L.scale));
+            cd.y1 = floorf(__fdiv_rn((float)(2 * oy + 1), L.scale));
+            cd.x2 = floorf(__fdiv_rn((float)(2 * ox + 12), L.scale));
+            cd.y2 = floorf(__fdiv_rn((float)(2 * oy + 12), L.scale));
+            cd.score = prob;
+            cd.r0 = h[2]; cd.r1 = h[3]; cd.r2 = h[4]; cd.r3 = h[5];
+            cd.key = (uint32_t)cell;
+            L.cand[(size_t)slotbase * p.cap + slot] = cd;
+          } else if (p.capflag) {
+            p.capflag->overflow = 1; p.capflag->stage = 1; p.capflag->frame = b;
+            p.capflag->count = slot + 1; p.capflag->capacity = p.cap;
           }
         }
       }
     }
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp_u == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
   if (range_bad && p.capflag) {
     p.capflag->overflow = 1; p.capflag->stage = 5; p.capflag->frame = b;
     p.capflag->count = 0; p.capflag->capacity = (int)ACT_MAX;
@@ -593,25 +640,23 @@ int pnet_pack_weights(trl_ctx* c, const float* h, size_t len) {
       }
     }
   for (int co = 0; co < 16; ++co) { pk[B2 + co] = b2[co]; pk[A2 + co] = a2[co]; }
-  // conv3 B fragments: k16 step = tap, b0 = channels (2t, 2t+1), b1 = channels (2t+8, 2t+9); n = g + 8 j
+  // conv3 UMMA B operand: [tap][k-half][row: w_hi of channel co = row (0-31), w_lo of co = row - 32][8 input channels]
   for (int tap = 0; tap < 9; ++tap)
-    for (int lane = 0; lane < 32; ++lane) {
-      const int g = lane >> 2, t = lane & 3;
-      for (int j = 0; j < 4; ++j)
-        for (int i = 0; i < 2; ++i) {
-          const int co = 8 * j + g, ci = 2 * t + 8 * i;
+    for (int kh = 0; kh < 2; ++kh)
+      for (int co = 0; co < 32; ++co)
+        for (int cp = 0; cp < 4; ++cp) {
+          const int ci = 8 * kh + 2 * cp;
           uint32_t hi, lo;
           split_pair(w3[co * 144 + ci * 9 + tap], w3[co * 144 + (ci + 1) * 9 + tap], s3, &hi, &lo);
-          const int word = ((j >> 1) * 32 + lane) * 4 + 2 * (j & 1) + i;
-          pu[W3 + tap * 512 + 0 * 256 + word] = hi;
-          pu[W3 + tap * 512 + 1 * 256 + word] = lo;
+          pu[W3 + ((tap * 2 + kh) * 64 + co) * 4 + cp] = hi;
+          pu[W3 + ((tap * 2 + kh) * 64 + 32 + co) * 4 + cp] = lo;
         }
-    }
-  for (int co = 0; co < 32; ++co) { pk[B3 + co] = b3[co]; pk[A3 + co] = a3[co]; }
   for (int ci = 0; ci < 32; ++ci) {
     pk[WH + ci * 8 + 0] = w41[0 * 32 + ci];
     pk[WH + ci * 8 + 1] = w41[1 * 32 + ci];
     for (int j = 0; j < 4; ++j) pk[WH + ci * 8 + 2 + j] = w42[j * 32 + ci];
+    pk[WH + ci * 8 + 6] = b3[ci];
+    pk[WH + ci * 8 + 7] = a3[ci];
   }
   pk[BH + 0] = b41[0]; pk[BH + 1] = b41[1];
   for (int j = 0; j < 4; ++j) pk[BH + 2 + j] = b42[j];
