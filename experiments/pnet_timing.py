@@ -1,5 +1,5 @@
-"""Phase timing of pnet_kernel (debug build with -DPNET_TIMING): average clock64 cycles a CTA spends in
-staging / conv1 / conv2 / conv3+heads.  Usage (GPU box): python experiments/pnet_timing.py
+"""Phase timing of pnet_kernel (debug build with -DPNET_TIMING): average clock64 cycles per tile that group A (staging +
+conv1) and group B (conv2, conv3 + heads) spend waiting and computing.  Usage (GPU box): python experiments/pnet_timing.py
 The timing .so is built next to this script and never replaces the product library."""
 import ctypes as C
 import glob
@@ -40,8 +40,6 @@ if __name__ == "__main__":
         torch.cuda.synchronize()
         buf = (C.c_ulonglong * 8)()
         lib.trl_debug_pnet_timing(buf)
-        n = buf[4]
-        names = ["stage", "conv1", "conv2", "conv3+heads"]
-        tot = sum(buf[i] for i in range(4))
-        print(f"iter {it}: {n} CTAs, {tot / max(n, 1):.0f} cycles/CTA resident: " +
-              ", ".join(f"{names[i]} {buf[i] / max(n, 1):.0f} ({100 * buf[i] / max(tot, 1):.0f}%)" for i in range(4)))
+        n = max(buf[5], 1)
+        print(f"iter {it}: {buf[5]} tiles; cycles per tile: group A wait {buf[0] / n:.0f}, conv1 {buf[1] / n:.0f} | "
+              f"group B wait {buf[2] / n:.0f}, conv2 {buf[3] / n:.0f}, conv3+heads {buf[4] / n:.0f}")

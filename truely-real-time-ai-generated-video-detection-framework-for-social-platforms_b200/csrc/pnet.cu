@@ -38,7 +38,8 @@ constexpr int C2TILES = (C2PX + 15) / 16;    // 41 M tiles of two 8-pixel segmen
 constexpr int C2NP = 720;                    // pixels per plane: 648 computed + slack read by the last (partial) M tile
 constexpr int C2PLANE = C2NP * 4;            // words per plane
 constexpr int C3TILES = 5;                   // conv3 M tiles of 128 flat pixels (16 rows x pitch 36 = 576 = 4.5 tiles)
-constexpr int TMEM_COLS = 256;               // tiles 0-2: 64 columns each, tiles 3-4: 32 columns each
+constexpr int TMEM_COLS = 512;               // 5 accumulators of 64 columns (one CTA per SM owns the whole TMEM)
+constexpr int NTHREADS = 512;                // warps 0-7: staging + conv1, warps 8-15: conv2 + conv3 + heads
 constexpr int INH = 2 * TOY + 10, INW = 2 * TOX + 10;   // 42 x 74 input tile
 constexpr int INP = 76;
 
@@ -61,11 +62,11 @@ constexpr int WTOTAL = SC + 4;
 static_assert(WTOTAL % 4 == 0 && W2 % 4 == 0 && W3 % 4 == 0 && WH % 4 == 0, "16-byte alignment of the operand arrays");
 
 constexpr int SM_IN = 3 * INH * INP;                 // 9576 words
-constexpr int SM_C2 = 4 * C2PLANE;                   // 11520 words (aliases the input tile)
-constexpr int SM_A = SM_C2 > SM_IN ? SM_C2 : SM_IN;
+constexpr int SM_C2 = 4 * C2PLANE;                   // 11520 words
 constexpr int SM_P1 = 2 * P1PX * P1WORDS;            // 7360 words
-constexpr int SMEM_WORDS = WTOTAL + SM_A + SM_P1;
-constexpr int SMEM_BYTES = SMEM_WORDS * 4;           // ~100 KB -> 2 CTAs / SM
+constexpr int SMEM_WORDS = WTOTAL + 2 * SM_IN + 2 * SM_P1 + SM_C2;    // weights, 2 input tiles, 2 pooled conv1 tiles, conv2 planes
+constexpr int SMEM_BYTES = SMEM_WORDS * 4;           // ~206 KB -> one persistent CTA per SM
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct Level {
   const float* in;     // [B][3][hs][pitch]
@@ -80,6 +81,8 @@ struct Level {
 
 struct Params {
   int n_levels;
+  int blocks;          // tiles per frame (all levels)
+  int n_frames;
   int blk_start[TRL_MAX_SCALES + 1];
   Level lv[TRL_MAX_SCALES];
   float thr;
@@ -158,25 +161,47 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1,
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ wpacked, const __grid_constant__ Params p) {
+// tile id -> (frame, level, tile origin); uniform per call
+struct TileRef { int b, lvl, oy0, ox0; };
+__device__ __forceinline__ TileRef decode_tile(const Params& p, int id) {
+  TileRef r;
+  r.b = id / p.blocks;
+  const int blk = id - r.b * p.blocks;
+  int lvl = 0;
+  while (lvl + 1 < p.n_levels && blk >= p.blk_start[lvl + 1]) ++lvl;
+  const int tile = blk - p.blk_start[lvl];
+  const int ty = tile / p.lv[lvl].tiles_x;
+  r.lvl = lvl; r.oy0 = ty * TOY; r.ox0 = (tile - ty * p.lv[lvl].tiles_x) * TOX;
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent, warp-specialised: one CTA per SM walks the tile list.  Warps 0-7 (group A) stage the input tile
+// (cp.async, double buffered) and run conv1 on the FMA pipe; warps 8-15 (group B) run conv2 (mma.sync), issue conv3
+// (tcgen05) and do the head epilogue.  The pooled conv1 tile is double buffered between the groups (full / empty
+// mbarriers), so conv1 of tile k+1 overlaps conv2 / conv3 of tile k and the FMA pipe, the tensor pipe and the
+// issue slots are busy at the same time.  Weights are loaded once per CTA.
+__global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restrict__ wpacked, const __grid_constant__ Params p) {
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t mma_bar[C3TILES];   // one single-use barrier per conv3 M tile (tcgen05.commit arrives)
+  __shared__ __align__(8) uint64_t mma_bar[C3TILES];   // tcgen05.commit of conv3 M tile i (one phase per tile of the list)
+  __shared__ __align__(8) uint64_t p1_full[2], p1_empty[2];
   __shared__ uint32_t tmem_slot;
   float* w_s = smem;
-  float* a_s = smem + WTOTAL;                                        // fp32 input tile, later the conv2 output
-  uint32_t* c2_s = reinterpret_cast<uint32_t*>(a_s);                 // [hi, lo][C2PX][8]
-  uint32_t* p1_s = reinterpret_cast<uint32_t*>(a_s + SM_A);          // [hi, lo][P1PX][5]
+  float* in_base = smem + WTOTAL;                                             // [2][SM_IN] fp32 input tiles
+  uint32_t* p1_base = reinterpret_cast<uint32_t*>(in_base + 2 * SM_IN);       // [2][hi, lo][P1PX][5]
+  uint32_t* c2_s = p1_base + 2 * SM_P1;                                       // [hi k0, hi k1, lo k0, lo k1][C2NP][4]
   const uint32_t* wu = reinterpret_cast<const uint32_t*>(w_s);
   const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
+  const int lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);        // warp-uniform copy (keeps the MMA issue path in uniform registers)
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);    // warp-uniform copy (keeps the MMA issue path in uniform registers)
   bool range_bad = false;
 #ifdef PNET_TIMING
-  long long tph[5]; tph[0] = clock64();
+  long long tw = 0, tc1 = 0, tc2 = 0, tc3 = 0, tmark;
 #endif
-  // TMEM for the conv3 accumulators: allocated up front (the allocator may have to wait for the co-resident CTA's
-  // predecessor to release its columns), published through shared memory by the first __syncthreads below
+
   if (warp_u == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -184,69 +209,92 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
 #pragma unroll
       for (int i = 0; i < C3TILES; ++i)
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mma_bar[i])), "r"(1u) : "memory");
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&p1_full[i])), "r"(256u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&p1_empty[i])), "r"(256u) : "memory");
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
-
-  int lvl = 0;
-  while (lvl + 1 < p.n_levels && (int)blockIdx.x >= p.blk_start[lvl + 1]) ++lvl;
-  const Level& L = p.lv[lvl];
-  const int b = blockIdx.y;
-  const int tile = (int)blockIdx.x - p.blk_start[lvl];
-  const int ty = tile / L.tiles_x, tx = tile - ty * L.tiles_x;
-  const int oy0 = ty * TOY, ox0 = tx * TOX;
-  const int hs = L.hs, ws = L.ws;
-
-  // ---- stage weights and the input tile with cp.async (LDGSTS): every copy of a thread is in flight at once, so
-  // the tile costs one L2 round trip instead of one per unrolled load group; out-of-image elements are zero filled
-  // (src-size 0).
+  // weights (once per CTA) + the slack pixels of both p1 buffers (read by conv2's last M tile, never written by conv1)
   {
-    const uint32_t w_dst = (uint32_t)__cvta_generic_to_shared(w_s);
-    for (int i = tid; i < WTOTAL / 4; i += 256)
+    const uint32_t w_dst = smem_u32(w_s);
+    for (int i = tid; i < WTOTAL / 4; i += NTHREADS)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(w_dst + 16u * i), "l"(wpacked + 4 * i) : "memory");
-    const int pitch = L.pitch;
-    const float* src = L.in + (size_t)b * 3 * hs * pitch;
-    const int iy0 = 2 * oy0, ix0 = 2 * ox0;
-    const uint32_t a_dst = (uint32_t)__cvta_generic_to_shared(a_s);
-    if ((pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(L.in) & 15) == 0) {
-      // 16-byte rows (the cascade's padded pyramid): 19 chunks per tile row, partial chunks zero filled by src-size
-      constexpr int CH = INP / 4;
-      for (int i = tid; i < 3 * INH * CH; i += 256) {
-        const int rr = i / CH, j = i - rr * CH;          // rr = ci * INH + r
-        const int ci = rr / INH, r = rr - ci * INH;
-        const int gy = iy0 + r, gx = ix0 + 4 * j;
-        const int nb = gy < hs ? min(max(ws - gx, 0), 4) * 4 : 0;
-        const float* gp = nb ? src + ((size_t)ci * hs + gy) * pitch + gx : src;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
-                     ::"r"(a_dst + 16u * (uint32_t)i), "l"(gp), "r"(nb) : "memory");
-      }
-    } else {
-      for (int i = tid; i < 3 * INH * INW; i += 256) {
-        const int ci = i / (INH * INW);
-        const int r = (i - ci * INH * INW) / INW;
-        const int cx = i - ci * INH * INW - r * INW;
-        const int gy = iy0 + r, gx = ix0 + cx;
-        const bool ok = gy < hs && gx < ws;
-        const float* gp = ok ? src + ((size_t)ci * hs + gy) * pitch + gx : src;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
-                     ::"r"(a_dst + 4u * ((ci * INH + r) * INP + cx)), "l"(gp), "r"(ok ? 4 : 0) : "memory");
-      }
-    }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    for (int i = tid; i < 2 * 2 * (P1PX - P1H * P1W) * P1WORDS; i += NTHREADS) {
+      const int per = (P1PX - P1H * P1W) * P1WORDS;
+      const int plane = i / per, off = i - plane * per;                       // plane = buf * 2 + (hi | lo)
+      p1_base[plane * (P1PX * P1WORDS) + P1H * P1W * P1WORDS + off] = 0u;
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#ifdef PNET_TIMING
-  tph[1] = clock64();
-#endif
+  const uint32_t tmem = tmem_slot;
+  const int total = p.blocks * p.n_frames;
 
-  // ---- conv1 (3->10, 3x3) + PReLU + maxpool(2,2,ceil): one pooled pixel x 10 channels per item, written as
-  // scaled fp16 hi / lo channel pairs
-  {
-    const int c1h = hs - 2, c1w = ws - 2;     // valid conv1 extent (ceil-mode pooling clips to it)
+  if (warp_u < 8) {
+    // =================================================================== group A: input staging + conv1
+    // the tile is staged with cp.async (LDGSTS): every copy of a thread is in flight at once; out-of-image elements
+    // are zero filled (src-size 0)
+    auto issue_load = [&](int id, int buf) {
+      const TileRef tr = decode_tile(p, id);
+      const Level& Lv = p.lv[tr.lvl];
+      const int hs = Lv.hs, ws = Lv.ws, pitch = Lv.pitch;
+      const float* src = Lv.in + (size_t)tr.b * 3 * hs * pitch;
+      const int iy0 = 2 * tr.oy0, ix0 = 2 * tr.ox0;
+      const uint32_t a_dst = smem_u32(in_base + buf * SM_IN);
+      if ((pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(Lv.in) & 15) == 0) {
+        // 16-byte rows (the cascade's padded pyramid): 19 chunks per tile row, partial chunks zero filled by src-size
+        constexpr int CH = INP / 4;
+        for (int i = tid; i < 3 * INH * CH; i += 256) {
+          const int rr = i / CH, j = i - rr * CH;          // rr = ci * INH + r
+          const int ci = rr / INH, r = rr - ci * INH;
+          const int gy = iy0 + r, gx = ix0 + 4 * j;
+          const int nb = gy < hs ? min(max(ws - gx, 0), 4) * 4 : 0;
+          const float* gp = nb ? src + ((size_t)ci * hs + gy) * pitch + gx : src;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                       ::"r"(a_dst + 16u * (uint32_t)i), "l"(gp), "r"(nb) : "memory");
+        }
+      } else {
+        for (int i = tid; i < 3 * INH * INW; i += 256) {
+          const int ci = i / (INH * INW);
+          const int r = (i - ci * INH * INW) / INW;
+          const int cx = i - ci * INH * INW - r * INW;
+          const int gy = iy0 + r, gx = ix0 + cx;
+          const bool ok = gy < hs && gx < ws;
+          const float* gp = ok ? src + ((size_t)ci * hs + gy) * pitch + gx : src;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
+                       ::"r"(a_dst + 4u * ((ci * INH + r) * INP + cx)), "l"(gp), "r"(ok ? 4 : 0) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if ((int)blockIdx.x < total) issue_load(blockIdx.x, 0);
+    int k = 0;
+    for (int id = blockIdx.x; id < total; id += gridDim.x, ++k) {
+#ifdef PNET_TIMING
+      tmark = clock64();
+#endif
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // tile k landed for all of A; all of A is done reading tile k-1
+      if (id + (int)gridDim.x < total) issue_load(id + gridDim.x, (k + 1) & 1);
+      if (k >= 2) mbar_wait(&p1_empty[k & 1], ((k >> 1) - 1) & 1);      // group B is done with tile k-2's p1
+#ifdef PNET_TIMING
+      tw += clock64() - tmark; tmark = clock64();
+#endif
+      const TileRef tr = decode_tile(p, id);
+      const Level& Lv = p.lv[tr.lvl];
+      const int oy0 = tr.oy0, ox0 = tr.ox0;
+      const float* in_s = in_base + (k & 1) * SM_IN;
+      uint32_t* p1_s = p1_base + (k & 1) * SM_P1;
+      // ---- conv1 (3->10, 3x3) + PReLU + maxpool(2,2,ceil): one pooled pixel x 10 channels per item, written as
+      // scaled fp16 hi / lo channel pairs
+      const int c1h = Lv.hs - 2, c1w = Lv.ws - 2;     // valid conv1 extent (ceil-mode pooling clips to it)
 #pragma unroll 1
-    for (int item = tid; item < P1H * P1W; item += 256) {
+      for (int item = tid; item < P1H * P1W; item += 256) {
       asm volatile("" ::: "memory");          // keep the weight loads inside the loop (hoisted, they spill)
       const int py = item / P1W, px = item - py * P1W;
       float patch[3][4][4];
@@ -254,8 +302,8 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
       for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const float2 v0 = *reinterpret_cast<const float2*>(&a_s[(ci * INH + 2 * py + r) * INP + 2 * px]);
-          const float2 v1 = *reinterpret_cast<const float2*>(&a_s[(ci * INH + 2 * py + r) * INP + 2 * px + 2]);
+          const float2 v0 = *reinterpret_cast<const float2*>(&in_s[(ci * INH + 2 * py + r) * INP + 2 * px]);
+          const float2 v1 = *reinterpret_cast<const float2*>(&in_s[(ci * INH + 2 * py + r) * INP + 2 * px + 2]);
           patch[ci][r][0] = v0.x; patch[ci][r][1] = v0.y; patch[ci][r][2] = v1.x; patch[ci][r][3] = v1.y;
         }
       // packed fp32 pairs: FFMA2 (fma.rn.f32x2) does two channels per issued instruction, same rounding as FFMA
@@ -312,26 +360,37 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
         p1_s[P1PX * P1WORDS + item * P1WORDS + cp] = lo;
       }
     }
-    // slack pixels read by conv2's last M tile (their outputs are never used, but they must be finite)
-    for (int i = tid; i < (P1PX - P1H * P1W) * P1WORDS; i += 256) {
-      p1_s[P1H * P1W * P1WORDS + i] = 0u;
-      p1_s[P1PX * P1WORDS + P1H * P1W * P1WORDS + i] = 0u;
-    }
-  }
-  __syncthreads();
+      mbar_arrive(&p1_full[k & 1]);
 #ifdef PNET_TIMING
-  tph[2] = clock64();
+      tc1 += clock64() - tmark;
 #endif
-
-  // ---- conv2 (10->16, 3x3) + PReLU on the tensor pipe, output over the dead input tile.
-  // Flat implicit GEMM: output pixel n = row * 36 + col reads input pixels n + ky * 36 + kx, so an M tile is any
-  // two 8-pixel runs of the flat index (41 tiles cover the 18 x 36 tile, columns 34/35 are computed but unused).
-  // K = 90 as 45 channel pairs P = ky*15 + kx*5 + cp (+3 zero-weight pads) = 6 k16 steps; the word offset of pair P
-  // relative to the pixel comes from T2.  Fragment coordinates (PTX m16n8k16): g = lane/4, t = lane%4
-  //   A: a0 (px g, pair t)  a1 (px g+8, pair t)  a2 (px g, pair t+4)  a3 (px g+8, pair t+4)
-  //   B: b0 (pair t, n g)   b1 (pair t+4, n g)        C: c0,c1 (px g, n 2t, 2t+1)  c2,c3 (px g+8, ..)
-  {
-    const int* tab = reinterpret_cast<const int*>(w_s + T2);
+    }
+  } else {
+    // =================================================================== group B: conv2, conv3, heads
+    const int warp = warp_u - 8;
+    int k = 0;
+    for (int id = blockIdx.x; id < total; id += gridDim.x, ++k) {
+#ifdef PNET_TIMING
+      tmark = clock64();
+#endif
+      mbar_wait(&p1_full[k & 1], (k >> 1) & 1);
+      if (k >= 1) mbar_wait(&mma_bar[C3TILES - 1], (k - 1) & 1);      // conv3 of tile k-1 has consumed c2
+#ifdef PNET_TIMING
+      tw += clock64() - tmark; tmark = clock64();
+#endif
+      const TileRef tr = decode_tile(p, id);
+      const Level& Lv = p.lv[tr.lvl];
+      const int b = tr.b, lvl = tr.lvl, oy0 = tr.oy0, ox0 = tr.ox0;
+      const uint32_t* p1_s = p1_base + (k & 1) * SM_P1;
+      // ---- conv2 (10->16, 3x3) + PReLU on the tensor pipe (mma.sync).
+      // Flat implicit GEMM: output pixel n = row * 36 + col reads input pixels n + ky * 36 + kx, so an M tile is any
+      // two 8-pixel runs of the flat index (41 tiles cover the 18 x 36 tile, columns 34/35 are computed but unused).
+      // K = 90 as 45 channel pairs P = ky*15 + kx*5 + cp (+3 zero-weight pads) = 6 k16 steps; the word offset of pair
+      // P relative to the pixel comes from T2.  Fragment coordinates (PTX m16n8k16): g = lane/4, t = lane%4
+      //   A: a0 (px g, pair t)  a1 (px g+8, pair t)  a2 (px g, pair t+4)  a3 (px g+8, pair t+4)
+      //   B: b0 (pair t, n g)   b1 (pair t+4, n g)        C: c0,c1 (px g, n 2t, 2t+1)  c2,c3 (px g+8, ..)
+      {
+        const int* tab = reinterpret_cast<const int*>(w_s + T2);
     const uint32_t* p1h = p1_s;
     const uint32_t* p1l = p1_s + P1PX * P1WORDS;
     const float inv = w_s[SC + 0];
@@ -406,80 +465,67 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
         }
       }
     }
-  }
-
-  // ---- conv3 (16->32, 3x3) as tcgen05 implicit GEMMs + PReLU + heads.
-  // Flat indexing again: output pixel n = row * 36 + col reads conv2 pixels n + ky * 36 + kx, so the A operand of
-  // filter tap (ky, kx) is the same shared-memory image with its start address moved by (ky * 36 + kx) * 16 bytes --
-  // no im2col copy.  One M tile = 128 flat pixels, one MMA = one tap x 16 channels (K = 16).  The 3-term split
-  //   a_hi w_hi + a_hi w_lo + a_lo w_hi
-  // costs two MMAs per tap on tiles 0-2 (B = [w_hi | w_lo] as N = 64, then a_lo x w_hi as N = 32 into the first 32
-  // columns; the epilogue adds the two column blocks) and three N = 32 MMAs per tap on tiles 3-4 (all into one
-  // 32-column block), so that the five accumulators fit the CTA's 256 TMEM columns (2 CTAs / SM).
-  // One elected thread issues everything; each tile's commit releases its epilogue (thread = pixel: 32 channels
-  // -> bias, PReLU, heads, softmax, candidate append; no cross-lane traffic).
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // c2 planes and weights -> visible to the UMMA proxy
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      mbar_arrive(&p1_empty[k & 1]);
 #ifdef PNET_TIMING
-  tph[3] = clock64();
+      tc2 += clock64() - tmark; tmark = clock64();
 #endif
-  const uint32_t tmem = tmem_slot;
-  if (warp_u == 0) {
-    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
-    const uint32_t a_base = __shfl_sync(0xffffffffu, smem_u32(c2_s), 0);
-    const uint32_t b_base = __shfl_sync(0xffffffffu, smem_u32(w_s + W3), 0);
-    constexpr uint32_t IDESC32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);   // f32 accumulate, f16 x f16, K-major
-    constexpr uint32_t IDESC64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-    constexpr uint32_t APL = C2PLANE * 4;                                                // plane stride in bytes
-    if (elect_one()) {
+
+      // ---- conv3 (16->32, 3x3) as tcgen05 implicit GEMMs + PReLU + heads.
+      // Flat indexing again: output pixel n = row * 36 + col reads conv2 pixels n + ky * 36 + kx, so the A operand
+      // of filter tap (ky, kx) is the same shared-memory image with its start address moved by (ky * 36 + kx) * 16
+      // bytes -- no im2col copy.  One M tile = 128 flat pixels (5 tiles cover 16 rows x pitch 36), one MMA = one tap
+      // x 16 channels (K = 16).  The 3-term split a_hi w_hi + a_hi w_lo + a_lo w_hi costs two MMAs per tap:
+      // B = [w_hi | w_lo] as N = 64, then a_lo x w_hi as N = 32 into the first 32 columns; the epilogue adds the two
+      // column blocks.  One elected thread issues everything; each tile's commit releases its epilogue (thread =
+      // pixel: 32 channels -> bias, PReLU, heads, softmax, candidate append; no cross-lane traffic).
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // c2 planes -> visible to the UMMA proxy
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync 2, 256;" ::: "memory");                    // also: every epilogue of tile k-1 has read its D
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (warp == 0) {
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint32_t a_base = __shfl_sync(0xffffffffu, smem_u32(c2_s), 0);
+        const uint32_t b_base = __shfl_sync(0xffffffffu, smem_u32(w_s + W3), 0);
+        constexpr uint32_t IDESC32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);   // f32 accumulate, f16 x f16, K-major
+        constexpr uint32_t IDESC64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+        constexpr uint32_t APL = C2PLANE * 4;                                                // plane stride in bytes
+        if (elect_one()) {
 #pragma unroll
-      for (int tile = 0; tile < C3TILES; ++tile) {
-        const uint32_t d = tm + (tile < 3 ? 64u * tile : 192u + 32u * (tile - 3));
+          for (int tile = 0; tile < C3TILES; ++tile) {
+            const uint32_t d = tm + 64u * tile;
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t a_off = (uint32_t)(tile * 128 + (tap / 3) * C2P + (tap % 3)) * 16u;
-          const uint64_t a_hi = umma_desc(a_base + a_off, APL, 128u);
-          const uint64_t a_lo = umma_desc(a_base + 2u * APL + a_off, APL, 128u);
-          const uint64_t b_hl = umma_desc(b_base + (uint32_t)tap * 2048u, 1024u, 128u);            // rows 0-31 w_hi, 32-63 w_lo
-          if (tile < 3) {
-            umma_f16(d, a_hi, b_hl, IDESC64, tap > 0 ? 1u : 0u);
-            umma_f16(d, a_lo, b_hl, IDESC32, 1u);
-          } else {
-            const uint64_t b_lo = umma_desc(b_base + (uint32_t)tap * 2048u + 512u, 1024u, 128u);
-            umma_f16(d, a_hi, b_hl, IDESC32, tap > 0 ? 1u : 0u);
-            umma_f16(d, a_lo, b_hl, IDESC32, 1u);
-            umma_f16(d, a_hi, b_lo, IDESC32, 1u);
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t a_off = (uint32_t)(tile * 128 + (tap / 3) * C2P + (tap % 3)) * 16u;
+              const uint64_t a_hi = umma_desc(a_base + a_off, APL, 128u);
+              const uint64_t a_lo = umma_desc(a_base + 2u * APL + a_off, APL, 128u);
+              const uint64_t b_hl = umma_desc(b_base + (uint32_t)tap * 2048u, 1024u, 128u);        // rows 0-31 w_hi, 32-63 w_lo
+              umma_f16(d, a_hi, b_hl, IDESC64, tap > 0 ? 1u : 0u);
+              umma_f16(d, a_lo, b_hl, IDESC32, 1u);
+            }
+            umma_commit(&mma_bar[tile]);
           }
         }
-        umma_commit(&mma_bar[tile]);
+        __syncwarp();
       }
-    }
-    __syncwarp();
-  }
-  {
-    const float inv = w_s[SC + 1];
-    const int lg = warp & 3;                      // TMEM lane group this warp may read
-    for (int tile = warp >> 2; tile < C3TILES; tile += 2) {
-      if (tile == 4 && lg >= 2) break;            // flat pixels >= 576 do not exist
-      mbar_wait(&mma_bar[tile], 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (tile < 3 ? 64u * tile : 192u + 32u * (tile - 3));
+      {
+        const float inv = w_s[SC + 1];
+        const int lg = warp & 3;                      // TMEM lane group this warp may read
+        for (int tile = warp >> 2; tile < C3TILES; tile += 2) {
+          mbar_wait(&mma_bar[tile], k & 1);
+          if (tile == 4 && lg >= 2) break;            // flat pixels >= 576 do not exist
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + 64u * tile;
       unsigned long long hp2[3] = {0ull, 0ull, 0ull};
 #pragma unroll
       for (int c0 = 0; c0 < 32; c0 += 16) {
         float dh[16];
         tmem_ld16(taddr + c0, dh);
-        if (tile < 3) {
-          float dl[16];
-          tmem_ld16(taddr + 32 + c0, dl);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float dl[16];
+        tmem_ld16(taddr + 32 + c0, dl);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 16; ++j) dh[j] += dl[j];
-        } else {
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        }
+        for (int j = 0; j < 16; ++j) dh[j] += dl[j];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float4 ha = *reinterpret_cast<const float4*>(&w_s[WH + (c0 + j) * 8]);      // h0..h3
@@ -499,54 +545,62 @@ __global__ void __launch_bounds__(256, 2) pnet_kernel(const float* __restrict__ 
       const int n = tile * 128 + lg * 32 + lane;
       const int row = n / C2P, col = n - row * C2P;
       const int oy = oy0 + row, ox = ox0 + col;
-      if (row < TOY && col < TOX && oy < L.oh && ox < L.ow) {
+      if (row < TOY && col < TOX && oy < Lv.oh && ox < Lv.ow) {
         // softmax over (h0, h1), class 1 -- same form as ATen's softmax (subtract max, exp, normalise)
         const float mx = fmaxf(h[0], h[1]);
         const float e0 = expf(h[0] - mx), e1 = expf(h[1] - mx);
         const float prob = __fdiv_rn(e1, e0 + e1);
-        const size_t cell = (size_t)oy * L.ow + ox;
-        if (L.prob) {
-          const size_t plane = (size_t)L.oh * L.ow;
-          L.prob[(size_t)b * plane + cell] = prob;
-          float* rg = L.reg + (size_t)b * 4 * plane + cell;
+        const size_t cell = (size_t)oy * Lv.ow + ox;
+        if (Lv.prob) {
+          const size_t plane = (size_t)Lv.oh * Lv.ow;
+          Lv.prob[(size_t)b * plane + cell] = prob;
+          float* rg = Lv.reg + (size_t)b * 4 * plane + cell;
           rg[0] = h[2]; rg[plane] = h[3]; rg[2 * plane] = h[4]; rg[3 * plane] = h[5];
         }
-        if (L.cand && prob >= p.thr) {
+        if (Lv.cand && prob >= p.thr) {
           // generateBoundingBox: q1 = floor((2*c + 1)/scale), q2 = floor((2*c + 12)/scale)  (fp32, true division)
           const int slotbase = b * p.n_levels + lvl;
-          const int slot = atomicAdd(&L.cnt[slotbase], 1);
+          const int slot = atomicAdd(&Lv.cnt[slotbase], 1);
           if (slot < p.cap) {
             Cand cd;
-            cd.x1 = floorf(__fdiv_rn((float)(2 * ox + 1), L.scale));
-            cd.y1 = floorf(__fdiv_rn((float)(2 * oy + 1), L.scale));
-            cd.x2 = floorf(__fdiv_rn((float)(2 * ox + 12), L.scale));
-            cd.y2 = floorf(__fdiv_rn((float)(2 * oy + 12), L.scale));
+            cd.x1 = floorf(__fdiv_rn((float)(2 * ox + 1), Lv.scale));
+            cd.y1 = floorf(__fdiv_rn((float)(2 * oy + 1), Lv.scale));
+            cd.x2 = floorf(__fdiv_rn((float)(2 * ox + 12), Lv.scale));
+            cd.y2 = floorf(__fdiv_rn((float)(2 * oy + 12), Lv.scale));
             cd.score = prob;
             cd.r0 = h[2]; cd.r1 = h[3]; cd.r2 = h[4]; cd.r3 = h[5];
             cd.key = (uint32_t)cell;
-            L.cand[(size_t)slotbase * p.cap + slot] = cd;
+            Lv.cand[(size_t)slotbase * p.cap + slot] = cd;
           } else if (p.capflag) {
             p.capflag->overflow = 1; p.capflag->stage = 1; p.capflag->frame = b;
             p.capflag->count = slot + 1; p.capflag->capacity = p.cap;
           }
         }
       }
+        }
+      }
+#ifdef PNET_TIMING
+      tc3 += clock64() - tmark;
+#endif
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp_u == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
   if (range_bad && p.capflag) {
-    p.capflag->overflow = 1; p.capflag->stage = 5; p.capflag->frame = b;
+    p.capflag->overflow = 1; p.capflag->stage = 5; p.capflag->frame = 0;
     p.capflag->count = 0; p.capflag->capacity = (int)ACT_MAX;
   }
 #ifdef PNET_TIMING
-  tph[4] = clock64();
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) atomicAdd(&g_pnet_phase[i], (unsigned long long)(tph[i + 1] - tph[i]));
-    atomicAdd(&g_pnet_phase[4], 1ull);
+    atomicAdd(&g_pnet_phase[0], (unsigned long long)tw); atomicAdd(&g_pnet_phase[1], (unsigned long long)tc1);
+  }
+  if (tid == 256) {
+    atomicAdd(&g_pnet_phase[2], (unsigned long long)tw); atomicAdd(&g_pnet_phase[3], (unsigned long long)tc2);
+    atomicAdd(&g_pnet_phase[4], (unsigned long long)tc3);
+    atomicAdd(&g_pnet_phase[5], (unsigned long long)((total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x));
   }
 #endif
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp_u == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
 }
 
 }  // namespace pnet
@@ -668,6 +722,12 @@ int pnet_pack_weights(trl_ctx* c, const float* h, size_t len) {
   return TRL_OK;
 }
 
+// persistent grid: one CTA per SM (or per tile when there are fewer tiles)
+static int grid_for(int blocks, int B) {
+  const long long total = (long long)blocks * B;
+  return (int)(total < TRL_NUM_SMS ? total : TRL_NUM_SMS);
+}
+
 int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float* d_prob, float* d_reg, cudaStream_t s) {
   using namespace pnet;
   Params p{};
@@ -680,8 +740,10 @@ int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float
   L.tiles = L.tiles_x * ceil_div(L.oh, TOY);
   L.scale = 1.f; L.prob = d_prob; L.reg = d_reg; L.cand = nullptr; L.cnt = nullptr;
   p.blk_start[0] = 0; p.blk_start[1] = L.tiles;
+  p.blocks = L.tiles; p.n_frames = B;
   p.thr = 2.f; p.cap = 0; p.capflag = c->d_cap;
-  pnet_kernel<<<dim3(L.tiles, B), 256, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
+  if (B == 0) return TRL_OK;
+  pnet_kernel<<<grid_for(L.tiles, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
@@ -705,8 +767,9 @@ int launch_pnet_candidates(trl_ctx* c, const float* d_pyr, int B, const PyramidG
   }
   p.blk_start[g.n] = blocks;
   p.thr = thr; p.cap = cap; p.capflag = c->d_cap;
+  p.blocks = blocks; p.n_frames = B;
   if (blocks == 0 || B == 0) return TRL_OK;
-  pnet_kernel<<<dim3(blocks, B), 256, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
+  pnet_kernel<<<grid_for(blocks, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
