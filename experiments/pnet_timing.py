@@ -42,4 +42,4 @@ if __name__ == "__main__":
         lib.trl_debug_pnet_timing(buf)
         n = max(buf[5], 1)
         print(f"iter {it}: {buf[5]} tiles; cycles per tile: group A wait {buf[0] / n:.0f}, conv1 {buf[1] / n:.0f} | "
-              f"group B wait {buf[2] / n:.0f}, conv2 {buf[3] / n:.0f}, conv3+heads {buf[4] / n:.0f}")
+              f"group B wait {buf[2] / n:.0f}, conv2 {buf[3] / n:.0f}, conv3+heads {buf[4] / n:.0f} (of which waiting for MMA commits {buf[6] / n:.0f})")

@@ -84,6 +84,7 @@ struct trl_ctx {
   long long launches = 0;
 
   // weights (device)
+  float h_pnet_head[32 * 8 + 8 + 1 + 20] = {0};   // P-Net head / conv3 epilogue constants, copied into the kernel parameters
   float* d_pnet_packed = nullptr;   // smem image of P-Net (pnet.cu layout)
   float* d_rnet = nullptr;          // packed R-Net (mtcnn_ro.cu layout)
   float* d_onet = nullptr;

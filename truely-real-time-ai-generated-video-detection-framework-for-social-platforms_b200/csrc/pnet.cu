@@ -28,8 +28,9 @@ namespace pnet {
 
 constexpr int TOY = 16, TOX = 32;            // output cells per CTA
 constexpr int P1H = TOY + 4, P1W = TOX + 4;  // pooled conv1 tile (20 x 36), flat pixel index n = row * 36 + col
-constexpr int P1PX = 736;                    // 720 pixels + slack read by conv2's last (partial) M tile
-constexpr int P1WORDS = 5;                   // 10 channels = 5 half2 words per pixel (hi plane, lo plane)
+constexpr int P1PL = 744;                    // pixels per p1 plane: 720 + slack read by conv2's last (partial) M tile; 744 % 32 = 8
+                                             // spreads the four channel-pair planes a warp reads at once over the banks
+constexpr int P1WORDS = 5;                   // 10 channels = 5 half2 planes [pair][pixel] (hi set, lo set)
 constexpr int C2H = TOY + 2, C2P = 36;       // conv2 tile: 18 rows at the same pitch as its input (flat indexing)
 constexpr int C2PX = C2H * C2P;              // 648 pixels (columns 34, 35 of a row are never read)
 constexpr int C2TILES = (C2PX + 15) / 16;    // 41 M tiles of two 8-pixel segments
@@ -38,8 +39,17 @@ constexpr int C2TILES = (C2PX + 15) / 16;    // 41 M tiles of two 8-pixel segmen
 constexpr int C2NP = 720;                    // pixels per plane: 648 computed + slack read by the last (partial) M tile
 constexpr int C2PLANE = C2NP * 4;            // words per plane
 constexpr int C3TILES = 5;                   // conv3 M tiles of 128 flat pixels (16 rows x pitch 36 = 576 = 4.5 tiles)
-constexpr int TMEM_COLS = 512;               // 5 accumulators of 64 columns (one CTA per SM owns the whole TMEM)
-constexpr int NTHREADS = 512;                // warps 0-7: staging + conv1, warps 8-15: conv2 + conv3 + heads
+constexpr int TMEM_COLS = 512;
+// DEFER_EPILOGUE = true: two accumulator sets of 256 columns (tiles 0-2 x 64, tiles 3-4 x 32 with a third MMA per tap) and
+// the head epilogue of tile k-1 runs under the MMAs of tile k.  Measured slower on B200 (15.1 vs 12.0 ms per 450 frames):
+// the MMAs are limited by shared-memory operand bandwidth, which the epilogue does not relieve, and the third MMA adds
+// 12 % tensor work.  false: one set of five 64-column accumulators, epilogue per tile as its commit arrives.
+constexpr bool DEFER_EPILOGUE = false;
+__host__ __device__ constexpr bool tile_n64(int tile) { return DEFER_EPILOGUE ? tile < 3 : true; }
+__host__ __device__ constexpr uint32_t tile_col(int set, int tile) {
+  return DEFER_EPILOGUE ? 256u * (uint32_t)(set & 1) + (tile < 3 ? 64u * tile : 192u + 32u * (tile - 3)) : 64u * tile;
+}
+constexpr int NTHREADS = 544;                // warps 0-7: staging + conv1, warps 8-15: conv2 + heads, warp 16: conv3 MMA issue
 constexpr int INH = 2 * TOY + 10, INW = 2 * TOX + 10;   // 42 x 74 input tile
 constexpr int INP = 76;
 
@@ -51,19 +61,17 @@ constexpr int W1 = 0;                 // fp32 [27][12]
 constexpr int B1 = W1 + 27 * 12;      // [12]
 constexpr int A1 = B1 + 12;           // [12]
 constexpr int W2 = A1 + 12;           // half2 B fragments: [6 k-steps][hi, lo][32 lanes][n0 b0, n0 b1, n1 b0, n1 b1]
-constexpr int T2 = W2 + 6 * 2 * 32 * 4;   // int[48]: p1 word offset of channel pair P (see conv2_pair())
+constexpr int T2 = W2 + 6 * 2 * 32 * 4;   // int[48]: p1 word offset (plane + tap shift) of channel pair P (see conv2_pair())
 constexpr int B2 = T2 + 48;           // [16]
 constexpr int A2 = B2 + 16;           // [16]
 constexpr int W3 = A2 + 16;           // UMMA B operand: [9 taps][k-half][64 rows: w_hi[32], w_lo[32]][8 channels as fp16]
-constexpr int WH = W3 + 9 * 2 * 64 * 4;   // fp32 [32][8]: conv4_1 (2), conv4_2 (4), conv3 bias, conv3 PReLU slope
-constexpr int BH = WH + 32 * 8;       // [8]
-constexpr int SC = BH + 8;            // [4]: 1 / (SA * S_w2), 1 / (SA * S_w3)
+constexpr int SC = W3 + 9 * 2 * 64 * 4;   // [4]: 1 / (SA * S_w2)
 constexpr int WTOTAL = SC + 4;
-static_assert(WTOTAL % 4 == 0 && W2 % 4 == 0 && W3 % 4 == 0 && WH % 4 == 0, "16-byte alignment of the operand arrays");
+static_assert(WTOTAL % 4 == 0 && W2 % 4 == 0 && W3 % 4 == 0, "16-byte alignment of the operand arrays");
 
 constexpr int SM_IN = 3 * INH * INP;                 // 9576 words
 constexpr int SM_C2 = 4 * C2PLANE;                   // 11520 words
-constexpr int SM_P1 = 2 * P1PX * P1WORDS;            // 7360 words
+constexpr int SM_P1 = 2 * P1WORDS * P1PL;            // 7440 words
 constexpr int SMEM_WORDS = WTOTAL + 2 * SM_IN + 2 * SM_P1 + SM_C2;    // weights, 2 input tiles, 2 pooled conv1 tiles, conv2 planes
 constexpr int SMEM_BYTES = SMEM_WORDS * 4;           // ~206 KB -> one persistent CTA per SM
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -88,6 +96,11 @@ struct Params {
   float thr;
   int cap;
   CapFlag* capflag;
+  float head[32][8];   // per conv3 channel: conv4_1 (2), conv4_2 (4), conv3 bias, conv3 PReLU slope -- read as constant-bank FFMA operands
+  float head_bias[8];
+  float inv3;          // 1 / (SA * S_w3)
+  float conv1_bias[10], conv1_slope[10];
+  int conv1_monotone;  // 1: every conv1 PReLU slope is >= 0 (max-pool may run before bias + PReLU, exactly)
 };
 
 #ifdef PNET_TIMING
@@ -185,12 +198,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // issue slots are busy at the same time.  Weights are loaded once per CTA.
 __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restrict__ wpacked, const __grid_constant__ Params p) {
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t mma_bar[C3TILES];   // tcgen05.commit of conv3 M tile i (one phase per tile of the list)
+  __shared__ __align__(8) uint64_t mma_bar[2 * C3TILES];   // [accumulator set][conv3 M tile]: tcgen05.commit arrives
   __shared__ __align__(8) uint64_t p1_full[2], p1_empty[2];
+  __shared__ __align__(8) uint64_t c2_full;            // conv2 output of the current tile is complete (256 arrivals)
   __shared__ uint32_t tmem_slot;
   float* w_s = smem;
   float* in_base = smem + WTOTAL;                                             // [2][SM_IN] fp32 input tiles
-  uint32_t* p1_base = reinterpret_cast<uint32_t*>(in_base + 2 * SM_IN);       // [2][hi, lo][P1PX][5]
+  uint32_t* p1_base = reinterpret_cast<uint32_t*>(in_base + 2 * SM_IN);       // [2][hi, lo][5 pairs][P1PL]
   uint32_t* c2_s = p1_base + 2 * SM_P1;                                       // [hi k0, hi k1, lo k0, lo k1][C2NP][4]
   const uint32_t* wu = reinterpret_cast<const uint32_t*>(w_s);
   const int tid = threadIdx.x;
@@ -199,7 +213,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);    // warp-uniform copy (keeps the MMA issue path in uniform registers)
   bool range_bad = false;
 #ifdef PNET_TIMING
-  long long tw = 0, tc1 = 0, tc2 = 0, tc3 = 0, tmark;
+  long long tw = 0, tc1 = 0, tc2 = 0, tc3 = 0, tmma = 0, tmark;
 #endif
 
   if (warp_u == 0) {
@@ -207,13 +221,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < C3TILES; ++i)
+      for (int i = 0; i < 2 * C3TILES; ++i)
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mma_bar[i])), "r"(1u) : "memory");
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&p1_full[i])), "r"(256u) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&p1_empty[i])), "r"(256u) : "memory");
       }
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&c2_full)), "r"(256u) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -223,10 +238,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
     for (int i = tid; i < WTOTAL / 4; i += NTHREADS)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(w_dst + 16u * i), "l"(wpacked + 4 * i) : "memory");
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-    for (int i = tid; i < 2 * 2 * (P1PX - P1H * P1W) * P1WORDS; i += NTHREADS) {
-      const int per = (P1PX - P1H * P1W) * P1WORDS;
-      const int plane = i / per, off = i - plane * per;                       // plane = buf * 2 + (hi | lo)
-      p1_base[plane * (P1PX * P1WORDS) + P1H * P1W * P1WORDS + off] = 0u;
+    for (int i = tid; i < 2 * 2 * P1WORDS * (P1PL - P1H * P1W); i += NTHREADS) {
+      const int per = P1PL - P1H * P1W;
+      const int plane = i / per, off = i - plane * per;                       // plane = (buf * 2 + (hi | lo)) * 5 + pair
+      p1_base[plane * P1PL + P1H * P1W + off] = 0u;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -339,25 +354,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
 #pragma unroll
         for (int cp = 0; cp < 5; ++cp) unpack_f32x2(acc[q][cp], accf[q][2 * cp], accf[q][2 * cp + 1]);
       float m[10];
+      if (p.conv1_monotone && gy + 1 < c1h && gx + 1 < c1w) {
+        // interior pixel and every PReLU slope >= 0: bias add and PReLU are non-decreasing (rounding included), so
+        // they commute exactly with the 2x2 max -- one bias / PReLU per channel instead of four
 #pragma unroll
-      for (int co = 0; co < 10; ++co) {
-        const float bias = w_s[B1 + co], al = w_s[A1 + co];
-        float mm = -INFINITY;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const bool ok = (gy + (q >> 1) < c1h) && (gx + (q & 1) < c1w);
-          const float v = prelu(accf[q][co] + bias, al);
-          mm = ok ? fmaxf(mm, v) : mm;
+        for (int co = 0; co < 10; ++co) {
+          const float mx = fmaxf(fmaxf(accf[0][co], accf[1][co]), fmaxf(accf[2][co], accf[3][co]));
+          m[co] = prelu(mx + p.conv1_bias[co], p.conv1_slope[co]);
+          range_bad |= fabsf(m[co]) > ACT_MAX;
         }
-        m[co] = (mm == -INFINITY) ? 0.f : mm;
-        range_bad |= fabsf(m[co]) > ACT_MAX;
+      } else {
+#pragma unroll
+        for (int co = 0; co < 10; ++co) {
+          const float bias = p.conv1_bias[co], al = p.conv1_slope[co];
+          float mm = -INFINITY;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const bool ok = (gy + (q >> 1) < c1h) && (gx + (q & 1) < c1w);
+            const float v = prelu(accf[q][co] + bias, al);
+            mm = ok ? fmaxf(mm, v) : mm;
+          }
+          m[co] = (mm == -INFINITY) ? 0.f : mm;
+          range_bad |= fabsf(m[co]) > ACT_MAX;
+        }
       }
 #pragma unroll
       for (int cp = 0; cp < 5; ++cp) {
         uint32_t hi, lo;
         split_h2(m[2 * cp] * SA, m[2 * cp + 1] * SA, hi, lo);
-        p1_s[item * P1WORDS + cp] = hi;
-        p1_s[P1PX * P1WORDS + item * P1WORDS + cp] = lo;
+        p1_s[cp * P1PL + item] = hi;
+        p1_s[(P1WORDS + cp) * P1PL + item] = lo;
       }
     }
       mbar_arrive(&p1_full[k & 1]);
@@ -365,22 +391,140 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
       tc1 += clock64() - tmark;
 #endif
     }
+  } else if (warp_u == 16) {
+    // =================================================================== conv3 MMA issue (one elected thread)
+    // kept off the compute warps: the issuing thread is held back by the MMA queue for as long as the MMAs run
+    int k = 0;
+    for (int id = blockIdx.x; id < total; id += gridDim.x, ++k) {
+      mbar_wait(&c2_full, k & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      {
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint32_t a_base = __shfl_sync(0xffffffffu, smem_u32(c2_s), 0);
+        const uint32_t b_base = __shfl_sync(0xffffffffu, smem_u32(w_s + W3), 0);
+        const uint32_t bar_base = __shfl_sync(0xffffffffu, smem_u32(&mma_bar[(k & 1) * C3TILES]), 0);
+        constexpr uint32_t IDESC32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);   // f32 accumulate, f16 x f16, K-major
+        constexpr uint32_t IDESC64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+        constexpr uint32_t APL = C2PLANE * 4;                                                // plane stride in bytes
+        if (elect_one()) {
+#pragma unroll
+          for (int tile = 0; tile < C3TILES; ++tile) {
+            const uint32_t d = tm + tile_col(k, tile);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t a_off = (uint32_t)(tile * 128 + (tap / 3) * C2P + (tap % 3)) * 16u;
+              const uint64_t a_hi = umma_desc(a_base + a_off, APL, 128u);
+              const uint64_t a_lo = umma_desc(a_base + 2u * APL + a_off, APL, 128u);
+              const uint64_t b_hl = umma_desc(b_base + (uint32_t)tap * 2048u, 1024u, 128u);        // rows 0-31 w_hi, 32-63 w_lo
+              if (tile_n64(tile)) {
+                umma_f16(d, a_hi, b_hl, IDESC64, tap > 0 ? 1u : 0u);
+                umma_f16(d, a_lo, b_hl, IDESC32, 1u);
+              } else {
+                const uint64_t b_lo = umma_desc(b_base + (uint32_t)tap * 2048u + 512u, 1024u, 128u);
+                umma_f16(d, a_hi, b_hl, IDESC32, tap > 0 ? 1u : 0u);
+                umma_f16(d, a_lo, b_hl, IDESC32, 1u);
+                umma_f16(d, a_hi, b_lo, IDESC32, 1u);
+              }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_base + 8u * tile) : "memory");
+          }
+        }
+        __syncwarp();
+      }
+    }
   } else {
-    // =================================================================== group B: conv2, conv3, heads
+    // =================================================================== group B: conv2, heads
     const int warp = warp_u - 8;
+    // head epilogue of the tile whose conv3 went into accumulator set kk & 1 (thread = pixel: 32 channels -> bias,
+    // PReLU, heads, softmax, candidate append; no cross-lane traffic)
+    auto conv3_epilogue = [&](const TileRef& tr, int kk) {
+      const Level& Lv = p.lv[tr.lvl];
+      const int b = tr.b, lvl = tr.lvl, oy0 = tr.oy0, ox0 = tr.ox0;
+      const int lg = warp & 3;                        // TMEM lane group this warp may read
+      for (int tile = warp >> 2; tile < C3TILES; tile += 2) {
+#ifdef PNET_TIMING
+        const long long tq = clock64();
+#endif
+        mbar_wait(&mma_bar[(kk & 1) * C3TILES + tile], (kk >> 1) & 1);
+#ifdef PNET_TIMING
+        tmma += clock64() - tq;
+#endif
+        if (tile == 4 && lg >= 2) break;              // flat pixels >= 576 do not exist
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + tile_col(kk, tile);
+      float h[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        float dh[16];
+        tmem_ld16(taddr + c0, dh);
+        if (tile_n64(tile)) {                           // N = 64 tiles: add the a_hi x w_lo column block
+          float dl[16];
+          tmem_ld16(taddr + 32 + c0, dl);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dh[j] += dl[j];
+        } else {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float* hw = p.head[c0 + j];                                  // compile-time index: c[0x0][..] operands, no LDS
+          const float v = prelu(fmaf(dh[j], p.inv3, hw[6]), hw[7]);
+#pragma unroll
+          for (int q = 0; q < 6; ++q) h[q] = fmaf(v, hw[q], h[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) h[q] += p.head_bias[q];
+      const int n = tile * 128 + lg * 32 + lane;
+      const int row = n / C2P, col = n - row * C2P;
+      const int oy = oy0 + row, ox = ox0 + col;
+      if (row < TOY && col < TOX && oy < Lv.oh && ox < Lv.ow) {
+        // softmax over (h0, h1), class 1 -- same form as ATen's softmax (subtract max, exp, normalise)
+        const float mx = fmaxf(h[0], h[1]);
+        const float e0 = expf(h[0] - mx), e1 = expf(h[1] - mx);
+        const float prob = __fdiv_rn(e1, e0 + e1);
+        const size_t cell = (size_t)oy * Lv.ow + ox;
+        if (Lv.prob) {
+          const size_t plane = (size_t)Lv.oh * Lv.ow;
+          Lv.prob[(size_t)b * plane + cell] = prob;
+          float* rg = Lv.reg + (size_t)b * 4 * plane + cell;
+          rg[0] = h[2]; rg[plane] = h[3]; rg[2 * plane] = h[4]; rg[3 * plane] = h[5];
+        }
+        if (Lv.cand && prob >= p.thr) {
+          // generateBoundingBox: q1 = floor((2*c + 1)/scale), q2 = floor((2*c + 12)/scale)  (fp32, true division)
+          const int slotbase = b * p.n_levels + lvl;
+          const int slot = atomicAdd(&Lv.cnt[slotbase], 1);
+          if (slot < p.cap) {
+            Cand cd;
+            cd.x1 = floorf(__fdiv_rn((float)(2 * ox + 1), Lv.scale));
+            cd.y1 = floorf(__fdiv_rn((float)(2 * oy + 1), Lv.scale));
+            cd.x2 = floorf(__fdiv_rn((float)(2 * ox + 12), Lv.scale));
+            cd.y2 = floorf(__fdiv_rn((float)(2 * oy + 12), Lv.scale));
+            cd.score = prob;
+            cd.r0 = h[2]; cd.r1 = h[3]; cd.r2 = h[4]; cd.r3 = h[5];
+            cd.key = (uint32_t)cell;
+            Lv.cand[(size_t)slotbase * p.cap + slot] = cd;
+          } else if (p.capflag) {
+            p.capflag->overflow = 1; p.capflag->stage = 1; p.capflag->frame = b;
+            p.capflag->count = slot + 1; p.capflag->capacity = p.cap;
+          }
+        }
+      }
+      }
+    };
+    TileRef prev{};
     int k = 0;
     for (int id = blockIdx.x; id < total; id += gridDim.x, ++k) {
 #ifdef PNET_TIMING
       tmark = clock64();
 #endif
       mbar_wait(&p1_full[k & 1], (k >> 1) & 1);
-      if (k >= 1) mbar_wait(&mma_bar[C3TILES - 1], (k - 1) & 1);      // conv3 of tile k-1 has consumed c2
+      if (k >= 1) mbar_wait(&mma_bar[((k - 1) & 1) * C3TILES + C3TILES - 1], ((k - 1) >> 1) & 1);      // conv3 of tile k-1 has consumed c2
 #ifdef PNET_TIMING
       tw += clock64() - tmark; tmark = clock64();
 #endif
       const TileRef tr = decode_tile(p, id);
-      const Level& Lv = p.lv[tr.lvl];
-      const int b = tr.b, lvl = tr.lvl, oy0 = tr.oy0, ox0 = tr.ox0;
       const uint32_t* p1_s = p1_base + (k & 1) * SM_P1;
       // ---- conv2 (10->16, 3x3) + PReLU on the tensor pipe (mma.sync).
       // Flat implicit GEMM: output pixel n = row * 36 + col reads input pixels n + ky * 36 + kx, so an M tile is any
@@ -392,15 +536,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
       {
         const int* tab = reinterpret_cast<const int*>(w_s + T2);
     const uint32_t* p1h = p1_s;
-    const uint32_t* p1l = p1_s + P1PX * P1WORDS;
+    const uint32_t* p1l = p1_s + P1WORDS * P1PL;
     const float inv = w_s[SC + 0];
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       // tiles warp + 8 i, i = 3 pass .. 3 pass + 2 (tile 40 exists for warp 0 only)
       const int mt0 = warp + 24 * pass;
+      const int nq = min(3, (C2TILES - mt0 + 7) / 8);      // live M tiles of this warp in this pass (warp uniform)
       int base[3];
 #pragma unroll
-      for (int q = 0; q < 3; ++q) base[q] = min(mt0 + 8 * q, C2TILES - 1) * 16 * P1WORDS + g * P1WORDS;
+      for (int q = 0; q < 3; ++q) base[q] = min(mt0 + 8 * q, C2TILES - 1) * 16 + g;
       float acc[3][2][4];
 #pragma unroll
       for (int q = 0; q < 3; ++q)
@@ -416,26 +561,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
         uint32_t ah[3][4], al[3][4];
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          ah[q][0] = p1h[base[q] + o0];                  al[q][0] = p1l[base[q] + o0];
-          ah[q][1] = p1h[base[q] + 8 * P1WORDS + o0];    al[q][1] = p1l[base[q] + 8 * P1WORDS + o0];
-          ah[q][2] = p1h[base[q] + o1];                  al[q][2] = p1l[base[q] + o1];
-          ah[q][3] = p1h[base[q] + 8 * P1WORDS + o1];    al[q][3] = p1l[base[q] + 8 * P1WORDS + o1];
+          ah[q][0] = p1h[base[q] + o0];        al[q][0] = p1l[base[q] + o0];
+          ah[q][1] = p1h[base[q] + 8 + o0];    al[q][1] = p1l[base[q] + 8 + o0];
+          ah[q][2] = p1h[base[q] + o1];        al[q][2] = p1l[base[q] + o1];
+          ah[q][3] = p1h[base[q] + 8 + o1];    al[q][3] = p1l[base[q] + 8 + o1];
         }
         // the three terms of one accumulator are dependent: issue the 6 independent accumulators between them
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          mma_f16(acc[q][0], al[q][0], al[q][1], al[q][2], al[q][3], bh.x, bh.y);
-          mma_f16(acc[q][1], al[q][0], al[q][1], al[q][2], al[q][3], bh.z, bh.w);
+          if (q < nq) {
+            mma_f16(acc[q][0], al[q][0], al[q][1], al[q][2], al[q][3], bh.x, bh.y);
+            mma_f16(acc[q][1], al[q][0], al[q][1], al[q][2], al[q][3], bh.z, bh.w);
+          }
         }
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          mma_f16(acc[q][0], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bl.x, bl.y);
-          mma_f16(acc[q][1], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bl.z, bl.w);
+          if (q < nq) {
+            mma_f16(acc[q][0], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bl.x, bl.y);
+            mma_f16(acc[q][1], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bl.z, bl.w);
+          }
         }
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          mma_f16(acc[q][0], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bh.x, bh.y);
-          mma_f16(acc[q][1], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bh.z, bh.w);
+          if (q < nq) {
+            mma_f16(acc[q][0], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bh.x, bh.y);
+            mma_f16(acc[q][1], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bh.z, bh.w);
+          }
         }
       }
       // epilogue: unscale, bias, PReLU, split; lane holds channels (2t, 2t+1) + 8 j of pixels g and g + 8.
@@ -475,114 +626,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
       // Flat indexing again: output pixel n = row * 36 + col reads conv2 pixels n + ky * 36 + kx, so the A operand
       // of filter tap (ky, kx) is the same shared-memory image with its start address moved by (ky * 36 + kx) * 16
       // bytes -- no im2col copy.  One M tile = 128 flat pixels (5 tiles cover 16 rows x pitch 36), one MMA = one tap
-      // x 16 channels (K = 16).  The 3-term split a_hi w_hi + a_hi w_lo + a_lo w_hi costs two MMAs per tap:
-      // B = [w_hi | w_lo] as N = 64, then a_lo x w_hi as N = 32 into the first 32 columns; the epilogue adds the two
-      // column blocks.  One elected thread issues everything; each tile's commit releases its epilogue (thread =
-      // pixel: 32 channels -> bias, PReLU, heads, softmax, candidate append; no cross-lane traffic).
+      // x 16 channels (K = 16).  The 3-term split a_hi w_hi + a_hi w_lo + a_lo w_hi costs two MMAs per tap on tiles
+      // 0-2 (B = [w_hi | w_lo] as N = 64, then a_lo x w_hi as N = 32 into the first 32 columns; the epilogue adds the
+      // two column blocks) and three N = 32 MMAs per tap on tiles 3-4, so one tile set needs 256 TMEM columns and the
+      // accumulators are double buffered: the MMAs of tile k run while the epilogue of tile k-1 is computed.
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // c2 planes -> visible to the UMMA proxy
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("bar.sync 2, 256;" ::: "memory");                    // also: every epilogue of tile k-1 has read its D
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (warp == 0) {
-        const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
-        const uint32_t a_base = __shfl_sync(0xffffffffu, smem_u32(c2_s), 0);
-        const uint32_t b_base = __shfl_sync(0xffffffffu, smem_u32(w_s + W3), 0);
-        constexpr uint32_t IDESC32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);   // f32 accumulate, f16 x f16, K-major
-        constexpr uint32_t IDESC64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-        constexpr uint32_t APL = C2PLANE * 4;                                                // plane stride in bytes
-        if (elect_one()) {
-#pragma unroll
-          for (int tile = 0; tile < C3TILES; ++tile) {
-            const uint32_t d = tm + 64u * tile;
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t a_off = (uint32_t)(tile * 128 + (tap / 3) * C2P + (tap % 3)) * 16u;
-              const uint64_t a_hi = umma_desc(a_base + a_off, APL, 128u);
-              const uint64_t a_lo = umma_desc(a_base + 2u * APL + a_off, APL, 128u);
-              const uint64_t b_hl = umma_desc(b_base + (uint32_t)tap * 2048u, 1024u, 128u);        // rows 0-31 w_hi, 32-63 w_lo
-              umma_f16(d, a_hi, b_hl, IDESC64, tap > 0 ? 1u : 0u);
-              umma_f16(d, a_lo, b_hl, IDESC32, 1u);
-            }
-            umma_commit(&mma_bar[tile]);
-          }
-        }
-        __syncwarp();
-      }
-      {
-        const float inv = w_s[SC + 1];
-        const int lg = warp & 3;                      // TMEM lane group this warp may read
-        for (int tile = warp >> 2; tile < C3TILES; tile += 2) {
-          mbar_wait(&mma_bar[tile], k & 1);
-          if (tile == 4 && lg >= 2) break;            // flat pixels >= 576 do not exist
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + 64u * tile;
-      unsigned long long hp2[3] = {0ull, 0ull, 0ull};
-#pragma unroll
-      for (int c0 = 0; c0 < 32; c0 += 16) {
-        float dh[16];
-        tmem_ld16(taddr + c0, dh);
-        float dl[16];
-        tmem_ld16(taddr + 32 + c0, dl);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 16; ++j) dh[j] += dl[j];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 ha = *reinterpret_cast<const float4*>(&w_s[WH + (c0 + j) * 8]);      // h0..h3
-          const float4 hb = *reinterpret_cast<const float4*>(&w_s[WH + (c0 + j) * 8 + 4]);  // h4, h5, bias, slope
-          const float v = prelu(fmaf(dh[j], inv, hb.z), hb.w);
-          const unsigned long long vv = pack_f32x2(v, v);
-          ffma2(hp2[0], vv, pack_f32x2(ha.x, ha.y));
-          ffma2(hp2[1], vv, pack_f32x2(ha.z, ha.w));
-          ffma2(hp2[2], vv, pack_f32x2(hb.x, hb.y));
-        }
-      }
-      float h[6];
-#pragma unroll
-      for (int q = 0; q < 3; ++q) unpack_f32x2(hp2[q], h[2 * q], h[2 * q + 1]);
-#pragma unroll
-      for (int q = 0; q < 6; ++q) h[q] += w_s[BH + q];
-      const int n = tile * 128 + lg * 32 + lane;
-      const int row = n / C2P, col = n - row * C2P;
-      const int oy = oy0 + row, ox = ox0 + col;
-      if (row < TOY && col < TOX && oy < Lv.oh && ox < Lv.ow) {
-        // softmax over (h0, h1), class 1 -- same form as ATen's softmax (subtract max, exp, normalise)
-        const float mx = fmaxf(h[0], h[1]);
-        const float e0 = expf(h[0] - mx), e1 = expf(h[1] - mx);
-        const float prob = __fdiv_rn(e1, e0 + e1);
-        const size_t cell = (size_t)oy * Lv.ow + ox;
-        if (Lv.prob) {
-          const size_t plane = (size_t)Lv.oh * Lv.ow;
-          Lv.prob[(size_t)b * plane + cell] = prob;
-          float* rg = Lv.reg + (size_t)b * 4 * plane + cell;
-          rg[0] = h[2]; rg[plane] = h[3]; rg[2 * plane] = h[4]; rg[3 * plane] = h[5];
-        }
-        if (Lv.cand && prob >= p.thr) {
-          // generateBoundingBox: q1 = floor((2*c + 1)/scale), q2 = floor((2*c + 12)/scale)  (fp32, true division)
-          const int slotbase = b * p.n_levels + lvl;
-          const int slot = atomicAdd(&Lv.cnt[slotbase], 1);
-          if (slot < p.cap) {
-            Cand cd;
-            cd.x1 = floorf(__fdiv_rn((float)(2 * ox + 1), Lv.scale));
-            cd.y1 = floorf(__fdiv_rn((float)(2 * oy + 1), Lv.scale));
-            cd.x2 = floorf(__fdiv_rn((float)(2 * ox + 12), Lv.scale));
-            cd.y2 = floorf(__fdiv_rn((float)(2 * oy + 12), Lv.scale));
-            cd.score = prob;
-            cd.r0 = h[2]; cd.r1 = h[3]; cd.r2 = h[4]; cd.r3 = h[5];
-            cd.key = (uint32_t)cell;
-            Lv.cand[(size_t)slotbase * p.cap + slot] = cd;
-          } else if (p.capflag) {
-            p.capflag->overflow = 1; p.capflag->stage = 1; p.capflag->frame = b;
-            p.capflag->count = slot + 1; p.capflag->capacity = p.cap;
-          }
-        }
-      }
-        }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // this thread's earlier epilogue reads of D are done
+      mbar_arrive(&c2_full);                                            // -> warp 16 issues the conv3 MMAs of this tile
+      if (DEFER_EPILOGUE) {
+        if (k >= 1) conv3_epilogue(prev, k - 1);
+        prev = tr;
+      } else {
+        conv3_epilogue(tr, k);
       }
 #ifdef PNET_TIMING
       tc3 += clock64() - tmark;
 #endif
     }
+    if (DEFER_EPILOGUE && k >= 1) conv3_epilogue(prev, k - 1);
   }
   if (range_bad && p.capflag) {
     p.capflag->overflow = 1; p.capflag->stage = 5; p.capflag->frame = 0;
@@ -595,6 +656,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
   if (tid == 256) {
     atomicAdd(&g_pnet_phase[2], (unsigned long long)tw); atomicAdd(&g_pnet_phase[3], (unsigned long long)tc2);
     atomicAdd(&g_pnet_phase[4], (unsigned long long)tc3);
+    atomicAdd(&g_pnet_phase[6], (unsigned long long)tmma);
     atomicAdd(&g_pnet_phase[5], (unsigned long long)((total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x));
   }
 #endif
@@ -688,7 +750,7 @@ int pnet_pack_weights(trl_ctx* c, const float* h, size_t len) {
           pu[W2 + ((2 * s + 1) * 32 + lane) * 4 + 2 * j + i] = lo;
         }
         if (g == 0) {
-          const int off = (ky * P1W + kx) * P1WORDS + cp;
+          const int off = cp * P1PL + ky * P1W + kx;
           memcpy(&pk[T2 + 8 * s + 4 * i + t], &off, sizeof(int));
         }
       }
@@ -705,21 +767,35 @@ int pnet_pack_weights(trl_ctx* c, const float* h, size_t len) {
           pu[W3 + ((tap * 2 + kh) * 64 + co) * 4 + cp] = hi;
           pu[W3 + ((tap * 2 + kh) * 64 + 32 + co) * 4 + cp] = lo;
         }
+  // conv3 epilogue + head constants travel in the kernel parameters (constant bank operands)
   for (int ci = 0; ci < 32; ++ci) {
-    pk[WH + ci * 8 + 0] = w41[0 * 32 + ci];
-    pk[WH + ci * 8 + 1] = w41[1 * 32 + ci];
-    for (int j = 0; j < 4; ++j) pk[WH + ci * 8 + 2 + j] = w42[j * 32 + ci];
-    pk[WH + ci * 8 + 6] = b3[ci];
-    pk[WH + ci * 8 + 7] = a3[ci];
+    float* hw = c->h_pnet_head + ci * 8;
+    hw[0] = w41[0 * 32 + ci];
+    hw[1] = w41[1 * 32 + ci];
+    for (int j = 0; j < 4; ++j) hw[2 + j] = w42[j * 32 + ci];
+    hw[6] = b3[ci];
+    hw[7] = a3[ci];
   }
-  pk[BH + 0] = b41[0]; pk[BH + 1] = b41[1];
-  for (int j = 0; j < 4; ++j) pk[BH + 2 + j] = b42[j];
+  c->h_pnet_head[256] = b41[0]; c->h_pnet_head[257] = b41[1];
+  for (int j = 0; j < 4; ++j) c->h_pnet_head[258 + j] = b42[j];
+  c->h_pnet_head[264] = 1.f / (SA * s3);
+  for (int co = 0; co < 10; ++co) { c->h_pnet_head[265 + co] = b1[co]; c->h_pnet_head[275 + co] = a1[co]; }
   pk[SC + 0] = 1.f / (SA * s2);
-  pk[SC + 1] = 1.f / (SA * s3);
   TRL_CUDA(c, cudaMalloc(&c->d_pnet_packed, WTOTAL * sizeof(float)));
   TRL_CUDA(c, cudaMemcpy(c->d_pnet_packed, pk.data(), WTOTAL * sizeof(float), cudaMemcpyHostToDevice));
   TRL_CUDA(c, cudaFuncSetAttribute(pnet::pnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   return TRL_OK;
+}
+
+static void fill_head(const trl_ctx* c, pnet::Params* p) {
+  memcpy(p->head, c->h_pnet_head, sizeof(p->head));
+  memset(p->head_bias, 0, sizeof(p->head_bias));
+  memcpy(p->head_bias, c->h_pnet_head + 256, 6 * sizeof(float));
+  p->inv3 = c->h_pnet_head[264];
+  memcpy(p->conv1_bias, c->h_pnet_head + 265, 10 * sizeof(float));
+  memcpy(p->conv1_slope, c->h_pnet_head + 275, 10 * sizeof(float));
+  p->conv1_monotone = 1;
+  for (int co = 0; co < 10; ++co) if (!(p->conv1_slope[co] >= 0.f)) p->conv1_monotone = 0;
 }
 
 // persistent grid: one CTA per SM (or per tile when there are fewer tiles)
@@ -741,6 +817,7 @@ int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float
   L.scale = 1.f; L.prob = d_prob; L.reg = d_reg; L.cand = nullptr; L.cnt = nullptr;
   p.blk_start[0] = 0; p.blk_start[1] = L.tiles;
   p.blocks = L.tiles; p.n_frames = B;
+  fill_head(c, &p);
   p.thr = 2.f; p.cap = 0; p.capflag = c->d_cap;
   if (B == 0) return TRL_OK;
   pnet_kernel<<<grid_for(L.tiles, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
@@ -768,6 +845,7 @@ int launch_pnet_candidates(trl_ctx* c, const float* d_pyr, int B, const PyramidG
   p.blk_start[g.n] = blocks;
   p.thr = thr; p.cap = cap; p.capflag = c->d_cap;
   p.blocks = blocks; p.n_frames = B;
+  fill_head(c, &p);
   if (blocks == 0 || B == 0) return TRL_OK;
   pnet_kernel<<<grid_for(blocks, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
   TRL_LAUNCH_CHECK(c);
