@@ -55,6 +55,61 @@ struct PyrParams {
   int tab_off[TRL_MAX_SCALES];         // offset of level k's window tables
 };
 
+
+#ifdef __CUDACC__
+// sm_100 packed fp32: two independent IEEE fmas per instruction (SASS FFMA2; a (v, v) pair becomes a scalar broadcast operand)
+__device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+#endif
+
+// ----------------------------------------------------------------------------- compact work lists
+// The cascade keeps per-frame candidate lists at fixed strides (slot = frame * cap + i, count[frame] live entries).
+// Kernels that do one CTA of work per live slot run as grid-stride loops over the *compacted* index space instead of
+// launching one (mostly empty) CTA per slot: every CTA scans the per-frame counts once (B <= SLOTMAP_MAX_FRAMES ints)
+// and maps work item j to its slot by binary search.
+#define SLOTMAP_MAX_FRAMES 1024
+#ifdef __CUDACC__
+// all threads of the CTA call this; s_pref holds n_frames + 1 ints.  Returns the number of live slots.
+__device__ __forceinline__ int slotmap_init(const int* __restrict__ d_count, int n_frames, int cap, int* s_pref) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int carry = 0;
+    if (lane == 0) s_pref[0] = 0;
+    for (int base = 0; base < n_frames; base += 32) {
+      const int i = base + lane;
+      int v = i < n_frames ? min(max(d_count[i], 0), cap) : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+      }
+      if (i < n_frames) s_pref[i + 1] = carry + v;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+  __syncthreads();
+  return s_pref[n_frames];
+}
+// work item j (0 <= j < total) -> slot = frame * cap + index
+__device__ __forceinline__ int slotmap_slot(const int* s_pref, int n_frames, int cap, int j) {
+  int lo = 0, hi = n_frames;           // invariant: s_pref[lo] <= j < s_pref[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (s_pref[mid] <= j) lo = mid; else hi = mid;
+  }
+  return lo * cap + (j - s_pref[lo]);
+}
+#endif
+
 namespace nms {
 // parameters of one cascade NMS stage (nms.cu)
 struct StageParams {

@@ -5,6 +5,8 @@
 // upstream: models/mtcnn.py RNet.forward / ONet.forward.  ceil_mode pooling clips the
 // window at the border; the flatten before the first dense layer is (W, H, C) ordered upstream -- the host
 // permutes the dense weight rows once so the kernel reads its [C][H][W] activations directly.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ro {
@@ -28,11 +30,10 @@ __device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* _
     const int rem = item - cg * (rows * PXG);
     const int row = rem / PXG, pg = rem - row * PXG;
     const int x0 = pg * 4;
-    float acc[4][4];
+    // packed fp32 pairs (FFMA2, common.cuh): two output channels per issued instruction, IEEE fma per element
+    unsigned long long acc2[4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int i = 0; i < 4; ++i) acc2[i][0] = acc2[i][1] = 0ull;
     for (int ci = 0; ci < CIN; ++ci) {
 #pragma unroll
       for (int ky = 0; ky < K; ++ky) {
@@ -43,15 +44,21 @@ __device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* _
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
           const float4 wv = __ldg(reinterpret_cast<const float4*>(w + ((ci * K + ky) * K + kx) * COUT + cg * 4));
+          const unsigned long long w01 = pack_f32x2(wv.x, wv.y), w23 = pack_f32x2(wv.z, wv.w);
 #pragma unroll
           for (int px = 0; px < 4; ++px) {
-            acc[px][0] = fmaf(v[px + kx], wv.x, acc[px][0]);
-            acc[px][1] = fmaf(v[px + kx], wv.y, acc[px][1]);
-            acc[px][2] = fmaf(v[px + kx], wv.z, acc[px][2]);
-            acc[px][3] = fmaf(v[px + kx], wv.w, acc[px][3]);
+            const unsigned long long vv = pack_f32x2(v[px + kx], v[px + kx]);
+            ffma2(acc2[px][0], vv, w01);
+            ffma2(acc2[px][1], vv, w23);
           }
         }
       }
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      unpack_f32x2(acc2[px][0], acc[px][0], acc[px][1]);
+      unpack_f32x2(acc2[px][1], acc[px][2], acc[px][3]);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -184,13 +191,29 @@ constexpr int S_H = S_PART + 256;          // 8
 constexpr int S_TOTAL = S_H + 8;
 }  // namespace r
 
+// work distribution shared by both kernels: compact (grid-stride over live slots) when the per-frame counts fit the
+// slot map, else one CTA per slot with an early exit
+struct WorkList {
+  bool compact;
+  int total;
+};
+__device__ __forceinline__ WorkList worklist_init(const int* d_count, int per_frame_cap, int n_frames, int n_slots, int* s_pref) {
+  WorkList wl;
+  wl.compact = per_frame_cap > 0 && n_frames > 0 && n_frames <= SLOTMAP_MAX_FRAMES;
+  wl.total = wl.compact ? slotmap_init(d_count, n_frames, per_frame_cap, s_pref) : n_slots;
+  return wl;
+}
+
 __global__ void __launch_bounds__(256) rnet_kernel(const float* __restrict__ in, const float* __restrict__ wp,
-                                                  const int* __restrict__ d_count, int per_frame_cap,
-                                                  float* __restrict__ prob, float* __restrict__ reg) {
+                                                  const int* __restrict__ d_count, int per_frame_cap, int n_frames,
+                                                  int n_slots, float* __restrict__ prob, float* __restrict__ reg) {
   using namespace r;
   extern __shared__ __align__(16) float sm[];
-  const int slot = blockIdx.x;
-  if (!slot_live(slot, d_count, per_frame_cap)) return;
+  __shared__ int s_pref[SLOTMAP_MAX_FRAMES + 1];
+  const WorkList wl = worklist_init(d_count, per_frame_cap, n_frames, n_slots, s_pref);
+  for (int work = blockIdx.x; work < wl.total; work += gridDim.x) {
+  const int slot = wl.compact ? slotmap_slot(s_pref, n_frames, per_frame_cap, work) : work;
+  if (!wl.compact && !slot_live(slot, d_count, per_frame_cap)) continue;      // CTA uniform
   const float* src = in + (size_t)slot * 1728;
   for (int i = threadIdx.x; i < 1728 / 4; i += blockDim.x)
     reinterpret_cast<float4*>(sm + S_IN)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
@@ -202,6 +225,8 @@ __global__ void __launch_bounds__(256) rnet_kernel(const float* __restrict__ in,
   dense<576, 128, true>(sm + S_C3, sm + S_D4, sm + S_PART, wp + W4, wp + B4, wp + A4);
   heads<128>(sm + S_D4, wp + WH, wp + BH, sm + S_H);
   write_outputs(sm + S_H, slot, prob, reg);
+  __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------- O-Net
@@ -227,12 +252,15 @@ constexpr int S_TOTAL = S_H + 8;
 }  // namespace o
 
 __global__ void __launch_bounds__(512) onet_kernel(const float* __restrict__ in, const float* __restrict__ wp,
-                                                  const int* __restrict__ d_count, int per_frame_cap,
-                                                  float* __restrict__ prob, float* __restrict__ reg) {
+                                                  const int* __restrict__ d_count, int per_frame_cap, int n_frames,
+                                                  int n_slots, float* __restrict__ prob, float* __restrict__ reg) {
   using namespace o;
   extern __shared__ __align__(16) float sm[];
-  const int slot = blockIdx.x;
-  if (!slot_live(slot, d_count, per_frame_cap)) return;
+  __shared__ int s_pref[SLOTMAP_MAX_FRAMES + 1];
+  const WorkList wl = worklist_init(d_count, per_frame_cap, n_frames, n_slots, s_pref);
+  for (int work = blockIdx.x; work < wl.total; work += gridDim.x) {
+  const int slot = wl.compact ? slotmap_slot(s_pref, n_frames, per_frame_cap, work) : work;
+  if (!wl.compact && !slot_live(slot, d_count, per_frame_cap)) continue;      // CTA uniform
   const float* src = in + (size_t)slot * 6912;
   for (int i = threadIdx.x; i < 6912 / 4; i += blockDim.x)
     reinterpret_cast<float4*>(sm + S_IN)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
@@ -246,6 +274,8 @@ __global__ void __launch_bounds__(512) onet_kernel(const float* __restrict__ in,
   dense<1152, 256, true>(sm + S_C4, sm + S_D5, sm + S_PART, wp + W5, wp + B5, wp + A5);
   heads<256>(sm + S_D5, wp + WH, wp + BH, sm + S_H);
   write_outputs(sm + S_H, slot, prob, reg);
+  __syncthreads();
+  }
 }
 
 }  // namespace ro
@@ -320,7 +350,10 @@ int ro_pack_weights(trl_ctx* c, const float* h_r, size_t rlen, const float* h_o,
 int launch_rnet_ex(trl_ctx* c, const float* d_in, int n_slots, const int* d_count, int per_frame_cap, float* d_prob,
                    float* d_reg, cudaStream_t s) {
   if (n_slots <= 0) return TRL_OK;
-  ro::rnet_kernel<<<n_slots, 256, ro::r::S_TOTAL * 4, s>>>(d_in, c->d_rnet, d_count, per_frame_cap, d_prob, d_reg);
+  const int n_frames = per_frame_cap > 0 ? n_slots / per_frame_cap : 0;
+  const bool compact = per_frame_cap > 0 && n_frames <= SLOTMAP_MAX_FRAMES;
+  const int grid = compact ? std::min(n_slots, TRL_NUM_SMS * 6) : n_slots;       // ~37 KB of shared memory per CTA: 6 CTAs / SM
+  ro::rnet_kernel<<<grid, 256, ro::r::S_TOTAL * 4, s>>>(d_in, c->d_rnet, d_count, per_frame_cap, n_frames, n_slots, d_prob, d_reg);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
@@ -328,7 +361,10 @@ int launch_rnet_ex(trl_ctx* c, const float* d_in, int n_slots, const int* d_coun
 int launch_onet_ex(trl_ctx* c, const float* d_in, int n_slots, const int* d_count, int per_frame_cap, float* d_prob,
                    float* d_reg, cudaStream_t s) {
   if (n_slots <= 0) return TRL_OK;
-  ro::onet_kernel<<<n_slots, 512, ro::o::S_TOTAL * 4, s>>>(d_in, c->d_onet, d_count, per_frame_cap, d_prob, d_reg);
+  const int n_frames = per_frame_cap > 0 ? n_slots / per_frame_cap : 0;
+  const bool compact = per_frame_cap > 0 && n_frames <= SLOTMAP_MAX_FRAMES;
+  const int grid = compact ? std::min(n_slots, TRL_NUM_SMS) : n_slots;           // ~168 KB of shared memory per CTA: 1 CTA / SM
+  ro::onet_kernel<<<grid, 512, ro::o::S_TOTAL * 4, s>>>(d_in, c->d_onet, d_count, per_frame_cap, n_frames, n_slots, d_prob, d_reg);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }

@@ -107,19 +107,6 @@ struct Params {
 __device__ unsigned long long g_pnet_phase[8];
 #endif
 __device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : v * a; }
-// sm_100 packed fp32: two independent IEEE fmas per instruction (SASS FFMA2; a (v, v) pair becomes a scalar broadcast operand)
-__device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
-}
-
 // (x0, x1), already scaled -> packed fp16 hi and lo = fp16(x - hi)
 __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x0, x1);

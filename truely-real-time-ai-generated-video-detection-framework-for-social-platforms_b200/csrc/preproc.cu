@@ -313,15 +313,20 @@ int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, con
 __global__ void __launch_bounds__(256) crop_resample_kernel(const uint8_t* __restrict__ frames, int H, int W,
                                                            const int* __restrict__ pad4, const int* __restrict__ img,
                                                            const int* __restrict__ d_count, int per_frame_cap,
-                                                           int S, float* __restrict__ out) {
-  const int slot = blockIdx.x;
+                                                           int n_frames, int n_slots, int S, float* __restrict__ out) {
+  // per-frame lists: grid-stride over the compacted live slots (common.cuh slot map); flat lists: one CTA per slot
+  __shared__ int s_pref[SLOTMAP_MAX_FRAMES + 1];
+  const bool compact = per_frame_cap > 0 && n_frames > 0 && n_frames <= SLOTMAP_MAX_FRAMES;
+  const int total_work = compact ? slotmap_init(d_count, n_frames, per_frame_cap, s_pref) : n_slots;
+  for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+  const int slot = compact ? slotmap_slot(s_pref, n_frames, per_frame_cap, work) : work;
   int b, n_live;
   if (per_frame_cap > 0) {          // slot = frame * cap + i, counts per frame
     b = slot / per_frame_cap;
     n_live = d_count[b];
-    if (slot - b * per_frame_cap >= n_live) return;
+    if (slot - b * per_frame_cap >= n_live) continue;
   } else {
-    if (d_count && slot >= *d_count) return;
+    if (d_count && slot >= *d_count) continue;
     b = img[slot];
   }
   const int y = pad4[slot * 4 + 0], ey = pad4[slot * 4 + 1], x = pad4[slot * 4 + 2], ex = pad4[slot * 4 + 3];
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(256) crop_resample_kernel(const uint8_t* __res
   const int ch = ey - (y - 1), cw = ex - (x - 1);
   if (ch <= 0 || cw <= 0) {   // degenerate: upstream skips such crops (detect_face.py stage 2/3 loop guard)
     for (int i = threadIdx.x; i < 3 * S * S; i += blockDim.x) o[i] = 0.f;
-    return;
+    continue;
   }
   const uint8_t* frame = frames + (size_t)b * H * W * 3;
   int grp = 1;
@@ -364,13 +369,17 @@ __global__ void __launch_bounds__(256) crop_resample_kernel(const uint8_t* __res
       o[2 * total + pix] = area_norm(s2, kh, kw);
     }
   }
+  }
 }
 
 // d_count semantics: if per_frame_cap > 0, d_count is int[B] and slots are frame*cap+i; else a single int (or null).
 int launch_crop_resample_ex(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const int* d_pad, const int* d_img,
                             const int* d_count, int per_frame_cap, int n_slots, int size, float* d_out, cudaStream_t s) {
   if (n_slots <= 0) return TRL_OK;
-  crop_resample_kernel<<<n_slots, 256, 0, s>>>(d_frames, H, W, d_pad, d_img, d_count, per_frame_cap, size, d_out);
+  const int n_frames = per_frame_cap > 0 ? n_slots / per_frame_cap : 0;
+  const bool compact = per_frame_cap > 0 && n_frames <= SLOTMAP_MAX_FRAMES;
+  const int grid = compact ? (n_slots < TRL_NUM_SMS * 8 ? n_slots : TRL_NUM_SMS * 8) : n_slots;
+  crop_resample_kernel<<<grid, 256, 0, s>>>(d_frames, H, W, d_pad, d_img, d_count, per_frame_cap, n_frames, n_slots, size, d_out);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
