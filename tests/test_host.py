@@ -105,3 +105,18 @@ def test_run_length_and_score_match_the_reference_logic():
         frame_count = n * stride - int(rng.integers(0, stride))
         assert rl.deepfake_count == run and rl.deep_fake_frame_count == flagged
         assert M.final_score(flagged, run, frame_count, fps, stride) == R.final_score(flagged, run, frame_count, fps, stride)
+
+
+def test_chunk_schedule_covers_every_frame_once():
+    from truely_b200.model import chunk_schedule
+    for n in (1, 7, 89, 90, 91, 250, 450, 1000):
+        for chunk in (1, 8, 90):
+            for ramp in (False, True):
+                r = chunk_schedule(n, chunk, ramp=ramp)
+                assert r[0][0] == 0 and r[-1][1] == n
+                assert all(a < b and b - a <= chunk for a, b in r)
+                assert all(r[i][1] == r[i + 1][0] for i in range(len(r) - 1))
+    r = chunk_schedule(450, 90, ramp=True)
+    sz = [b - a for a, b in r]
+    assert sz[0] == 22 and 45 <= sz[-1] < 90                            # short first copy, shorter last cascade
+    assert all(sz[i] >= sz[i + 1] for i in range(2, len(sz) - 1))       # the tail only shrinks

@@ -202,8 +202,8 @@ class Analyzer:
         """All processed frames of a clip (or of this rank's range) in one go.
 
         ``frames``: uint8 [N,H,W,3] tensor, either on the device (``h2d=False``) or in pinned host memory
-        (``h2d=True``: chunks are copied to the device inside this call on a copy stream, double buffered in
-        ``dev_frames`` [2,chunk,H,W,3], so the copy of chunk k+1 overlaps the cascade on chunk k).
+        (``h2d=True``: chunks are copied to the device inside this call on a copy stream, multi-buffered in
+        ``dev_frames`` [nbuf,chunk,H,W,3], so the copies of the next chunks overlap the cascade on chunk k).
         The MTCNN cascade + crop-align run chunk by chunk (bounded workspace); all N crops are then embedded by ONE
         FaceNet call (large-M GEMMs) and compared by one consistency call.  Nothing synchronises with the host.
         Returns the dict of device outputs [N, ...]; if ``host_out`` (pinned tensors keyed like the outputs) is given,
@@ -221,7 +221,8 @@ class Analyzer:
         if h2d and getattr(self, "_copy_stream", None) is None:
             self._copy_stream = t.cuda.Stream(device=self.device)
         he, hv = (halo if halo is not None else (None, None))
-        chunks = [(a, min(N, a + chunk)) for a in range(0, N, chunk)]
+        chunks = chunk_schedule(N, chunk, ramp=h2d)
+        nbuf = dev_frames.shape[0] if h2d else 0
         if h2d:
             cs = self._copy_stream
             copied = [t.cuda.Event() for _ in chunks]
@@ -230,11 +231,11 @@ class Analyzer:
         for k, (a, b) in enumerate(chunks):
             if h2d:
                 with t.cuda.stream(cs):
-                    if k >= 2:
-                        cs.wait_event(consumed[k - 2])          # staging buffer k&1 is free again
-                    dev_frames[k & 1, : b - a].copy_(frames[a:b], non_blocking=True)
+                    if k >= nbuf:
+                        cs.wait_event(consumed[k - nbuf])       # staging buffer k % nbuf is free again
+                    dev_frames[k % nbuf, : b - a].copy_(frames[a:b], non_blocking=True)
                     copied[k].record(cs)
-                d = dev_frames[k & 1, : b - a]
+                d = dev_frames[k % nbuf, : b - a]
             else:
                 d = frames[a:b]
             with t.cuda.stream(self.stream):
@@ -246,6 +247,8 @@ class Analyzer:
                 if h2d:
                     consumed[k].record(self.stream)
         with t.cuda.stream(self.stream):
+            # one FaceNet batch for the whole range: per-chunk calls (tried, to hide FaceNet under the next copy) make the
+            # step launch bound on the host (~110 launches per call) and were 8 ms slower end to end
             self._check(self.lib.trl_facenet(self.ctx, _vp(out["crops"]), N, S, _vp(out["emb"]), self._sptr()))
             self._check(self.lib.trl_consistency(
                 self.ctx, _vp(out["emb"]), _vp(out["valid"]), N, _vp(he), _vp(hv), thr, _vp(out["sim"]), _vp(out["below"]),
@@ -254,6 +257,36 @@ class Analyzer:
                 for key, h in host_out.items():
                     h[:N].copy_(out[key][:N], non_blocking=True)
         return out
+
+
+def chunk_schedule(n: int, chunk: int, ramp: bool = False):
+    """[(start, end)] ranges of at most ``chunk`` frames.  With ``ramp`` (host frames: the H2D copy of chunk k+1 overlaps
+    the cascade on chunk k) the chunks grow at the start and shrink towards the end: the copy of the first chunk and the
+    cascade of the last one are the parts of the pipeline that nothing overlaps.  A cascade launch has a fixed cost
+    (about 0.8 ms on B200, experiments/e2e_timeline.py), so a chunk keeps up with the copy of its successor only if the
+    successor is at least ~0.65 of its size + 16 frames: the tail shrinks by that rule and stops at half a chunk."""
+    if not ramp or n <= chunk:
+        return [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
+    head = [max(1, chunk // 4), max(1, chunk // 2)]
+    tail, t = [], chunk
+    while True:
+        t = int(0.65 * t + 16)
+        if t >= chunk or t < chunk // 2 or (tail and t >= tail[-1]) or len(tail) == 3:
+            break
+        tail.append(t)
+    if sum(head) + sum(tail) + chunk > n:
+        tail = tail[-1:] if tail and sum(head) + tail[-1] < n else []
+    rest = n - sum(head) - sum(tail)
+    full, rem = divmod(rest, chunk)
+    if rem and rem + head[1] <= chunk:
+        head[1] += rem                   # a small remainder rides with the second chunk
+        rem = 0
+    sizes = head + ([rem] if rem else []) + [chunk] * full + tail
+    out, a = [], 0
+    for sz in sizes:
+        out.append((a, a + sz))
+        a += sz
+    return out
 
 
 def score_from_flags(valid, has_sim, below, frame_count: int, fps: int, stride: int):
