@@ -42,6 +42,7 @@ struct ConvOp {
   int flat;             // 1x1 stride-1: rows are consecutive pixels (box_w = 128)
   CUtensorMap tmap_a;   // 4-D (C, W, H, N) over the input slice
   CUtensorMap tmap_w;   // 2-D (K, Cout)
+  CUtensorMap tmap_r;   // 2-D (Cout, pixels) over the residual operand (EPI_RESID* only)
 };
 
 struct PoolOp {       // MaxPool2d(3, stride 2), NHWC

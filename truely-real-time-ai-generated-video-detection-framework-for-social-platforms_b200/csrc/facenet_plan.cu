@@ -387,6 +387,38 @@ int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, float* d_e
   return launch_head(c, e->d_act[e->buf_final], n, e->sz[L9] * e->sz[L9], e->d_head_w, e->d_head_b, d_emb, s);
 }
 
+
+// debug / profiling: one forward pass with a CUDA-event pair around every step.  info[i] = {kind, Cin, Cout, kh, kw, Hout,
+// block_n, block_k}, ms[i] = device time of step i.  Returns the number of steps (<= max_steps) or a negative error.
+extern "C" int trl_debug_facenet_step_times(trl_ctx* c, const uint8_t* d_crops, int n, int S, float* d_emb, int max_steps,
+                                            int* info /*[max_steps][8]*/, float* ms /*[max_steps]*/, void* stream) {
+  FaceNetEngine* e = c->facenet;
+  if (!e || !info || !ms) return TRL_E_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = facenet_forward(c, d_crops, n, S, d_emb, s);      // sizes the engine, warms up
+  if (rc != TRL_OK) return rc;
+  const int ns = (int)e->steps.size();
+  if (ns > max_steps) return TRL_E_INVALID;
+  std::vector<cudaEvent_t> ev(ns + 1);
+  for (auto& x : ev) cudaEventCreate(&x);
+  cudaEventRecord(ev[0], s);
+  for (int i = 0; i < ns; ++i) {
+    const FaceNetEngine::Step& st = e->steps[i];
+    if (st.kind == 1) rc = launch_maxpool(c, st.pool, n, s);
+    else rc = (c->cfg.facenet_impl == 0) ? launch_conv_umma(c, st.conv, n, s) : launch_conv_simt(c, st.conv, n, s);
+    if (rc != TRL_OK) return rc;
+    cudaEventRecord(ev[i + 1], s);
+    int* f = info + i * 8;
+    if (st.kind == 1) { f[0] = 1; f[1] = st.pool.C; f[2] = st.pool.C; f[3] = 3; f[4] = 3; f[5] = st.pool.Hout; f[6] = 0; f[7] = 0; }
+    else { f[0] = 0; f[1] = st.conv.Cin; f[2] = st.conv.Cout; f[3] = st.conv.kh; f[4] = st.conv.kw; f[5] = st.conv.Hout;
+           f[6] = st.conv.block_n; f[7] = st.conv.block_k; }
+  }
+  cudaStreamSynchronize(s);
+  for (int i = 0; i < ns; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+  for (auto& x : ev) cudaEventDestroy(x);
+  return ns;
+}
+
 // debug / validation access to intermediate activations (tests compare the tcgen05 path layer by layer)
 extern "C" int trl_debug_facenet_num_layers(trl_ctx* c) { return c->facenet ? (int)c->facenet->layers.size() : 0; }
 

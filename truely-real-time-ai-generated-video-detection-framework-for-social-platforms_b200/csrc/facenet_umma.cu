@@ -16,7 +16,7 @@
 namespace umma {
 
 constexpr int BLOCK_M = 128;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane group: column halves)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -97,13 +97,38 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
-__global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_constant__ ConvOp op, int n_img, int tiles_w,
-                                                                int tiles_h, int stages, uint32_t tmem_cols) {
+// tile id -> output tile: N tiles fastest, so CTAs running side by side share the same A rows through L2
+struct TileCoord { int ox0, oy0, n0, n_off; };
+__device__ __forceinline__ TileCoord tile_coord(const ConvOp& op, int t, int n_ntiles, int tiles_w, int tiles_h) {
+  const int nt = t % n_ntiles, mt = t / n_ntiles;
+  const int tw = mt % tiles_w, th = (mt / tiles_w) % tiles_h, tn = mt / (tiles_w * tiles_h);
+  TileCoord c;
+  c.ox0 = tw * op.box_w; c.oy0 = th * op.box_h; c.n0 = tn * op.box_n; c.n_off = nt * op.block_n;
+  return c;
+}
+
+// Persistent: one CTA per SM walks the tile list.  The TMA producer runs ahead across tile boundaries (the smem ring
+// never drains), the MMA issuer alternates between two TMEM accumulators, and the epilogue warps drain accumulator
+// i while the MMAs of the next tile fill accumulator i^1 -- load, MMA and epilogue of consecutive tiles overlap.
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_constant__ ConvOp op, int n_img, int tiles_w,
+                                                                   int tiles_h, int n_ntiles, int total_tiles, int stages,
+                                                                   uint32_t acc_cols) {
+  // shared memory: [stages x A][stages x B][barriers, tmem slot, row table][output tile][residual tile]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int BK = op.block_k, BN = op.block_n;
@@ -112,26 +137,31 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
   uint8_t* smem_b = smem + stages * a_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + stages * b_bytes);
   uint64_t* empty_bar = full_bar + stages;
-  uint64_t* accum_bar = empty_bar + stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + stages;      // [2] accumulator complete (tcgen05.commit)
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained (128 epilogue threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* rfull_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);          // [2] residual tile landed (TMA)
+  uint64_t* rempty_bar = rfull_bar + 2;                                       // [2] residual tile consumed (256 epilogue threads)
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(rempty_bar + 2) + 15) & ~(uintptr_t)15);   // [Cout] bias, once per CTA
+  // residual tiles: [2][BN / 64] boxes of 128 rows x 64 channels (128 B rows, SWIZZLE_128B), 1024-byte aligned
+  uint8_t* rt = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sbias + op.Cout) + 1023) & ~(uintptr_t)1023);
+  const bool has_resid = op.epi != EPI_RELU;
+  const uint32_t rt_bytes = (uint32_t)(BN / 64) * 16384u;                     // one residual tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x;
-  const int tw = mt % tiles_w, th = (mt / tiles_w) % tiles_h, tn = mt / (tiles_w * tiles_h);
-  const int ox0 = tw * op.box_w, oy0 = th * op.box_h, n0 = tn * op.box_n;
-  const int n_off = blockIdx.y * BN;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&op.tmap_a);
     prefetch_tmap(&op.tmap_w);
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(accum_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); mbar_init(&rfull_bar[i], 1); mbar_init(&rempty_bar[i], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2u * acc_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < op.Cout; i += NUM_THREADS) sbias[i] = __ldg(op.bias + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -147,15 +177,27 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
       const uint32_t tx_bytes = box_rows * BK * 2 + b_bytes;
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < k_iters; ++it) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        const int tap = it / cin_blocks, cb = it - tap * cin_blocks;
-        const int ky = tap / op.kw, kx = tap - ky * op.kw;
-        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-        tma_load_4d(smem_u32(smem_a + stage * a_bytes), &op.tmap_a, &full_bar[stage], cb * BK,
-                    ox0 * op.stride + kx - op.pad_w, oy0 * op.stride + ky - op.pad_h, n0);
-        tma_load_2d(smem_u32(smem_b + stage * b_bytes), &op.tmap_w, &full_bar[stage], tap * op.Cin + cb * BK, n_off);
-        if (++stage == stages) { stage = 0; phase ^= 1; }
+      int tl = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+        const TileCoord tc = tile_coord(op, t, n_ntiles, tiles_w, tiles_h);
+        if (has_resid) {
+          // the tile's residual rows (flat 1x1 layers only): fetched by TMA a tile ahead of its epilogue
+          const int rb = tl & 1;
+          mbar_wait(&rempty_bar[rb], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&rfull_bar[rb], rt_bytes);
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(smem_u32(rt + rb * rt_bytes + j * 16384), &op.tmap_r, &rfull_bar[rb], tc.n_off + 64 * j, tc.ox0);
+        }
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int tap = it / cin_blocks, cb = it - tap * cin_blocks;
+          const int ky = tap / op.kw, kx = tap - ky * op.kw;
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_4d(smem_u32(smem_a + stage * a_bytes), &op.tmap_a, &full_bar[stage], cb * BK,
+                      tc.ox0 * op.stride + kx - op.pad_w, tc.oy0 * op.stride + ky - op.pad_h, tc.n0);
+          tma_load_2d(smem_u32(smem_b + stage * b_bytes), &op.tmap_w, &full_bar[stage], tap * op.Cin + cb * BK, tc.n_off);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -166,56 +208,85 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
       const uint32_t sbo = 8u * (uint32_t)BK * 2u;
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < k_iters; ++it) {
-        mbar_wait(&full_bar[stage], phase);
+      int tl = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+        const int buf = tl & 1;
+        mbar_wait(&tempty_bar[buf], ((uint32_t)(tl >> 1) & 1u) ^ 1u);       // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * a_bytes), sbo, layout);
-        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * b_bytes), sbo, layout);
-        for (int kk = 0; kk < BK / 16; ++kk)
-          mma_bf16(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (it > 0 || kk > 0) ? 1u : 0u);
-        mma_commit(&empty_bar[stage]);          // frees this smem stage when the MMAs above retire
-        if (it == k_iters - 1) mma_commit(accum_bar);
-        if (++stage == stages) { stage = 0; phase ^= 1; }
+        const uint32_t d = tmem_base + (uint32_t)buf * acc_cols;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * a_bytes), sbo, layout);
+          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * b_bytes), sbo, layout);
+          for (int kk = 0; kk < BK / 16; ++kk)
+            mma_bf16(d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          mma_commit(&empty_bar[stage]);          // frees this smem stage when the MMAs above retire
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(&tfull_bar[buf]);
       }
     }
   } else {
-    // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 ; thread <-> one output pixel (tile row)
+    // ===== epilogue (8 warps): warp w owns TMEM lanes 32*(w%4) .. +31 and one half of the tile's columns; thread <->
+    // one output pixel (tile row).  No global loads on this path: bias comes from shared memory, the residual tile was
+    // fetched by the producer's TMA.  All accumulator columns of the thread are loaded first (one wait) and the
+    // accumulator is handed back to the MMA warp before the bias / residual / ReLU / store work starts.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
-    bool valid;
-    long long m;
-    if (op.flat) {
-      m = (long long)ox0 + r;
-      valid = m < (long long)n_img * op.Hout * op.Wout;
-    } else {
-      const int per_img = op.box_w * op.box_h;
-      const int ni = r / per_img, rem = r - ni * per_img;
-      const int hy = rem / op.box_w, wx = rem - hy * op.box_w;
-      const int n = n0 + ni, oy = oy0 + hy, ox = ox0 + wx;
-      valid = (ni < op.box_n) && (n < n_img) && (oy < op.Hout) && (ox < op.Wout);
-      m = ((long long)n * op.Hout + oy) * op.Wout + ox;
-    }
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c = 0; c < BN; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(taddr_row + (uint32_t)c, v);
-      if (valid) {
-        const int ng = n_off + c;
+    const int BNh = BN >> 1;                      // columns of this thread: [half * BNh, half * BNh + BNh), BNh in {16..96}
+    int tl = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+      const TileCoord tc = tile_coord(op, t, n_ntiles, tiles_w, tiles_h);
+      const int ox0 = tc.ox0, oy0 = tc.oy0, n0 = tc.n0, n_off = tc.n_off;
+      const int buf = tl & 1;
+      bool valid;
+      long long m;
+      if (op.flat) {
+        m = (long long)ox0 + r;
+        valid = m < (long long)n_img * op.Hout * op.Wout;
+      } else {
+        const int per_img = op.box_w * op.box_h;
+        const int ni = r / per_img, rem = r - ni * per_img;
+        const int hy = rem / op.box_w, wx = rem - hy * op.box_w;
+        const int n = n0 + ni, oy = oy0 + hy, ox = ox0 + wx;
+        valid = (ni < op.box_n) && (n < n_img) && (oy < op.Hout) && (ox < op.Wout);
+        m = ((long long)n * op.Hout + oy) * op.Wout + ox;
+      }
+      const int cbase = half * BNh;
+      mbar_wait(&tfull_bar[buf], (uint32_t)(tl >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)cbase;
+      uint32_t v[6][16];
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc)
+        if (cc * 16 < BNh) tmem_ld16_async(taddr_row + (uint32_t)(cc * 16), v[cc]);
+      tmem_ld_wait();
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[buf])) : "memory");
+      if (has_resid) mbar_wait(&rfull_bar[buf], (uint32_t)(tl >> 1) & 1u);
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) {
+        if (cc * 16 >= BNh) break;
+        const int cl = cbase + cc * 16;            // column within the tile
+        const int ng = n_off + cl;
         float f[16];
-        const float4* b4 = reinterpret_cast<const float4*>(op.bias + ng);
+        const float4* b4 = reinterpret_cast<const float4*>(sbias + ng);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 bv = __ldg(b4 + j);
-          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bv.x;
-          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv.y;
-          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv.z;
-          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv.w;
+          const float4 bv = b4[j];
+          f[4 * j + 0] = __uint_as_float(v[cc][4 * j + 0]) + bv.x;
+          f[4 * j + 1] = __uint_as_float(v[cc][4 * j + 1]) + bv.y;
+          f[4 * j + 2] = __uint_as_float(v[cc][4 * j + 2]) + bv.z;
+          f[4 * j + 3] = __uint_as_float(v[cc][4 * j + 3]) + bv.w;
         }
-        if (op.epi != EPI_RELU) {
-          const uint4* xr = reinterpret_cast<const uint4*>(op.resid + (size_t)m * op.Cout + ng);
-          const uint4 x0 = xr[0], x1 = xr[1];
+        if (has_resid) {
+          // 128-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+          const uint8_t* box = rt + buf * rt_bytes + (cl >> 6) * 16384 + r * 128;
+          const int ch = (cl & 63) >> 3;             // first of the two 16-byte chunks
+          const uint4 x0 = *reinterpret_cast<const uint4*>(box + ((ch ^ (r & 7)) << 4));
+          const uint4 x1 = *reinterpret_cast<const uint4*>(box + (((ch + 1) ^ (r & 7)) << 4));
           const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&x0);
           const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&x1);
 #pragma unroll
@@ -231,25 +302,28 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        uint4 o0, o1;
-        o0.x = pack_bf16(f[0], f[1]); o0.y = pack_bf16(f[2], f[3]); o0.z = pack_bf16(f[4], f[5]); o0.w = pack_bf16(f[6], f[7]);
-        o1.x = pack_bf16(f[8], f[9]); o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
-        for (int sidx = 0; sidx < op.nseg; ++sidx) {
-          const OutSeg& sg = op.seg[sidx];
-          if (ng >= sg.n_begin && ng < sg.n_end) {
-            uint4* d = reinterpret_cast<uint4*>(sg.dst + (size_t)m * sg.dst_ctot + sg.dst_coff + (ng - sg.n_begin));
-            d[0] = o0;
-            d[1] = o1;
+        if (valid) {
+          uint4 o0, o1;
+          o0.x = pack_bf16(f[0], f[1]); o0.y = pack_bf16(f[2], f[3]); o0.z = pack_bf16(f[4], f[5]); o0.w = pack_bf16(f[6], f[7]);
+          o1.x = pack_bf16(f[8], f[9]); o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
+          for (int sidx = 0; sidx < op.nseg; ++sidx) {
+            const OutSeg& sg = op.seg[sidx];
+            if (ng >= sg.n_begin && ng < sg.n_end) {
+              uint4* d = reinterpret_cast<uint4*>(sg.dst + (size_t)m * sg.dst_ctot + sg.dst_coff + (ng - sg.n_begin));
+              d[0] = o0;
+              d[1] = o1;
+            }
           }
         }
       }
+      if (has_resid) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&rempty_bar[buf])) : "memory");
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * acc_cols) : "memory");
   }
 }
 
@@ -329,6 +403,18 @@ int umma_encode_maps(trl_ctx* c, ConvOp& op, int n_cap) {
   r = g_encode(&op.tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)op.w, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) TRL_FAIL(c, TRL_E_CUDA, "%s: cuTensorMapEncodeTiled(W) failed with %d", op.name, (int)r);
+  if (op.epi != EPI_RELU) {
+    // residual operand [pixels][Cout] of the (flat 1x1) up-projections: 128 rows x 64 channels per box, 128-byte swizzle
+    if (!op.flat || op.block_n % 64 != 0) TRL_FAIL(c, TRL_E_INVALID, "%s: residual epilogue needs a flat 1x1 layer with block_n %% 64 == 0", op.name);
+    const cuuint64_t opix = (cuuint64_t)n_cap * op.Hout * op.Wout;
+    cuuint64_t rd[2] = {(cuuint64_t)op.Cout, opix};
+    cuuint64_t rs[1] = {(cuuint64_t)op.Cout * 2};
+    cuuint32_t rb[2] = {64, 128};
+    cuuint32_t re[2] = {1, 1};
+    r = g_encode(&op.tmap_r, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)op.resid, rd, rs, rb, re, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) TRL_FAIL(c, TRL_E_CUDA, "%s: cuTensorMapEncodeTiled(R) failed with %d", op.name, (int)r);
+  }
   return TRL_OK;
 }
 
@@ -344,16 +430,22 @@ int launch_conv_umma(trl_ctx* c, const ConvOp& op, int n, cudaStream_t s) {
     tiles_h = ceil_div(op.Hout, op.box_h);
     tiles_n = ceil_div(n, op.box_n);
   }
-  const int k_iters = op.kh * op.kw * (op.Cin / op.block_k);
   const int stage_bytes = (BLOCK_M + op.block_n) * op.block_k * 2;
-  int stages = k_iters < 4 ? k_iters : 4;
-  while (stages > 2 && stages * stage_bytes > 100 * 1024) --stages;
-  if (stages < 1) stages = 1;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-  uint32_t cols = 32;
-  while ((int)cols < op.block_n) cols <<= 1;
-  dim3 grid(tiles_w * tiles_h * tiles_n, op.Cout / op.block_n);
-  conv_umma_kernel<<<grid, NUM_THREADS, smem, s>>>(op, n, tiles_w, tiles_h, stages, cols);
+  // persistent CTA, one per SM: as many ring stages as fit (the producer prefetches across tile boundaries); the
+  // footprint is kept above half of the SM's shared memory so that two CTAs (2 x 512 TMEM columns) never co-reside
+  const bool has_resid = op.epi != EPI_RELU;
+  const size_t epi_bytes = (size_t)op.Cout * 4 + (has_resid ? 1024 + 2 * (size_t)(op.block_n / 64) * 16384 : 1024);
+  const size_t fixed = 1024 /*alignment*/ + 512 /*barriers: 2 x 20 stages + 8*/ + 64 + epi_bytes;
+  int stages = (int)((196 * 1024 - fixed) / stage_bytes);
+  if (stages > 20) stages = 20;      // small-K / narrow layers are TMA-latency bound: keep many loads in flight
+  if (stages < 2) stages = 2;
+  size_t smem = (size_t)stages * stage_bytes + fixed;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  const uint32_t acc_cols = op.block_n <= 32 ? 32u : op.block_n <= 64 ? 64u : op.block_n <= 128 ? 128u : 256u;
+  const int n_ntiles = op.Cout / op.block_n;
+  const long long total = (long long)tiles_w * tiles_h * tiles_n * n_ntiles;
+  const int grid = (int)(total < TRL_NUM_SMS ? total : TRL_NUM_SMS);
+  conv_umma_kernel<<<grid, NUM_THREADS, smem, s>>>(op, n, tiles_w, tiles_h, n_ntiles, (int)total, stages, acc_cols);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
