@@ -189,6 +189,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     an = M.Analyzer(device=local_rank)
     clip, stride, pinned, n_proc_total, n_local = make_frames(WORKLOADS[args.workload]["cfg"], rank, world, torch)
