@@ -203,3 +203,44 @@ def test_fused_process_equals_staged_calls(analyzer):
     assert np.array_equal(a.nfaces, b.nfaces) and np.array_equal(a.box, b.box) and np.array_equal(a.valid, b.valid)
     assert np.array_equal(a.emb, b.emb) and np.array_equal(a.below, b.below)
     assert np.allclose(a.sim, b.sim, equal_nan=True)
+
+
+def test_chunking_and_host_buffer_path_do_not_change_results(analyzer):
+    """size-independent properties at the bench's frame size: the cascade is per-frame independent, so any chunking of
+    the batch and the pinned-host (H2D overlapped) path must give bit-identical boxes, crops, embeddings and flags"""
+    an = analyzer
+    clip = SyntheticClip(720, 1280, 30, 240, n_faces=(1, 1), seed=3)
+    frames = np.stack([clip.frame(i) for i in clip.processed_indices()[:40]])
+    d = torch.from_numpy(frames).cuda()
+    out0 = an.analyze_resident(d, chunk=40)
+    torch.cuda.synchronize()                       # the analyzer works on its own stream
+    ref = {k: out0[k][:40].clone() for k in ("box", "valid", "emb", "sim", "below", "has_sim", "crops")}
+    torch.cuda.synchronize()
+    pinned = torch.from_numpy(frames).pin_memory()
+    stage = torch.empty((3, 16, 720, 1280, 3), dtype=torch.uint8, device="cuda")
+    for kwargs in (dict(chunk=7), dict(chunk=16, h2d=True, dev_frames=stage)):
+        src = pinned if kwargs.get("h2d") else d
+        out = an.analyze_resident(src, **kwargs)
+        an.stream.synchronize()
+        torch.cuda.synchronize()
+        for k, v in ref.items():
+            a, b = out[k][:40], v[:40]
+            if a.is_floating_point():          # sim of a frame without a predecessor is NaN by design
+                a, b = torch.nan_to_num(a, nan=-2.0), torch.nan_to_num(b, nan=-2.0)
+            assert torch.equal(a, b), f"{k} differs with {list(kwargs)}"
+    assert int(ref["valid"][:40].sum()) > 30          # the property is not vacuous: faces were found
+
+
+def test_1080p_multi_face_matches_oracle(analyzer):
+    """BASELINE.json configs[3] shape: 1080p, 4-8 faces per frame, 12 pyramid scales -- same face count, IoU >= 0.95"""
+    an = analyzer
+    clip = SyntheticClip(1080, 1920, 60, 64, n_faces=(4, 8), face_h=(60.0, 300.0), seed=9)
+    frames = np.stack([clip.frame(i) for i in (0, 24, 48)])
+    res = an.process_frames(frames, detail=True)
+    mt = H.oracle_mtcnn()
+    for i, f in enumerate(frames):
+        boxes, _ = mt.detect(f)
+        n_ref = 0 if boxes is None else len(boxes)
+        assert int(res.counts[i, 3]) == n_ref, f"frame {i}: {int(res.counts[i, 3])} faces, oracle {n_ref}"
+        if n_ref:
+            _match_boxes(res.boxes[i, :n_ref, :4], boxes)

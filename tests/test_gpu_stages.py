@@ -95,6 +95,44 @@ def test_pnet_maps_match_oracle(analyzer, clip_frames):
         assert (d_reg.cpu() - reg).abs().max().item() < 2e-5, f"scale {s}"
 
 
+# tile geometry of the persistent P-Net kernel: outputs smaller than one 16x32 tile, exact tile multiples, one cell more
+# than a multiple (a second, nearly empty tile row / column), the 12x12 minimum, many frames with few tiles each
+@pytest.mark.parametrize("B,hs,ws", [(1, 12, 12), (3, 13, 29), (2, 42, 74), (2, 44, 76), (1, 47, 83), (5, 121, 67), (37, 20, 33)])
+def test_pnet_maps_tile_edges(analyzer, B, hs, ws):
+    an = analyzer
+    pnet = H.oracle_mtcnn().pnet
+    g = torch.Generator().manual_seed(1000 * hs + ws)
+    im = (torch.rand((B, 3, hs, ws), generator=g) * 2 - 1).contiguous()
+    with torch.no_grad():
+        reg, prob = pnet(im)
+    oh, ow = prob.shape[2:]
+    assert (oh, ow) == ((hs - 2 + 1) // 2 - 4, (ws - 2 + 1) // 2 - 4)
+    d_in = im.cuda()
+    d_prob = torch.full((B, oh, ow), -1.0, dtype=torch.float32, device="cuda")
+    d_reg = torch.full((B, 4, oh, ow), -9.0, dtype=torch.float32, device="cuda")
+    ok(an, an.lib.trl_pnet(an.ctx, vp(d_in), B, hs, ws, vp(d_prob), vp(d_reg), None))
+    torch.cuda.synchronize()
+    assert (d_prob.cpu() - prob[:, 1]).abs().max().item() < 2e-5
+    assert (d_reg.cpu() - reg).abs().max().item() < 2e-5
+
+
+def test_pnet_is_deterministic_across_launches(analyzer):
+    """the persistent kernel's tile -> CTA assignment must not leak into the maps (no stale shared memory / TMEM)"""
+    an = analyzer
+    g = torch.Generator().manual_seed(5)
+    im = (torch.rand((4, 3, 90, 150), generator=g) * 2 - 1).cuda().contiguous()
+    oh, ow = (90 - 2 + 1) // 2 - 4, (150 - 2 + 1) // 2 - 4
+    outs = []
+    for _ in range(3):
+        d_prob = torch.empty((4, oh, ow), dtype=torch.float32, device="cuda")
+        d_reg = torch.empty((4, 4, oh, ow), dtype=torch.float32, device="cuda")
+        ok(an, an.lib.trl_pnet(an.ctx, vp(im), 4, 90, 150, vp(d_prob), vp(d_reg), None))
+        torch.cuda.synchronize()
+        outs.append((d_prob.clone(), d_reg.clone()))
+    for pr, rg in outs[1:]:
+        assert torch.equal(pr, outs[0][0]) and torch.equal(rg, outs[0][1])
+
+
 # ----------------------------------------------------------------------------- K4 / K5
 def _random_boxes(rng, n, spread, ties=False):
     c = rng.uniform(0, spread, (n, 2)).astype(np.float32)
