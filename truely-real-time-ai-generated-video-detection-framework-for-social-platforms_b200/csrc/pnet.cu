@@ -49,7 +49,11 @@ __host__ __device__ constexpr bool tile_n64(int tile) { return DEFER_EPILOGUE ? 
 __host__ __device__ constexpr uint32_t tile_col(int set, int tile) {
   return DEFER_EPILOGUE ? 256u * (uint32_t)(set & 1) + (tile < 3 ? 64u * tile : 192u + 32u * (tile - 3)) : 64u * tile;
 }
-constexpr int NTHREADS = 544;                // warps 0-7: staging + conv1, warps 8-15: conv2 + heads, warp 16: conv3 MMA issue
+constexpr int NB_WARPS = 8;                  // group B (conv2 + heads) warps; 12 was measured no faster (11.46 vs 11.35 ms per 450 frames)
+constexpr int NB_THREADS = 32 * NB_WARPS;
+constexpr int ISSUE_WARP = 8 + NB_WARPS;
+constexpr int NTHREADS = 32 * (ISSUE_WARP + 1);   // warps 0-7: staging + conv1, warps 8..8+NB-1: conv2 + heads, last warp: conv3 MMA issue
+static_assert(NB_WARPS % 4 == 0, "group B covers the four TMEM lane groups evenly");
 constexpr int INH = 2 * TOY + 10, INW = 2 * TOX + 10;   // 42 x 74 input tile
 constexpr int INP = 76;
 
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t mma_bar[2 * C3TILES];   // [accumulator set][conv3 M tile]: tcgen05.commit arrives
   __shared__ __align__(8) uint64_t p1_full[2], p1_empty[2];
-  __shared__ __align__(8) uint64_t c2_full;            // conv2 output of the current tile is complete (256 arrivals)
+  __shared__ __align__(8) uint64_t c2_full;            // conv2 output of the current tile is complete (NB_THREADS arrivals)
   __shared__ uint32_t tmem_slot;
   float* w_s = smem;
   float* in_base = smem + WTOTAL;                                             // [2][SM_IN] fp32 input tiles
@@ -213,9 +217,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&p1_full[i])), "r"(256u) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&p1_empty[i])), "r"(256u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&p1_empty[i])), "r"((uint32_t)NB_THREADS) : "memory");
       }
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&c2_full)), "r"(256u) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&c2_full)), "r"((uint32_t)NB_THREADS) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
       tc1 += clock64() - tmark;
 #endif
     }
-  } else if (warp_u == 16) {
+  } else if (warp_u == ISSUE_WARP) {
     // =================================================================== conv3 MMA issue (one elected thread)
     // kept off the compute warps: the issuing thread is held back by the MMA queue for as long as the MMAs run
     int k = 0;
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
       const Level& Lv = p.lv[tr.lvl];
       const int b = tr.b, lvl = tr.lvl, oy0 = tr.oy0, ox0 = tr.ox0;
       const int lg = warp & 3;                        // TMEM lane group this warp may read
-      for (int tile = warp >> 2; tile < C3TILES; tile += 2) {
+      for (int tile = warp >> 2; tile < C3TILES; tile += NB_WARPS / 4) {
 #ifdef PNET_TIMING
         const long long tq = clock64();
 #endif
@@ -527,12 +531,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
     const float inv = w_s[SC + 0];
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-      // tiles warp + 8 i, i = 3 pass .. 3 pass + 2 (tile 40 exists for warp 0 only)
-      const int mt0 = warp + 24 * pass;
-      const int nq = min(3, (C2TILES - mt0 + 7) / 8);      // live M tiles of this warp in this pass (warp uniform)
+      // tiles warp + NB_WARPS * i, i = 3 pass .. 3 pass + 2
+      const int mt0 = warp + 3 * NB_WARPS * pass;
+      const int nq = max(0, min(3, (C2TILES - mt0 + NB_WARPS - 1) / NB_WARPS));      // live M tiles of this warp in this pass (warp uniform)
+      if (nq == 0) break;
       int base[3];
 #pragma unroll
-      for (int q = 0; q < 3; ++q) base[q] = min(mt0 + 8 * q, C2TILES - 1) * 16 + g;
+      for (int q = 0; q < 3; ++q) base[q] = min(mt0 + NB_WARPS * q, C2TILES - 1) * 16 + g;
       float acc[3][2][4];
 #pragma unroll
       for (int q = 0; q < 3; ++q)
@@ -548,6 +553,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
         uint32_t ah[3][4], al[3][4];
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
+          if (q >= nq) continue;               // warp uniform
           ah[q][0] = p1h[base[q] + o0];        al[q][0] = p1l[base[q] + o0];
           ah[q][1] = p1h[base[q] + 8 + o0];    al[q][1] = p1l[base[q] + 8 + o0];
           ah[q][2] = p1h[base[q] + o1];        al[q][2] = p1l[base[q] + o1];
@@ -581,7 +587,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
       const float al0 = w_s[A2 + 2 * t], al1 = w_s[A2 + 2 * t + 1], al2 = w_s[A2 + 8 + 2 * t], al3 = w_s[A2 + 9 + 2 * t];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        const int mt = mt0 + 8 * q;
+        const int mt = mt0 + NB_WARPS * q;
         if (mt >= C2TILES) break;                 // warp uniform
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
