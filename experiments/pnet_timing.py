@@ -32,6 +32,7 @@ if __name__ == "__main__":
     _lib.LIB_PATH = OUT
     lib = _lib.load()
     lib.trl_debug_pnet_timing.argtypes = [C.POINTER(C.c_ulonglong)]
+    lib.trl_debug_onet_timing.argtypes = [C.POINTER(C.c_ulonglong)]
     clip = SyntheticClip(720, 1280, 30, 1800, n_faces=(1, 1), seed=0)
     frames = np.stack([clip.frame(i) for i in clip.processed_indices()[:90]])
     an = model.Analyzer(device=0)
@@ -43,3 +44,8 @@ if __name__ == "__main__":
         n = max(buf[5], 1)
         print(f"iter {it}: {buf[5]} tiles; cycles per tile: group A wait {buf[0] / n:.0f}, conv1 {buf[1] / n:.0f} | "
               f"group B wait {buf[2] / n:.0f}, conv2 {buf[3] / n:.0f}, conv3+heads {buf[4] / n:.0f} (of which waiting for MMA commits {buf[6] / n:.0f})")
+        ob = (C.c_ulonglong * 8)()
+        lib.trl_debug_onet_timing(ob)
+        nc = max(ob[7], 1)
+        onames = ["load", "conv1+pool", "conv2+pool", "conv3+pool", "conv4", "dense5", "heads"]
+        print(f"        O-Net: {ob[7]} candidates; cycles per candidate: " + ", ".join(f"{onames[i]} {ob[i] / nc:.0f}" for i in range(7)))

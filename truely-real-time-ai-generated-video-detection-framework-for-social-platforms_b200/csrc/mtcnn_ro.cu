@@ -14,59 +14,103 @@ namespace ro {
 __device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : v * a; }
 
 // conv (valid, stride 1) + bias + PReLU for conv output rows [r0, r1): in [CIN][HIN][WIN] (smem) ->
-// out [COUT][r1-r0][WOUT] (smem).  w: global [CIN*K*K][COUT].  item = 4 channels x 4 pixels of one row.
-template <int CIN, int COUT, int K, int HIN, int WIN>
+// out [COUT][r1-r0][WOUT] (smem).  w: global [CIN*K*K][COUT].  item = 4 channels x 4 pixels of one row; a thread owns
+// up to MAXI items.  The weights are staged through shared memory in slabs of CC input channels (cp.async, double
+// buffered in wbuf): one coalesced L2 read per slab for the whole CTA instead of a dependent global load in front of
+// every 16 FMAs of every thread (that chain, not the FMA pipe, set the single-candidate latency).
+// The accumulation order over (ci, ky, kx) is unchanged.
+template <int CIN, int COUT, int K, int HIN, int WIN, int CC, int MAXI>
 __device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* __restrict__ out, int r0, int r1,
                                           const float* __restrict__ w, const float* __restrict__ bias,
-                                          const float* __restrict__ alpha) {
+                                          const float* __restrict__ alpha, float* __restrict__ wbuf) {
   constexpr int WOUT = WIN - K + 1;
   constexpr int PXG = (WOUT + 3) / 4;
   constexpr int CG = COUT / 4;
-  static_assert(COUT % 4 == 0, "COUT");
+  constexpr int SLAB = CC * K * K * COUT;          // floats per slab
+  constexpr int NCH = CIN / CC;
+  static_assert(COUT % 4 == 0 && CIN % CC == 0 && SLAB % 4 == 0, "conv_rows tiling");
   const int rows = r1 - r0;
   const int items = CG * rows * PXG;
-  for (int item = threadIdx.x; item < items; item += blockDim.x) {
-    const int cg = item / (rows * PXG);
-    const int rem = item - cg * (rows * PXG);
-    const int row = rem / PXG, pg = rem - row * PXG;
-    const int x0 = pg * 4;
-    // packed fp32 pairs (FFMA2, common.cuh): two output channels per issued instruction, IEEE fma per element
-    unsigned long long acc2[4][2];
+  const uint32_t wb_s = (uint32_t)__cvta_generic_to_shared(wbuf);
+  auto stage = [&](int ch) {
+    const float* src = w + (size_t)ch * SLAB;
+    const uint32_t dst = wb_s + (uint32_t)(ch & 1) * SLAB * 4u;
+    for (int i = threadIdx.x; i < SLAB / 4; i += blockDim.x)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 4 * i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int base = 0; base < items; base += MAXI * (int)blockDim.x) {
+    int cg[MAXI], row[MAXI], x0[MAXI];
+    bool live[MAXI];
+    unsigned long long acc2[MAXI][4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc2[i][0] = acc2[i][1] = 0ull;
-    for (int ci = 0; ci < CIN; ++ci) {
+    for (int i = 0; i < MAXI; ++i) {
+      const int item = base + (int)threadIdx.x + i * (int)blockDim.x;
+      live[i] = item < items;
+      const int it = live[i] ? item : 0;
+      cg[i] = it / (rows * PXG);
+      const int rem = it - cg[i] * (rows * PXG);
+      row[i] = rem / PXG;
+      x0[i] = (rem - row[i] * PXG) * 4;
 #pragma unroll
-      for (int ky = 0; ky < K; ++ky) {
-        const float* ir = in + (ci * HIN + r0 + row + ky) * WIN + x0;
-        float v[4 + K - 1];
+      for (int px = 0; px < 4; ++px) acc2[i][px][0] = acc2[i][px][1] = 0ull;
+    }
+    stage(0);
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (ch + 1 < NCH) {
+        stage(ch + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();                                   // slab ch is visible to every thread
+      const float* ws = wbuf + (ch & 1) * SLAB;
 #pragma unroll
-        for (int t = 0; t < 4 + K - 1; ++t) v[t] = (x0 + t < WIN) ? ir[t] : 0.f;
+      for (int i = 0; i < MAXI; ++i) {
+        if (!live[i]) continue;
+#pragma unroll 2
+        for (int cl = 0; cl < CC; ++cl) {
+          const int ci = ch * CC + cl;
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(w + ((ci * K + ky) * K + kx) * COUT + cg * 4));
-          const unsigned long long w01 = pack_f32x2(wv.x, wv.y), w23 = pack_f32x2(wv.z, wv.w);
+          for (int ky = 0; ky < K; ++ky) {
+            const float* ir = in + (ci * HIN + r0 + row[i] + ky) * WIN + x0[i];
+            float v[4 + K - 1];
 #pragma unroll
-          for (int px = 0; px < 4; ++px) {
-            const unsigned long long vv = pack_f32x2(v[px + kx], v[px + kx]);
-            ffma2(acc2[px][0], vv, w01);
-            ffma2(acc2[px][1], vv, w23);
+            for (int t = 0; t < 4 + K - 1; ++t) v[t] = (x0[i] + t < WIN) ? ir[t] : 0.f;
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+              const float4 wv = *reinterpret_cast<const float4*>(ws + ((cl * K + ky) * K + kx) * COUT + cg[i] * 4);
+              const unsigned long long w01 = pack_f32x2(wv.x, wv.y), w23 = pack_f32x2(wv.z, wv.w);
+#pragma unroll
+              for (int px = 0; px < 4; ++px) {
+                const unsigned long long vv = pack_f32x2(v[px + kx], v[px + kx]);
+                ffma2(acc2[i][px][0], vv, w01);
+                ffma2(acc2[i][px][1], vv, w23);
+              }
+            }
           }
         }
       }
-    }
-    float acc[4][4];
-#pragma unroll
-    for (int px = 0; px < 4; ++px) {
-      unpack_f32x2(acc2[px][0], acc[px][0], acc[px][1]);
-      unpack_f32x2(acc2[px][1], acc[px][2], acc[px][3]);
+      __syncthreads();                                   // slab buffer ch & 1 may be overwritten by stage(ch + 2)
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = cg * 4 + j;
-      const float b = __ldg(bias + co), a = __ldg(alpha + co);
+    for (int i = 0; i < MAXI; ++i) {
+      if (!live[i]) continue;
+      float acc[4][4];
 #pragma unroll
-      for (int px = 0; px < 4; ++px)
-        if (x0 + px < WOUT) out[(co * rows + row) * WOUT + x0 + px] = prelu(acc[px][j] + b, a);
+      for (int px = 0; px < 4; ++px) {
+        unpack_f32x2(acc2[i][px][0], acc[px][0], acc[px][1]);
+        unpack_f32x2(acc2[i][px][1], acc[px][2], acc[px][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int co = cg[i] * 4 + j;
+        const float b = __ldg(bias + co), a = __ldg(alpha + co);
+#pragma unroll
+        for (int px = 0; px < 4; ++px)
+          if (x0[i] + px < WOUT) out[(co * rows + row[i]) * WOUT + x0[i] + px] = prelu(acc[px][j] + b, a);
+      }
     }
   }
 }
@@ -97,15 +141,15 @@ __device__ __forceinline__ void pool_rows(const float* __restrict__ band, int ba
 }
 
 // conv + PReLU + ceil-mode maxpool, banded over PR pooled rows at a time
-template <int CIN, int COUT, int K, int HIN, int WIN, int PK, int PS, int PR>
+template <int CIN, int COUT, int K, int HIN, int WIN, int PK, int PS, int PR, int CC, int MAXI>
 __device__ __forceinline__ void conv_pool(const float* in, float* band, float* out, const float* w, const float* b,
-                                          const float* a) {
+                                          const float* a, float* wbuf) {
   constexpr int HC = HIN - K + 1, WC = WIN - K + 1;
   constexpr int HP = (HC - PK + PS - 1) / PS + 1, WP = (WC - PK + PS - 1) / PS + 1;
   for (int p0 = 0; p0 < HP; p0 += PR) {
     const int p1 = min(p0 + PR, HP);
     const int r0 = p0 * PS, r1 = min((p1 - 1) * PS + PK, HC);
-    conv_rows<CIN, COUT, K, HIN, WIN>(in, band, r0, r1, w, b, a);
+    conv_rows<CIN, COUT, K, HIN, WIN, CC, MAXI>(in, band, r0, r1, w, b, a, wbuf);
     __syncthreads();
     pool_rows<COUT, HC, WC, PK, PS, HP, WP>(band, r0, r1 - r0, out, p0, p1);
     __syncthreads();
@@ -120,13 +164,19 @@ __device__ __forceinline__ void dense(const float* __restrict__ in_s, float* __r
   const int o = threadIdx.x % OUT, ks = threadIdx.x / OUT;
   if (ks < ks_n) {
     const int k0 = (IN * ks) / ks_n, k1 = (IN * (ks + 1)) / ks_n;
-    float acc0 = 0.f, acc1 = 0.f;
+    // 8 independent loads in flight per thread (the weight stream from L2 is the cost of this layer); the partial sums
+    // are combined in a fixed order
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int k = k0;
-    for (; k + 1 < k1; k += 2) {
-      acc0 = fmaf(in_s[k], __ldg(w + (size_t)k * OUT + o), acc0);
-      acc1 = fmaf(in_s[k + 1], __ldg(w + (size_t)(k + 1) * OUT + o), acc1);
+    for (; k + 7 < k1; k += 8) {
+      float wv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = __ldg(w + (size_t)(k + j) * OUT + o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(in_s[k + j], wv[j], acc[j]);
     }
-    if (k < k1) acc0 = fmaf(in_s[k], __ldg(w + (size_t)k * OUT + o), acc0);
+    for (; k < k1; ++k) acc[0] = fmaf(in_s[k], __ldg(w + (size_t)k * OUT + o), acc[0]);
+    const float acc0 = (acc[0] + acc[1]) + (acc[2] + acc[3]), acc1 = (acc[4] + acc[5]) + (acc[6] + acc[7]);
     part_s[ks * OUT + o] = acc0 + acc1;
   }
   __syncthreads();
@@ -188,7 +238,8 @@ constexpr int S_C3 = S_P2 + 768;           // 64*3*3 = 576
 constexpr int S_D4 = S_C3 + 576;           // 128
 constexpr int S_PART = S_D4 + 128;         // 256
 constexpr int S_H = S_PART + 256;          // 8
-constexpr int S_TOTAL = S_H + 8;
+constexpr int S_WB = S_H + 8;              // weight slabs: 2 x max(27*28, 7*9*48, 8*4*64) = 2 x 3024
+constexpr int S_TOTAL = S_WB + 2 * 3024;
 }  // namespace r
 
 // work distribution shared by both kernels: compact (grid-stride over live slots) when the per-frame counts fit the
@@ -218,9 +269,9 @@ __global__ void __launch_bounds__(256) rnet_kernel(const float* __restrict__ in,
   for (int i = threadIdx.x; i < 1728 / 4; i += blockDim.x)
     reinterpret_cast<float4*>(sm + S_IN)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
   __syncthreads();
-  conv_pool<3, 28, 3, 24, 24, 3, 2, 4>(sm + S_IN, sm + S_BAND, sm + S_P1, wp + W1, wp + B1, wp + A1);    // -> 28x11x11
-  conv_pool<28, 48, 3, 11, 11, 3, 2, 4>(sm + S_P1, sm + S_BAND, sm + S_P2, wp + W2, wp + B2, wp + A2);   // -> 48x4x4
-  conv_rows<48, 64, 2, 4, 4>(sm + S_P2, sm + S_C3, 0, 3, wp + W3, wp + B3, wp + A3);                    // -> 64x3x3
+  conv_pool<3, 28, 3, 24, 24, 3, 2, 4, 3, 2>(sm + S_IN, sm + S_BAND, sm + S_P1, wp + W1, wp + B1, wp + A1, sm + S_WB);    // -> 28x11x11
+  conv_pool<28, 48, 3, 11, 11, 3, 2, 4, 7, 2>(sm + S_P1, sm + S_BAND, sm + S_P2, wp + W2, wp + B2, wp + A2, sm + S_WB);   // -> 48x4x4
+  conv_rows<48, 64, 2, 4, 4, 8, 1>(sm + S_P2, sm + S_C3, 0, 3, wp + W3, wp + B3, wp + A3, sm + S_WB);                    // -> 64x3x3
   __syncthreads();
   dense<576, 128, true>(sm + S_C3, sm + S_D4, sm + S_PART, wp + W4, wp + B4, wp + A4);
   heads<128>(sm + S_D4, wp + WH, wp + BH, sm + S_H);
@@ -228,6 +279,13 @@ __global__ void __launch_bounds__(256) rnet_kernel(const float* __restrict__ in,
   __syncthreads();
   }
 }
+
+#ifdef PNET_TIMING
+__device__ unsigned long long g_onet_phase[8];
+#define OT_MARK(i) do { __syncthreads(); if (threadIdx.x == 0) { const long long _t = clock64(); atomicAdd(&g_onet_phase[i], (unsigned long long)(_t - t_prev)); t_prev = _t; } } while (0)
+#else
+#define OT_MARK(i) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------- O-Net
 // packed: w1[27][32] | w2[288][64] | w3[576][64] | w4[256][128] | w5[1152][256] | wh[6][256] bh[6]  (+ b/a each)
@@ -248,7 +306,8 @@ constexpr int S_C4 = S_P3 + 1024;           // 128*3*3 = 1152
 constexpr int S_D5 = S_C4 + 1152;           // 256
 constexpr int S_PART = S_D5 + 256;          // 512
 constexpr int S_H = S_PART + 512;
-constexpr int S_TOTAL = S_H + 8;
+constexpr int S_WB = S_H + 8;               // weight slabs: 2 x max(27*32, 8*9*64, 8*4*128) = 2 x 4608
+constexpr int S_TOTAL = S_WB + 2 * 4608;
 }  // namespace o
 
 __global__ void __launch_bounds__(512) onet_kernel(const float* __restrict__ in, const float* __restrict__ wp,
@@ -261,24 +320,44 @@ __global__ void __launch_bounds__(512) onet_kernel(const float* __restrict__ in,
   for (int work = blockIdx.x; work < wl.total; work += gridDim.x) {
   const int slot = wl.compact ? slotmap_slot(s_pref, n_frames, per_frame_cap, work) : work;
   if (!wl.compact && !slot_live(slot, d_count, per_frame_cap)) continue;      // CTA uniform
+#ifdef PNET_TIMING
+  long long t_prev = clock64();
+#endif
   const float* src = in + (size_t)slot * 6912;
   for (int i = threadIdx.x; i < 6912 / 4; i += blockDim.x)
     reinterpret_cast<float4*>(sm + S_IN)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
   __syncthreads();
-  conv_pool<3, 32, 3, 48, 48, 3, 2, 4>(sm + S_IN, sm + S_BAND, sm + S_P1, wp + W1, wp + B1, wp + A1);     // -> 32x23x23
+  OT_MARK(0);
+  conv_pool<3, 32, 3, 48, 48, 3, 2, 4, 3, 2>(sm + S_IN, sm + S_BAND, sm + S_P1, wp + W1, wp + B1, wp + A1, sm + S_WB);     // -> 32x23x23
+  OT_MARK(1);
   float* p2 = sm + S_IN;                                                                                  // input is dead
-  conv_pool<32, 64, 3, 23, 23, 3, 2, 5>(sm + S_P1, sm + S_BAND, p2, wp + W2, wp + B2, wp + A2);           // -> 64x10x10
-  conv_pool<64, 64, 3, 10, 10, 2, 2, 4>(p2, sm + S_BAND, sm + S_P3, wp + W3, wp + B3, wp + A3);           // -> 64x4x4
-  conv_rows<64, 128, 2, 4, 4>(sm + S_P3, sm + S_C4, 0, 3, wp + W4, wp + B4, wp + A4);                     // -> 128x3x3
+  conv_pool<32, 64, 3, 23, 23, 3, 2, 5, 8, 3>(sm + S_P1, sm + S_BAND, p2, wp + W2, wp + B2, wp + A2, sm + S_WB);           // -> 64x10x10
+  OT_MARK(2);
+  conv_pool<64, 64, 3, 10, 10, 2, 2, 4, 8, 1>(p2, sm + S_BAND, sm + S_P3, wp + W3, wp + B3, wp + A3, sm + S_WB);           // -> 64x4x4
+  OT_MARK(3);
+  conv_rows<64, 128, 2, 4, 4, 8, 1>(sm + S_P3, sm + S_C4, 0, 3, wp + W4, wp + B4, wp + A4, sm + S_WB);                     // -> 128x3x3
   __syncthreads();
+  OT_MARK(4);
   dense<1152, 256, true>(sm + S_C4, sm + S_D5, sm + S_PART, wp + W5, wp + B5, wp + A5);
+  OT_MARK(5);
   heads<256>(sm + S_D5, wp + WH, wp + BH, sm + S_H);
   write_outputs(sm + S_H, slot, prob, reg);
+  OT_MARK(6);
+#ifdef PNET_TIMING
+  if (threadIdx.x == 0) atomicAdd(&g_onet_phase[7], 1ull);
+#endif
   __syncthreads();
   }
 }
 
 }  // namespace ro
+#ifdef PNET_TIMING
+extern "C" void trl_debug_onet_timing(unsigned long long* out) {
+  cudaMemcpyFromSymbol(out, ro::g_onet_phase, sizeof(unsigned long long) * 8);
+  unsigned long long z[8] = {0};
+  cudaMemcpyToSymbol(ro::g_onet_phase, z, sizeof(z));
+}
+#endif
 
 // ---------------------------------------------------------------- host: weight packing + launch
 
