@@ -313,13 +313,17 @@ int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, con
 __global__ void __launch_bounds__(256) crop_resample_kernel(const uint8_t* __restrict__ frames, int H, int W,
                                                            const int* __restrict__ pad4, const int* __restrict__ img,
                                                            const int* __restrict__ d_count, int per_frame_cap,
-                                                           int n_frames, int n_slots, int S, float* __restrict__ out) {
+                                                           int n_frames, int n_slots, int split, int S,
+                                                           float* __restrict__ out) {
   // per-frame lists: grid-stride over the compacted live slots (common.cuh slot map); flat lists: one CTA per slot
   __shared__ int s_pref[SLOTMAP_MAX_FRAMES + 1];
   const bool compact = per_frame_cap > 0 && n_frames > 0 && n_frames <= SLOTMAP_MAX_FRAMES;
-  const int total_work = compact ? slotmap_init(d_count, n_frames, per_frame_cap, s_pref) : n_slots;
+  // a candidate is split over `split` CTAs (interleaved pixel iterations): with a few hundred candidates per launch the
+  // stage time is the latency of one candidate, not throughput
+  const int total_work = (compact ? slotmap_init(d_count, n_frames, per_frame_cap, s_pref) : n_slots) * split;
   for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-  const int slot = compact ? slotmap_slot(s_pref, n_frames, per_frame_cap, work) : work;
+  const int part = work % split;
+  const int slot = compact ? slotmap_slot(s_pref, n_frames, per_frame_cap, work / split) : work / split;
   int b, n_live;
   if (per_frame_cap > 0) {          // slot = frame * cap + i, counts per frame
     b = slot / per_frame_cap;
@@ -333,7 +337,8 @@ __global__ void __launch_bounds__(256) crop_resample_kernel(const uint8_t* __res
   float* o = out + (size_t)slot * 3 * S * S;
   const int ch = ey - (y - 1), cw = ex - (x - 1);
   if (ch <= 0 || cw <= 0) {   // degenerate: upstream skips such crops (detect_face.py stage 2/3 loop guard)
-    for (int i = threadIdx.x; i < 3 * S * S; i += blockDim.x) o[i] = 0.f;
+    if (part == 0)
+      for (int i = threadIdx.x; i < 3 * S * S; i += blockDim.x) o[i] = 0.f;
     continue;
   }
   const uint8_t* frame = frames + (size_t)b * H * W * 3;
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(256) crop_resample_kernel(const uint8_t* __res
   const int per_iter = blockDim.x / grp;
   const int total = S * S;
   const int iters = (total + per_iter - 1) / per_iter;
-  for (int it = 0; it < iters; ++it) {
+  for (int it = part; it < iters; it += split) {
     const int pix = it * per_iter + (int)threadIdx.x / grp;
     const bool valid = pix < total;
     int s0 = 0, s1 = 0, s2 = 0, kh = 1, kw = 1;
@@ -378,8 +383,10 @@ int launch_crop_resample_ex(trl_ctx* c, const uint8_t* d_frames, int B, int H, i
   if (n_slots <= 0) return TRL_OK;
   const int n_frames = per_frame_cap > 0 ? n_slots / per_frame_cap : 0;
   const bool compact = per_frame_cap > 0 && n_frames <= SLOTMAP_MAX_FRAMES;
-  const int grid = compact ? (n_slots < TRL_NUM_SMS * 8 ? n_slots : TRL_NUM_SMS * 8) : n_slots;
-  crop_resample_kernel<<<grid, 256, 0, s>>>(d_frames, H, W, d_pad, d_img, d_count, per_frame_cap, n_frames, n_slots, size, d_out);
+  const int split = compact ? (size == 24 ? 4 : 8) : 1;
+  const long long slots = (long long)n_slots * split;
+  const int grid = compact ? (int)(slots < TRL_NUM_SMS * 8 ? slots : TRL_NUM_SMS * 8) : n_slots;
+  crop_resample_kernel<<<grid, 256, 0, s>>>(d_frames, H, W, d_pad, d_img, d_count, per_frame_cap, n_frames, n_slots, split, size, d_out);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
