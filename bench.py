@@ -293,7 +293,8 @@ def main():
                 d["achieved_tflops_bf16"] = flops_facenet * n_local / (ms * 1e-3) / 1e12
         stages[name] = d
     dom = max(per_step, key=per_step.get)
-    dom_ms_launch = per_step[dom] / max(1, calls // args.steps)      # average duration of one launch (one chunk)
+    n_chunks = len(M.chunk_schedule(n_local, args.chunk))
+    dom_ms_launch = per_step[dom] / max(1, n_chunks)                  # average duration of one launch of the stage (one chunk)
     frames_per_launch = min(args.chunk, n_local)
     if dom == "facenet":
         ach = flops_facenet * n_local / (per_step[dom] * 1e-3) / 1e12
