@@ -262,16 +262,17 @@ class Analyzer:
 def chunk_schedule(n: int, chunk: int, ramp: bool = False):
     """[(start, end)] ranges of at most ``chunk`` frames.  With ``ramp`` (host frames: the H2D copy of chunk k+1 overlaps
     the cascade on chunk k) the chunks grow at the start and shrink towards the end: the copy of the first chunk and the
-    cascade of the last one are the parts of the pipeline that nothing overlaps.  A cascade launch has a fixed cost
-    (about 0.8 ms on B200, experiments/e2e_timeline.py), so a chunk keeps up with the copy of its successor only if the
-    successor is at least ~0.65 of its size + 16 frames: the tail shrinks by that rule and stops at half a chunk."""
+    cascade of the last one are the parts of the pipeline that nothing overlaps.  A cascade costs about
+    0.47 ms + 0.0325 ms/frame and a copy 0.05 ms/frame (720p, B200, experiments/e2e_timeline.py), so a chunk keeps up
+    with the copy of its successor only if the successor is at least ~0.65 of its size + 10 frames: the tail shrinks by
+    that rule (at most five steps, not below a third of a chunk)."""
     if not ramp or n <= chunk:
         return [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
     head = [max(1, chunk // 4), max(1, chunk // 2)]
     tail, t = [], chunk
     while True:
-        t = int(0.65 * t + 16)
-        if t >= chunk or t < chunk // 2 or (tail and t >= tail[-1]) or len(tail) == 3:
+        t = int(0.65 * t + 10)
+        if t >= chunk or t < chunk // 3 or (tail and t >= tail[-1]) or len(tail) == 5:
             break
         tail.append(t)
     if sum(head) + sum(tail) + chunk > n:
