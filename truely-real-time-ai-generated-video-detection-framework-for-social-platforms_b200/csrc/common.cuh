@@ -71,6 +71,9 @@ __device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long 
 }
 #endif
 
+int tma_encode_tiled_f32(trl_ctx* c, void* map, const void* base, int rank, const unsigned long long* dims,
+                         const unsigned long long* strides_bytes, const unsigned* box);   // facenet_umma.cu
+
 // ----------------------------------------------------------------------------- compact work lists
 // The cascade keeps per-frame candidate lists at fixed strides (slot = frame * cap + i, count[frame] live entries).
 // Kernels that do one CTA of work per live slot run as grid-stride loops over the *compacted* index space instead of

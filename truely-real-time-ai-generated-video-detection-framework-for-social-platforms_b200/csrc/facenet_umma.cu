@@ -348,6 +348,23 @@ int umma_init(trl_ctx* c) {
   return TRL_OK;
 }
 
+// fp32 tiled tensor map for other kernels of the library (P-Net input staging); `map` = CUtensorMap storage (128 B, 64-byte
+// aligned); zero fill out of bounds, no swizzle, no interleave
+int tma_encode_tiled_f32(trl_ctx* c, void* map, const void* base, int rank, const unsigned long long* dims,
+                         const unsigned long long* strides_bytes, const unsigned* box) {
+  int rc = umma_init(c);
+  if (rc != TRL_OK) return rc;
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d,
+                        st, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) TRL_FAIL(c, TRL_E_CUDA, "cuTensorMapEncodeTiled(f32) failed with %d", (int)r);
+  return TRL_OK;
+}
+
 // Choose the 128-row tile shape (box_w, box_h, box_n) that minimises the number of tiles for a nominal batch.
 static void choose_box(const ConvOp& op, int* bw, int* bh, int* bn) {
   const int NB = 240;   // nominal batch

@@ -19,6 +19,8 @@
 // re-reading the A tile from shared memory (~73 cycles per M128 x N32 x K8 step, experiments/umma_probe.cu).
 // The two CTAs of an SM overlap one CTA's FMA-pipe stage with the other's tensor-pipe stages.
 // FLOP roof, not HBM, binds this kernel.
+#include <cuda.h>
+
 #include "common.cuh"
 #include <cuda_fp16.h>
 #include <math.h>
@@ -73,10 +75,12 @@ constexpr int SC = W3 + 9 * 2 * 64 * 4;   // [4]: 1 / (SA * S_w2)
 constexpr int WTOTAL = SC + 4;
 static_assert(WTOTAL % 4 == 0 && W2 % 4 == 0 && W3 % 4 == 0, "16-byte alignment of the operand arrays");
 
-constexpr int SM_IN = 3 * INH * INP;                 // 9576 words
+constexpr int SM_IN = ((3 * INH * INP + 31) / 32) * 32;      // 9576 words, padded to 128 bytes (TMA destination alignment)
+constexpr int IN_BYTES = 3 * INH * INP * 4;                  // bytes one TMA box delivers
+constexpr int IN_OFF = ((WTOTAL + 31) / 32) * 32;            // input tiles start 128-byte aligned behind the weights
 constexpr int SM_C2 = 4 * C2PLANE;                   // 11520 words
 constexpr int SM_P1 = 2 * P1WORDS * P1PL;            // 7440 words
-constexpr int SMEM_WORDS = WTOTAL + 2 * SM_IN + 2 * SM_P1 + SM_C2;    // weights, 2 input tiles, 2 pooled conv1 tiles, conv2 planes
+constexpr int SMEM_WORDS = IN_OFF + 2 * SM_IN + 2 * SM_P1 + SM_C2;    // weights, 2 input tiles, 2 pooled conv1 tiles, conv2 planes
 constexpr int SMEM_BYTES = SMEM_WORDS * 4;           // ~206 KB -> one persistent CTA per SM
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -92,6 +96,8 @@ struct Level {
 };
 
 struct Params {
+  CUtensorMap tmap[TRL_MAX_SCALES];   // per level: fp32 {ws, hs, 3 B} view of the pyramid, box {76, 42, 3}, zero fill out of bounds
+  int use_tma;         // 1: every level has a tensor map (16-byte aligned rows); 0: cp.async staging
   int n_levels;
   int blocks;          // tiles per frame (all levels)
   int n_frames;
@@ -191,10 +197,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t mma_bar[2 * C3TILES];   // [accumulator set][conv3 M tile]: tcgen05.commit arrives
   __shared__ __align__(8) uint64_t p1_full[2], p1_empty[2];
+  __shared__ __align__(8) uint64_t in_full[2];         // input tile landed (TMA complete_tx)
   __shared__ __align__(8) uint64_t c2_full;            // conv2 output of the current tile is complete (NB_THREADS arrivals)
   __shared__ uint32_t tmem_slot;
   float* w_s = smem;
-  float* in_base = smem + WTOTAL;                                             // [2][SM_IN] fp32 input tiles
+  float* in_base = smem + IN_OFF;                                             // [2][SM_IN] fp32 input tiles
   uint32_t* p1_base = reinterpret_cast<uint32_t*>(in_base + 2 * SM_IN);       // [2][hi, lo][5 pairs][P1PL]
   uint32_t* c2_s = p1_base + 2 * SM_P1;                                       // [hi k0, hi k1, lo k0, lo k1][C2NP][4]
   const uint32_t* wu = reinterpret_cast<const uint32_t*>(w_s);
@@ -220,6 +227,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&p1_empty[i])), "r"((uint32_t)NB_THREADS) : "memory");
       }
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&c2_full)), "r"((uint32_t)NB_THREADS) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&in_full[0])), "r"(1u) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&in_full[1])), "r"(1u) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -247,6 +256,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
     // are zero filled (src-size 0)
     auto issue_load = [&](int id, int buf) {
       const TileRef tr = decode_tile(p, id);
+      if (p.use_tma) {
+        // one elected thread: a single 3-D TMA box {76 columns, 42 rows, 3 channel planes}; rows / columns beyond the
+        // level are zero filled by the TMA unit
+        if (tid == 0) {
+          const uint32_t bar = smem_u32(&in_full[buf]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)IN_BYTES) : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                       ::"r"(smem_u32(in_base + buf * SM_IN)), "l"(reinterpret_cast<uint64_t>(&p.tmap[tr.lvl])), "r"(bar),
+                         "r"(2 * tr.ox0), "r"(2 * tr.oy0), "r"(3 * tr.b) : "memory");
+        }
+        return;
+      }
       const Level& Lv = p.lv[tr.lvl];
       const int hs = Lv.hs, ws = Lv.ws, pitch = Lv.pitch;
       const float* src = Lv.in + (size_t)tr.b * 3 * hs * pitch;
@@ -284,7 +305,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
 #ifdef PNET_TIMING
       tmark = clock64();
 #endif
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (p.use_tma) mbar_wait(&in_full[k & 1], (k >> 1) & 1);
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");      // tile k landed for all of A; all of A is done reading tile k-1
       if (id + (int)gridDim.x < total) issue_load(id + gridDim.x, (k + 1) & 1);
       if (k >= 2) mbar_wait(&p1_empty[k & 1], ((k >> 1) - 1) & 1);      // group B is done with tile k-2's p1
@@ -811,6 +833,15 @@ int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float
   p.blk_start[0] = 0; p.blk_start[1] = L.tiles;
   p.blocks = L.tiles; p.n_frames = B;
   fill_head(c, &p);
+  // stage entry point: arbitrary row pitch -- TMA staging when the rows are 16-byte aligned, else cp.async
+  p.use_tma = ((ws & 3) == 0 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0) ? 1 : 0;
+  if (p.use_tma) {
+    const unsigned long long dims[3] = {(unsigned long long)ws, (unsigned long long)hs, (unsigned long long)3 * B};
+    const unsigned long long strides[2] = {(unsigned long long)ws * 4, (unsigned long long)hs * ws * 4};
+    const unsigned box[3] = {(unsigned)INP, (unsigned)INH, 3u};
+    int rc = tma_encode_tiled_f32(c, &p.tmap[0], d_in, 3, dims, strides, box);
+    if (rc != TRL_OK) return rc;
+  }
   p.thr = 2.f; p.cap = 0; p.capflag = c->d_cap;
   if (B == 0) return TRL_OK;
   pnet_kernel<<<grid_for(L.tiles, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
@@ -839,6 +870,16 @@ int launch_pnet_candidates(trl_ctx* c, const float* d_pyr, int B, const PyramidG
   p.thr = thr; p.cap = cap; p.capflag = c->d_cap;
   p.blocks = blocks; p.n_frames = B;
   fill_head(c, &p);
+  p.use_tma = 1;
+  for (int k = 0; k < g.n && p.use_tma; ++k) {
+    const Level& L = p.lv[k];
+    if ((L.pitch & 3) != 0 || (reinterpret_cast<uintptr_t>(L.in) & 15) != 0) { p.use_tma = 0; break; }
+    const unsigned long long dims[3] = {(unsigned long long)L.ws, (unsigned long long)L.hs, (unsigned long long)3 * B};
+    const unsigned long long strides[2] = {(unsigned long long)L.pitch * 4, (unsigned long long)L.hs * L.pitch * 4};
+    const unsigned box[3] = {(unsigned)INP, (unsigned)INH, 3u};
+    int rc = tma_encode_tiled_f32(c, &p.tmap[k], L.in, 3, dims, strides, box);
+    if (rc != TRL_OK) return rc;
+  }
   if (blocks == 0 || B == 0) return TRL_OK;
   pnet_kernel<<<grid_for(blocks, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
   TRL_LAUNCH_CHECK(c);
