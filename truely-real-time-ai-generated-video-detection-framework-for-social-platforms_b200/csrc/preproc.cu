@@ -96,7 +96,7 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t* __restrict__ frames
   return v;
 }
 
-template <bool ALIGNED>
+template <int MODE>     // 0: byte-aligned rows, 1: 4-byte aligned rows, 2: 16-byte aligned rows (one 128-bit load per thread and row)
 __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restrict__ frames, int H, int W, size_t total_bytes,
                                                          const __grid_constant__ PyrParams p, const int* __restrict__ tab,
                                                          float* __restrict__ out) {
@@ -115,6 +115,32 @@ __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restr
   const size_t fbase = (size_t)b * H * rowbytes;
   const int tid = threadIdx.x;
 
+  constexpr bool ALIGNED = MODE >= 1;
+  if (MODE == 2) {
+    // 16-byte rows: thread owns 4 consecutive words of a row -> one LDG.128 per source row, two STS.128 per output row
+    const int nq = nw >> 2;                                  // uint4 per row
+    for (int c0 = 0; c0 < nq; c0 += 256) {
+      const int q = c0 + tid;
+      if (q >= nq) continue;
+      for (int jj = 0; jj < nrows; ++jj) {
+        const int y0 = __ldg(ty0 + jj), y1 = __ldg(ty1 + jj);
+        uint32_t ae0 = 0, ao0 = 0, ae1 = 0, ao1 = 0, ae2 = 0, ao2 = 0, ae3 = 0, ao3 = 0;
+        const uint4* row = reinterpret_cast<const uint4*>(frames + fbase) + (size_t)y0 * nq + q;
+        for (int y = y0; y < y1; ++y, row += nq) {
+          const uint4 w = __ldg(row);
+          ae0 += w.x & 0x00FF00FFu; ao0 += __byte_perm(w.x, 0, 0x4341);
+          ae1 += w.y & 0x00FF00FFu; ao1 += __byte_perm(w.y, 0, 0x4341);
+          ae2 += w.z & 0x00FF00FFu; ao2 += __byte_perm(w.z, 0, 0x4341);
+          ae3 += w.w & 0x00FF00FFu; ao3 += __byte_perm(w.w, 0, 0x4341);
+        }
+        uint4* vrow = reinterpret_cast<uint4*>(vs) + jj * (nw >> 1) + 2 * q;      // 2 words of sums per source word
+        vrow[0] = make_uint4(__byte_perm(ae0, ao0, 0x5410), __byte_perm(ae0, ao0, 0x7632),
+                             __byte_perm(ae1, ao1, 0x5410), __byte_perm(ae1, ao1, 0x7632));
+        vrow[1] = make_uint4(__byte_perm(ae2, ao2, 0x5410), __byte_perm(ae2, ao2, 0x7632),
+                             __byte_perm(ae3, ao3, 0x5410), __byte_perm(ae3, ao3, 0x7632));
+      }
+    }
+  } else
   for (int c0 = 0; c0 < nw; c0 += 1024) {
     const int q = c0 + tid;
     const bool v0 = q < nw, v1 = q + 256 < nw, v2 = q + 512 < nw, v3 = q + 768 < nw;
@@ -294,13 +320,16 @@ int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, con
   const size_t total = (size_t)B * H * W * 3;
   const bool aligned = (3 * W) % 4 == 0;
   if (smem > c->pyr_smem_set) {
-    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     c->pyr_smem_set = smem;
   }
   dim3 grid(blocks, B);
-  if (aligned) pyramid_sep_kernel<true><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out);
-  else pyramid_sep_kernel<false><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out);
+  const bool rows16 = (3 * W) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 15) == 0;
+  if (rows16) pyramid_sep_kernel<2><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out);
+  else if (aligned) pyramid_sep_kernel<1><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out);
+  else pyramid_sep_kernel<0><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
