@@ -52,10 +52,12 @@ __host__ __device__ constexpr uint32_t tile_col(int set, int tile) {
   return DEFER_EPILOGUE ? 256u * (uint32_t)(set & 1) + (tile < 3 ? 64u * tile : 192u + 32u * (tile - 3)) : 64u * tile;
 }
 constexpr int NB_WARPS = 8;                  // group B (conv2 + heads) warps; 12 was measured no faster (11.46 vs 11.35 ms per 450 frames)
+constexpr int NA_WARPS = 8;                  // group A (staging + conv1) warps; 12 was measured slower (10.84 vs 10.58 ms)
+constexpr int NA_THREADS = 32 * NA_WARPS;
 constexpr int NB_THREADS = 32 * NB_WARPS;
-constexpr int ISSUE_WARP = 8 + NB_WARPS;
-constexpr int NTHREADS = 32 * (ISSUE_WARP + 1);   // warps 0-7: staging + conv1, warps 8..8+NB-1: conv2 + heads, last warp: conv3 MMA issue
-static_assert(NB_WARPS % 4 == 0, "group B covers the four TMEM lane groups evenly");
+constexpr int ISSUE_WARP = NA_WARPS + NB_WARPS;
+constexpr int NTHREADS = 32 * (ISSUE_WARP + 1);   // group A warps: staging + conv1, then group B: conv2 + heads, last warp: conv3 MMA issue
+static_assert(NB_WARPS % 4 == 0 && NA_WARPS % 4 == 0, "group B covers the four TMEM lane groups evenly and starts at a multiple of 4");
 constexpr int INH = 2 * TOY + 10, INW = 2 * TOX + 10;   // 42 x 74 input tile
 constexpr int INP = 76;
 
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mma_bar[i])), "r"(1u) : "memory");
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&p1_full[i])), "r"(256u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&p1_full[i])), "r"((uint32_t)NA_THREADS) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&p1_empty[i])), "r"((uint32_t)NB_THREADS) : "memory");
       }
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&c2_full)), "r"((uint32_t)NB_THREADS) : "memory");
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
   const uint32_t tmem = tmem_slot;
   const int total = p.blocks * p.n_frames;
 
-  if (warp_u < 8) {
+  if (warp_u < NA_WARPS) {
     // =================================================================== group A: input staging + conv1
     // the tile is staged with cp.async (LDGSTS): every copy of a thread is in flight at once; out-of-image elements
     // are zero filled (src-size 0)
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
       if ((pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(Lv.in) & 15) == 0) {
         // 16-byte rows (the cascade's padded pyramid): 19 chunks per tile row, partial chunks zero filled by src-size
         constexpr int CH = INP / 4;
-        for (int i = tid; i < 3 * INH * CH; i += 256) {
+        for (int i = tid; i < 3 * INH * CH; i += NA_THREADS) {
           const int rr = i / CH, j = i - rr * CH;          // rr = ci * INH + r
           const int ci = rr / INH, r = rr - ci * INH;
           const int gy = iy0 + r, gx = ix0 + 4 * j;
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
                        ::"r"(a_dst + 16u * (uint32_t)i), "l"(gp), "r"(nb) : "memory");
         }
       } else {
-        for (int i = tid; i < 3 * INH * INW; i += 256) {
+        for (int i = tid; i < 3 * INH * INW; i += NA_THREADS) {
           const int ci = i / (INH * INW);
           const int r = (i - ci * INH * INW) / INW;
           const int cx = i - ci * INH * INW - r * INW;
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
 #endif
       if (p.use_tma) mbar_wait(&in_full[k & 1], (k >> 1) & 1);
       else asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");      // tile k landed for all of A; all of A is done reading tile k-1
+      asm volatile("bar.sync 1, %0;" ::"n"(NA_THREADS) : "memory");      // tile k landed for all of A; all of A is done reading tile k-1
       if (id + (int)gridDim.x < total) issue_load(id + gridDim.x, (k + 1) & 1);
       if (k >= 2) mbar_wait(&p1_empty[k & 1], ((k >> 1) - 1) & 1);      // group B is done with tile k-2's p1
 #ifdef PNET_TIMING
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
       // scaled fp16 hi / lo channel pairs
       const int c1h = Lv.hs - 2, c1w = Lv.ws - 2;     // valid conv1 extent (ceil-mode pooling clips to it)
 #pragma unroll 1
-      for (int item = tid; item < P1H * P1W; item += 256) {
+      for (int item = tid; item < P1H * P1W; item += NA_THREADS) {
       asm volatile("" ::: "memory");          // keep the weight loads inside the loop (hoisted, they spill)
       const int py = item / P1W, px = item - py * P1W;
       float patch[3][4][4];
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
     }
   } else {
     // =================================================================== group B: conv2, heads
-    const int warp = warp_u - 8;
+    const int warp = warp_u - NA_WARPS;
     // head epilogue of the tile whose conv3 went into accumulator set kk & 1 (thread = pixel: 32 channels -> bias,
     // PReLU, heads, softmax, candidate append; no cross-lane traffic)
     auto conv3_epilogue = [&](const TileRef& tr, int kk) {
@@ -668,7 +670,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
   if (tid == 0) {
     atomicAdd(&g_pnet_phase[0], (unsigned long long)tw); atomicAdd(&g_pnet_phase[1], (unsigned long long)tc1);
   }
-  if (tid == 256) {
+  if (tid == NA_THREADS) {
     atomicAdd(&g_pnet_phase[2], (unsigned long long)tw); atomicAdd(&g_pnet_phase[3], (unsigned long long)tc2);
     atomicAdd(&g_pnet_phase[4], (unsigned long long)tc3);
     atomicAdd(&g_pnet_phase[6], (unsigned long long)tmma);
