@@ -40,6 +40,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;       // fast path: no clock read (the producer / MMA issue loops are latency critical)
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) __trap();
@@ -60,6 +61,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .pred px;\nelect.sync _|px, %1;\n@px mov.s32 %0, 1;\n}\n" : "+r"(pred) : "r"(0xFFFFFFFFu));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -125,6 +132,10 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvOp& op, int t, int n_n
 // Persistent: one CTA per SM walks the tile list.  The TMA producer runs ahead across tile boundaries (the smem ring
 // never drains), the MMA issuer alternates between two TMEM accumulators, and the epilogue warps drain accumulator
 // i while the MMAs of the next tile fill accumulator i^1 -- load, MMA and epilogue of consecutive tiles overlap.
+#ifdef PNET_TIMING
+__device__ unsigned long long g_umma_phase[8];
+#endif
+
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_constant__ ConvOp op, int n_img, int tiles_w,
                                                                    int tiles_h, int n_ntiles, int total_tiles, int stages,
                                                                    uint32_t acc_cols) {
@@ -148,7 +159,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
   const bool has_resid = op.epi != EPI_RELU;
   const uint32_t rt_bytes = (uint32_t)(BN / 64) * 16384u;                     // one residual tile
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index as a warp-uniform value: the TMA / MMA issue loops then live in uniform registers (no R2UR per instruction)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&op.tmap_a);
@@ -165,19 +177,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int cin_blocks = op.Cin / BK;
   const int k_iters = op.kh * op.kw * cin_blocks;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== TMA producer
       const uint32_t box_rows = (uint32_t)(op.box_w * op.box_h * op.box_n);
       const uint32_t tx_bytes = box_rows * BK * 2 + b_bytes;
       int stage = 0;
       uint32_t phase = 0;
       int tl = 0;
+#ifdef PNET_TIMING
+      long long p_wait = 0, p_total = clock64();
+#endif
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
         const TileCoord tc = tile_coord(op, t, n_ntiles, tiles_w, tiles_h);
         if (has_resid) {
@@ -188,20 +203,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
           for (int j = 0; j < BN / 64; ++j)
             tma_load_2d(smem_u32(rt + rb * rt_bytes + j * 16384), &op.tmap_r, &rfull_bar[rb], tc.n_off + 64 * j, tc.ox0);
         }
+        int tap = 0, cb = 0, ky = 0, kx = 0;            // incremental (tap, channel block) counters: no divisions in the issue loop
         for (int it = 0; it < k_iters; ++it) {
+#ifdef PNET_TIMING
+          const long long tq = clock64();
+#endif
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          const int tap = it / cin_blocks, cb = it - tap * cin_blocks;
-          const int ky = tap / op.kw, kx = tap - ky * op.kw;
+#ifdef PNET_TIMING
+          p_wait += clock64() - tq;
+#endif
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           tma_load_4d(smem_u32(smem_a + stage * a_bytes), &op.tmap_a, &full_bar[stage], cb * BK,
                       tc.ox0 * op.stride + kx - op.pad_w, tc.oy0 * op.stride + ky - op.pad_h, tc.n0);
           tma_load_2d(smem_u32(smem_b + stage * b_bytes), &op.tmap_w, &full_bar[stage], tap * op.Cin + cb * BK, tc.n_off);
           if (++stage == stages) { stage = 0; phase ^= 1; }
+          if (++cb == cin_blocks) { cb = 0; ++tap; if (++kx == op.kw) { kx = 0; ++ky; } }
         }
       }
+#ifdef PNET_TIMING
+      atomicAdd(&g_umma_phase[0], (unsigned long long)(clock64() - p_total));
+      atomicAdd(&g_umma_phase[1], (unsigned long long)p_wait);
+      atomicAdd(&g_umma_phase[6], (unsigned long long)tl * k_iters);
+#endif
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== MMA issuer
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
       const uint32_t layout = (BK == 64) ? 2u : 4u;
@@ -209,13 +235,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
       int stage = 0;
       uint32_t phase = 0;
       int tl = 0;
+#ifdef PNET_TIMING
+      long long m_wfull = 0, m_wtmem = 0, m_total = clock64();
+#endif
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
         const int buf = tl & 1;
+#ifdef PNET_TIMING
+        const long long tq0 = clock64();
+#endif
         mbar_wait(&tempty_bar[buf], ((uint32_t)(tl >> 1) & 1u) ^ 1u);       // the epilogue has drained this accumulator
+#ifdef PNET_TIMING
+        m_wtmem += clock64() - tq0;
+#endif
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)buf * acc_cols;
         for (int it = 0; it < k_iters; ++it) {
+#ifdef PNET_TIMING
+          const long long tq1 = clock64();
+#endif
           mbar_wait(&full_bar[stage], phase);
+#ifdef PNET_TIMING
+          m_wfull += clock64() - tq1;
+#endif
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * a_bytes), sbo, layout);
           const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * b_bytes), sbo, layout);
@@ -226,6 +267,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
         }
         mma_commit(&tfull_bar[buf]);
       }
+#ifdef PNET_TIMING
+      atomicAdd(&g_umma_phase[2], (unsigned long long)(clock64() - m_total));
+      atomicAdd(&g_umma_phase[3], (unsigned long long)m_wfull);
+      atomicAdd(&g_umma_phase[4], (unsigned long long)m_wtmem);
+      atomicAdd(&g_umma_phase[5], (unsigned long long)tl);
+#endif
     }
   } else {
     // ===== epilogue (8 warps): warp w owns TMEM lanes 32*(w%4) .. +31 and one half of the tile's columns; thread <->
@@ -327,7 +374,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
   }
 }
 
+
 }  // namespace umma
+#ifdef PNET_TIMING
+extern "C" void trl_debug_umma_timing(unsigned long long* out) {
+  cudaMemcpyFromSymbol(out, umma::g_umma_phase, sizeof(unsigned long long) * 8);
+  unsigned long long z[8] = {0};
+  cudaMemcpyToSymbol(umma::g_umma_phase, z, sizeof(z));
+}
+#endif
 
 // ----------------------------------------------------------------------------- host side
 
