@@ -16,7 +16,8 @@
 namespace umma {
 
 constexpr int BLOCK_M = 128;
-constexpr int NUM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane group: column halves)
+constexpr int NUM_THREADS = 352;     // warp 0 TMA (A operand), warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane group:
+                                     // column halves), warp 10 TMA (weights + residual): two issue threads halve the per-k-iteration issue time
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&op.tmap_a);
     prefetch_tmap(&op.tmap_w);
-    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }      // full: A producer + B producer
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); mbar_init(&rfull_bar[i], 1); mbar_init(&rempty_bar[i], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -184,15 +185,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
 
   if (warp == 0) {
     if (elect_one()) {
-      // ===== TMA producer
+      // ===== TMA producer, A operand
       const uint32_t box_rows = (uint32_t)(op.box_w * op.box_h * op.box_n);
-      const uint32_t tx_bytes = box_rows * BK * 2 + b_bytes;
+      const uint32_t tx_bytes = box_rows * BK * 2;
       int stage = 0;
       uint32_t phase = 0;
       int tl = 0;
 #ifdef PNET_TIMING
       long long p_wait = 0, p_total = clock64();
 #endif
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+        const TileCoord tc = tile_coord(op, t, n_ntiles, tiles_w, tiles_h);
+        const int cx = tc.ox0 * op.stride - op.pad_w, cy = tc.oy0 * op.stride - op.pad_h;
+        int cb = 0, ky = 0, kx = 0;                     // incremental (tap, channel block) counters: no divisions in the issue loop
+        for (int it = 0; it < k_iters; ++it) {
+#ifdef PNET_TIMING
+          const long long tq = clock64();
+#endif
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+#ifdef PNET_TIMING
+          p_wait += clock64() - tq;
+#endif
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_4d(smem_u32(smem_a + stage * a_bytes), &op.tmap_a, &full_bar[stage], cb * BK, cx + kx, cy + ky, tc.n0);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+          if (++cb == cin_blocks) { cb = 0; if (++kx == op.kw) { kx = 0; ++ky; } }
+        }
+      }
+#ifdef PNET_TIMING
+      atomicAdd(&g_umma_phase[0], (unsigned long long)(clock64() - p_total));
+      atomicAdd(&g_umma_phase[1], (unsigned long long)p_wait);
+      atomicAdd(&g_umma_phase[6], (unsigned long long)tl * k_iters);
+#endif
+    }
+  } else if (warp == 10) {
+    if (elect_one()) {
+      // ===== TMA producer, weights (and the residual tile of the up-projections)
+      int stage = 0;
+      uint32_t phase = 0;
+      int tl = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
         const TileCoord tc = tile_coord(op, t, n_ntiles, tiles_w, tiles_h);
         if (has_resid) {
@@ -203,28 +234,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
           for (int j = 0; j < BN / 64; ++j)
             tma_load_2d(smem_u32(rt + rb * rt_bytes + j * 16384), &op.tmap_r, &rfull_bar[rb], tc.n_off + 64 * j, tc.ox0);
         }
-        int tap = 0, cb = 0, ky = 0, kx = 0;            // incremental (tap, channel block) counters: no divisions in the issue loop
-        for (int it = 0; it < k_iters; ++it) {
-#ifdef PNET_TIMING
-          const long long tq = clock64();
-#endif
+        int kcol = 0;                                   // K coordinate of the weight tile: (tap * Cin + cb * BK) = it * BK
+        for (int it = 0; it < k_iters; ++it, kcol += BK) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-#ifdef PNET_TIMING
-          p_wait += clock64() - tq;
-#endif
-          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          tma_load_4d(smem_u32(smem_a + stage * a_bytes), &op.tmap_a, &full_bar[stage], cb * BK,
-                      tc.ox0 * op.stride + kx - op.pad_w, tc.oy0 * op.stride + ky - op.pad_h, tc.n0);
-          tma_load_2d(smem_u32(smem_b + stage * b_bytes), &op.tmap_w, &full_bar[stage], tap * op.Cin + cb * BK, tc.n_off);
+          mbar_arrive_expect_tx(&full_bar[stage], b_bytes);
+          tma_load_2d(smem_u32(smem_b + stage * b_bytes), &op.tmap_w, &full_bar[stage], kcol, tc.n_off);
           if (++stage == stages) { stage = 0; phase ^= 1; }
-          if (++cb == cin_blocks) { cb = 0; ++tap; if (++kx == op.kw) { kx = 0; ++ky; } }
         }
       }
-#ifdef PNET_TIMING
-      atomicAdd(&g_umma_phase[0], (unsigned long long)(clock64() - p_total));
-      atomicAdd(&g_umma_phase[1], (unsigned long long)p_wait);
-      atomicAdd(&g_umma_phase[6], (unsigned long long)tl * k_iters);
-#endif
     }
   } else if (warp == 1) {
     if (elect_one()) {
@@ -274,7 +291,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
       atomicAdd(&g_umma_phase[5], (unsigned long long)tl);
 #endif
     }
-  } else {
+  } else if (warp >= 2 && warp <= 9) {
     // ===== epilogue (8 warps): warp w owns TMEM lanes 32*(w%4) .. +31 and one half of the tile's columns; thread <->
     // one output pixel (tile row).  No global loads on this path: bias comes from shared memory, the residual tile was
     // fetched by the producer's TMA.  All accumulator columns of the thread are loaded first (one wait) and the
