@@ -25,6 +25,24 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on file
+# descriptor 1 when the first communicator is created), so everything that is not the result line goes to stderr.
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
@@ -148,7 +166,7 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t0
     v = args.steps * per_step / dt
     sample = f"{per_step} processed frames of the workload clip per step (oracle MTCNN+FaceNet+consistency, torch CPU fp32)"
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -156,7 +174,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def main():
@@ -172,6 +190,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    _claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -189,7 +208,6 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     an = M.Analyzer(device=local_rank)
     clip, stride, pinned, n_proc_total, n_local = make_frames(WORKLOADS[args.workload]["cfg"], rank, world, torch)
@@ -363,7 +381,7 @@ def main():
         "cpu_baseline": cpu_baseline,
         "result": {"score": last.get("score"), "flagged_frames": last.get("flagged")},
     }
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
