@@ -207,6 +207,8 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    from truely_b200.dist import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     an = M.Analyzer(device=local_rank)
@@ -369,7 +371,8 @@ def main():
                    "processed_frames_per_gpu": n_local, "chunk": args.chunk, "crop": S,
                    "weights": {"mtcnn": an.mtcnn_source, "facenet": an.facenet_source},
                    "cache": "inputs larger than L2 (%.2f GB of frames per step per GPU)" % (n_local * H * W * 3 / 1e9),
-                   "sharding": "contiguous frame ranges + embedding halo all-gather" if world > 1 else "single GPU"},
+                   "sharding": "contiguous frame ranges + embedding halo all-gather" if world > 1 else "single GPU",
+                   "host_cpus_bound_per_rank": numa},
         "video_frames_per_s": value * stride,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps, "h2d_only_ms_per_step": ms_h2d_only,

@@ -16,6 +16,8 @@ kilobytes, so they are latency bound and there is nothing to fuse them with.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 
@@ -102,3 +104,22 @@ class ShardedAnalyzer:
             v, s, b = gather_flags(out["valid"], out["has_sim"], out["below"], n_local, n_max, self.group)
         score, flagged, _ = M.score_from_flags(v, s, b, frame_count, fps, stride)
         return score, flagged, out
+
+
+def bind_to_gpu_numa_node(index: int):
+    """Multi-rank runs: pin this process (and therefore its pinned host buffers, first touch) to the CPUs NVML reports as
+    local to GPU `index`, so that the ranks' H2D streams do not all cross the same socket link.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
