@@ -179,6 +179,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  // Programmatic dependent launch: everything above (barriers, TMEM, bias -- none of it produced by the previous
+  // layer) may run while the previous kernel of the stream is still finishing; the activations may not.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int cin_blocks = op.Cin / BK;
   const int k_iters = op.kh * op.kw * cin_blocks;
@@ -534,7 +538,17 @@ int launch_conv_umma(trl_ctx* c, const ConvOp& op, int n, cudaStream_t s) {
   const int n_ntiles = op.Cout / op.block_n;
   const long long total = (long long)tiles_w * tiles_h * tiles_n * n_ntiles;
   const int grid = (int)(total < TRL_NUM_SMS ? total : TRL_NUM_SMS);
-  conv_umma_kernel<<<grid, NUM_THREADS, smem, s>>>(op, n, tiles_w, tiles_h, n_ntiles, (int)total, stages, acc_cols);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // the ~100 back-to-back layers overlap their prologues
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TRL_CUDA(c, cudaLaunchKernelEx(&cfg, conv_umma_kernel, op, n, tiles_w, tiles_h, n_ntiles, (int)total, stages, acc_cols));
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
