@@ -64,25 +64,63 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region."""
+    """SM clock + throttle reasons during the timed region: NVML every 5 ms (a query takes well under a millisecond),
+    nvidia-smi every 200 ms if NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
-        self.index, self.rows, self.stop, self.th = index, [], threading.Event(), None
+        self.index, self.stop, self.th = index, threading.Event(), None
+        self.sm, self.mx, self.reasons, self.source = [], [], set(), "nvidia-smi"
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
 
-    def _run(self):
+    def _run_nvml(self):
+        n = self.nvml
+        try:
+            self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                mask = int(get_reasons(self.handle))
+                for bit, name in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop.wait(0.005)
+
+    def _run_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                r = [c.strip() for c in out.split(",")] if out else []
+                if r and r[0].replace(".", "").isdigit():
+                    self.sm.append(float(r[0]))
+                if len(r) > 1 and r[1].replace(".", "").isdigit():
+                    self.mx.append(float(r[1]))
+                for k, nme in enumerate(names):
+                    if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                        self.reasons.add(nme)
             except Exception:
                 pass
             self.stop.wait(0.2)
 
     def __enter__(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th = threading.Thread(target=self._run_nvml if self.nvml else self._run_smi, daemon=True)
         self.th.start()
         return self
 
@@ -91,16 +129,8 @@ class ClockSampler:
         self.th.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nme in enumerate(names):
-                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
-                    reasons.add(nme)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
-                    samples=len(self.rows))
+        return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=max(self.mx) if self.mx else None,
+                    reasons=sorted(self.reasons), samples=len(self.sm), source=self.source)
 
 
 def pnet_work(H, W):
