@@ -149,8 +149,9 @@ def pnet_work(H, W):
     return 2 * macs, byts, cells, 2 * tmacs
 
 
-def make_frames(cfg_name, rank, world, torch):
-    """This rank's processed frames of the (world x longer) clip, in pinned host memory."""
+def make_frames(cfg_name, rank, world, torch, staging="wc"):
+    """This rank's processed frames of the (world x longer) clip, in page-locked host staging memory
+    (staging="wc": write-combined, the product's default staging buffer, model.staging_empty; "pinned": plain)."""
     from truely_b200.synth import CONFIGS, SyntheticClip
     cfg = dict(CONFIGS[cfg_name])
     per_rank_frames = cfg["n_frames"]
@@ -160,7 +161,12 @@ def make_frames(cfg_name, rank, world, torch):
     idx = list(range(0, cfg["n_frames"], stride))
     per = len(idx) // world
     mine = idx[rank * per:(rank + 1) * per]
-    pinned = torch.empty((len(mine), clip.height, clip.width, 3), dtype=torch.uint8, pin_memory=True)
+    shape = (len(mine), clip.height, clip.width, 3)
+    if staging == "wc":
+        from truely_b200.model import staging_empty
+        pinned = staging_empty(torch, shape, write_combined=True)
+    else:
+        pinned = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
     for k, i in enumerate(mine):
         pinned[k].copy_(torch.from_numpy(clip.frame(i)))
     return clip, stride, pinned, len(idx), per
@@ -218,6 +224,8 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=48, help="processed frames in the cpu_baseline sample")
     ap.add_argument("--cpu-frames-per-step", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--staging", default="wc", choices=["wc", "pinned"],
+                    help="host staging memory of the e2e path: write-combined page-locked (default) or plain page-locked")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     _claim_stdout()
@@ -242,7 +250,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     an = M.Analyzer(device=local_rank)
-    clip, stride, pinned, n_proc_total, n_local = make_frames(WORKLOADS[args.workload]["cfg"], rank, world, torch)
+    clip, stride, pinned, n_proc_total, n_local = make_frames(WORKLOADS[args.workload]["cfg"], rank, world, torch, args.staging)
     H, W = clip.height, clip.width
     frame_count = clip.n_frames
     dev = f"cuda:{local_rank}"
@@ -385,7 +393,7 @@ def main():
         torch.set_num_threads(cores)
         mt, fn = helpers.oracle_mtcnn(), helpers.oracle_facenet()
         nfr = min(args.cpu_frames, n_local)
-        frames = [pinned[i].numpy().copy() for i in range(nfr)]
+        frames = [clip.frame(i * stride) for i in range(nfr)]       # regenerated: the staging buffer is write-combined (slow to read back)
         reference_run_frames(iter(frames[:2]), 7, W, H, mt, fn)            # warm-up
         t0 = time.perf_counter()
         reference_run_frames(iter(frames), 7, W, H, mt, fn)
@@ -402,7 +410,8 @@ def main():
                    "weights": {"mtcnn": an.mtcnn_source, "facenet": an.facenet_source},
                    "cache": "inputs larger than L2 (%.2f GB of frames per step per GPU)" % (n_local * H * W * 3 / 1e9),
                    "sharding": "contiguous frame ranges + embedding halo all-gather" if world > 1 else "single GPU",
-                   "host_cpus_bound_per_rank": numa},
+                   "host_cpus_bound_per_rank": numa,
+                   "host_staging": "page-locked write-combined (trl_host_alloc)" if args.staging == "wc" else "page-locked"},
         "video_frames_per_s": value * stride,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps, "h2d_only_ms_per_step": ms_h2d_only,

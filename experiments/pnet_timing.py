@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 PKG = os.path.join(ROOT, "truely-real-time-ai-generated-video-detection-framework-for-social-platforms_b200")
-OUT = os.path.join(ROOT, "experiments", "libtruely_b200_timing.so")
+OUT = os.environ.get("TRL_TIMING_LIB", os.path.join(ROOT, "experiments", "libtruely_b200_timing.so"))
 
 
 def build():

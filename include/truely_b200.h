@@ -160,6 +160,15 @@ int trl_set_profiling(trl_ctx_t* ctx, int on);
 int trl_read_stage_times(trl_ctx_t* ctx, float* h_ms);
 int trl_stage_name(int stage, char* buf, int len);
 
+/* Host staging buffers for the frames on their way to the device (what replaces the pageable numpy frame that
+ * cv2.VideoCapture.read returns, server/model.py:43, as the source of the host->device copy).  Page-locked;
+ * with write_combined != 0 the pages are also write-combined (cudaHostAllocWriteCombined): the host only ever
+ * WRITES decoded frames into a staging buffer and the copy engine reads it without snooping the CPU caches, which
+ * matters when eight GPUs of one box pull frames at the same time.  Reading such a buffer from the CPU is slow.
+ * No context needed; returns TRL_E_NOMEM / TRL_E_CUDA on failure. */
+int trl_host_alloc(size_t bytes, int write_combined, void** out);
+int trl_host_free(void* p);
+
 /* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */
 long long trl_launch_count(const trl_ctx_t* ctx);
 

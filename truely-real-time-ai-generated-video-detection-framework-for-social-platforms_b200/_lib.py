@@ -59,6 +59,8 @@ SIGNATURES = {
     "trl_set_profiling": (C.c_int, [_P, C.c_int]),
     "trl_read_stage_times": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "trl_stage_name": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
+    "trl_host_alloc": (C.c_int, [C.c_size_t, C.c_int, C.POINTER(_P)]),
+    "trl_host_free": (C.c_int, [_P]),
 }
 # validation-only exports (not part of the public header)
 DEBUG_SIGNATURES = {

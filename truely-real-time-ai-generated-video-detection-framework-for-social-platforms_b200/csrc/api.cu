@@ -53,6 +53,19 @@ const char* trl_last_error(const trl_ctx_t* ctx) { return ctx ? ctx->err.c_str()
 
 long long trl_launch_count(const trl_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
 
+int trl_host_alloc(size_t bytes, int write_combined, void** out) {
+  if (!out || bytes == 0) return TRL_E_INVALID;
+  *out = nullptr;
+  const cudaError_t e = cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+  if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return TRL_E_NOMEM; }
+  if (e != cudaSuccess) { cudaGetLastError(); return TRL_E_CUDA; }
+  return TRL_OK;
+}
+int trl_host_free(void* p) {
+  if (!p) return TRL_OK;
+  return cudaFreeHost(p) == cudaSuccess ? TRL_OK : TRL_E_CUDA;
+}
+
 static void free_workspace(trl_ctx* c) {
   void* ptrs[] = {c->d_pyr, c->d_cand1, c->d_cnt1, c->d_cand2, c->d_cnt2, c->d_cand3, c->d_cnt3, c->d_pad3, c->d_rin,
                   c->d_cand4, c->d_cnt4, c->d_pad4, c->d_oin, c->d_rprob, c->d_rreg, c->d_oprob, c->d_oreg,

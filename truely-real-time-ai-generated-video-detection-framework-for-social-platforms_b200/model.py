@@ -369,6 +369,30 @@ class Trace:
     timings: dict = None
 
 
+def staging_empty(torch, shape, write_combined: bool = True):
+    """uint8 host staging tensor for frames on their way to the GPU (trl_host_alloc): page-locked and, by default,
+    write-combined -- the host only writes decoded frames into it (server/model.py:43 yields them one by one) and the
+    copy engine reads it without snooping the CPU caches.  Do not read it back on the CPU (uncached reads are slow).
+    TRL_STAGING=pinned selects plain page-locked memory."""
+    import weakref
+    if os.environ.get("TRL_STAGING", "").lower() == "pinned":
+        write_combined = False
+    lib = L.load()
+    n_bytes = 1
+    for s in shape:
+        n_bytes *= int(s)
+    if n_bytes == 0:
+        return torch.empty(shape, dtype=torch.uint8, pin_memory=True)
+    ptr = C.c_void_p()
+    rc = lib.trl_host_alloc(n_bytes, 1 if write_combined else 0, C.byref(ptr))
+    if rc != L.TRL_OK:
+        raise L.TrlError(rc, f"trl_host_alloc({n_bytes} bytes) failed")
+    buf = (C.c_uint8 * n_bytes).from_address(ptr.value)
+    ten = torch.frombuffer(buf, dtype=torch.uint8).view(*shape)
+    weakref.finalize(buf, lib.trl_host_free, ptr.value)       # buf lives as long as any tensor viewing it
+    return ten
+
+
 class _Chunk:
     __slots__ = ("frames", "proc_pos", "proc_idx", "pinned", "out", "host", "event", "n")
 
@@ -401,7 +425,7 @@ def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, a
         if free_bufs:
             c.pinned, c.out, c.host = free_bufs.pop()
         else:
-            c.pinned = t.empty((chunk, height, width, 3), dtype=t.uint8, pin_memory=True)
+            c.pinned = staging_empty(t, (chunk, height, width, 3))
             c.out = an.alloc_outputs(chunk)
             c.out["frames"] = t.empty((chunk, height, width, 3), dtype=t.uint8, device=dev)
             c.host = {k: t.empty(c.out[k].shape, dtype=c.out[k].dtype, pin_memory=True)
