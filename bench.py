@@ -220,7 +220,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="720p30_single", choices=list(WORKLOADS))
-    ap.add_argument("--chunk", type=int, default=90)
+    ap.add_argument("--chunk", type=int, default=90, help="frames per host->device copy / cascade call of the e2e path")
+    ap.add_argument("--resident-chunk", type=int, default=225,
+                    help="frames per cascade call when the frames are already in HBM (`value`); bounded by the workspace only")
     ap.add_argument("--cpu-frames", type=int, default=48, help="processed frames in the cpu_baseline sample")
     ap.add_argument("--cpu-frames-per-step", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -263,10 +265,12 @@ def main():
     def step(h2d):
         src = pinned if h2d else d_frames
         if sharded is not None:
-            score, flagged, _ = sharded.analyze(src, n_local + 1, frame_count, clip.fps, stride, chunk=args.chunk, h2d=h2d,
+            score, flagged, _ = sharded.analyze(src, n_local + 1, frame_count, clip.fps, stride,
+                                                chunk=args.chunk if h2d else args.resident_chunk, h2d=h2d,
                                                 dev_frames=stage_buf)
         else:
-            an.analyze_resident(src, chunk=args.chunk, host_out=host_out, h2d=h2d, dev_frames=stage_buf)
+            an.analyze_resident(src, chunk=args.chunk if h2d else args.resident_chunk, host_out=host_out, h2d=h2d,
+                                dev_frames=stage_buf)
             an.stream.synchronize()
             score, flagged, _ = M.score_from_flags(host_out["valid"].numpy(), host_out["has_sim"].numpy(),
                                                    host_out["below"].numpy(), frame_count, clip.fps, stride)
@@ -294,15 +298,22 @@ def main():
         step(False)
     an.check_capacity()
     launches0 = an.launch_count()
-    an.set_profiling(True)
-    an.read_stage_times()
     with ClockSampler(local_rank) as cs:
         ms_total = timed(False, args.steps)
-    stage_ms, calls = an.read_stage_times()
-    an.set_profiling(False)
     launches = an.launch_count() - launches0
     clocks = cs.summary()
     value = args.steps * n_local * world / (ms_total / 1e3)
+    # per-stage device times: a second pass of the same steps with CUDA events around every stage.  The events need a
+    # serial schedule, so this pass runs the cascade un-pipelined (trl_detect_align_async degrades to trl_detect_align
+    # while profiling is on); the stage times therefore add up to a little more than ms_per_step.
+    an.set_profiling(True)
+    an.read_stage_times()
+    barrier()
+    for _ in range(args.steps):
+        step(False)
+    barrier()
+    stage_ms, calls = an.read_stage_times()
+    an.set_profiling(False)
 
     # ---- e2e: host (pinned) frames in, flags out, through the same public API
     for _ in range(min(args.warmup, 2)):
@@ -351,9 +362,9 @@ def main():
                 d["achieved_tflops_bf16"] = flops_facenet * n_local / (ms * 1e-3) / 1e12
         stages[name] = d
     dom = max(per_step, key=per_step.get)
-    n_chunks = len(M.chunk_schedule(n_local, args.chunk))
+    n_chunks = len(M.chunk_schedule(n_local, args.resident_chunk))
     dom_ms_launch = per_step[dom] / max(1, n_chunks)                  # average duration of one launch of the stage (one chunk)
-    frames_per_launch = min(args.chunk, n_local)
+    frames_per_launch = n_local / n_chunks
     if dom == "facenet":
         ach = flops_facenet * n_local / (per_step[dom] * 1e-3) / 1e12
         roof = {"kernel": "facenet (conv_umma_kernel x103 + stem/pool/head)", "bound": "tensor", "achieved": ach,
@@ -374,11 +385,12 @@ def main():
         ach = (3 * H * W) * n_local / (per_step[dom] * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": None}
-    if dom == "pnet" and args.workload == "720p30_single" and frames_per_launch == 90:
-        # dram__bytes_read.sum + dram__bytes_write.sum of one pnet_kernel launch (90 frames), ncu --set full capture
-        # summarised in profiles/r01c_pnet_full.md: the fp32 pyramid of the chunk (723 MB) read exactly once
-        roof["traffic"] = 732.2e6
-        roof["traffic_unit"] = "bytes/launch (ncu, profiles/r01c_pnet_full.md)"
+    if dom == "pnet" and args.workload == "720p30_single" and frames_per_launch in (90, 225):
+        # dram__bytes_read.sum + dram__bytes_write.sum of one pnet_kernel launch, ncu --set full captures summarised in
+        # profiles/r01d_pnet_full.md (225 frames: 1.8179 GB + 5.9 MB) and r01c_pnet_full.md (90 frames: 726.9 + 6.5 MB):
+        # the fp32 pyramid of the chunk read exactly once
+        roof["traffic"] = 1823.7e6 if frames_per_launch == 225 else 733.5e6
+        roof["traffic_unit"] = "bytes/launch (ncu, profiles/%s_pnet_full.md)" % ("r01d" if frames_per_launch == 225 else "r01c")
         roof["algorithmic_bytes_per_launch"] = bytes_pnet * frames_per_launch
     roof["peak_source"] = pk["source"]
     roof["launch_ms"] = dom_ms_launch
@@ -406,7 +418,9 @@ def main():
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 tensor-core FaceNet (fp32 accumulate) + fp32 MTCNN + u8/int pre-processing", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload]["desc"], "frame": [H, W], "fps": clip.fps, "stride": stride,
-                   "processed_frames_per_gpu": n_local, "chunk": args.chunk, "crop": S,
+                   "processed_frames_per_gpu": n_local, "chunk": args.resident_chunk, "e2e_chunk": args.chunk,
+                   "cascade": "tail of chunk k (NMS, crops, R-Net, O-Net, crop-align) on a second stream under the pyramid of chunk k+1",
+                   "crop": S,
                    "weights": {"mtcnn": an.mtcnn_source, "facenet": an.facenet_source},
                    "cache": "inputs larger than L2 (%.2f GB of frames per step per GPU)" % (n_local * H * W * 3 / 1e9),
                    "sharding": "contiguous frame ranges + embedding halo all-gather" if world > 1 else "single GPU",

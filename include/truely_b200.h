@@ -148,6 +148,17 @@ int trl_process(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, co
 int trl_detect_align(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, int* d_box_int, uint8_t* d_valid,
                      int* d_nfaces, uint8_t* d_crops, void* stream);
 
+/* Pipelined form of trl_detect_align for a host that feeds a clip chunk by chunk: the two throughput stages (pyramid,
+ * P-Net) are enqueued on `stream`, the latency-bound rest of the cascade (NMS, crops, R-Net, O-Net, crop-align) on an
+ * internal high-priority stream, so that it runs under the pyramid of the NEXT chunk.  The outputs of a call
+ * (d_box_int, d_valid, d_nfaces, d_crops) and its reads of d_frames are complete, in `stream` order, only after
+ * the next trl_detect_align_async call has returned (it orders them before its own P-Net), after trl_pipeline_join,
+ * or after any other stream-taking call on this context (each of them joins first).  Same results as
+ * trl_detect_align, bit for bit. */
+int trl_detect_align_async(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, int* d_box_int, uint8_t* d_valid,
+                           int* d_nfaces, uint8_t* d_crops, void* stream);
+int trl_pipeline_join(trl_ctx_t* ctx, void* stream);
+
 /* After the stream has been synchronised by the caller: TRL_E_CAPACITY if any candidate buffer overflowed
  * since the last check (h_detail, optional int32[4]: which stage, frame, count, capacity). */
 int trl_check_capacity(trl_ctx_t* ctx, int* h_detail);

@@ -212,13 +212,17 @@ def test_chunking_and_host_buffer_path_do_not_change_results(analyzer):
     clip = SyntheticClip(720, 1280, 30, 240, n_faces=(1, 1), seed=3)
     frames = np.stack([clip.frame(i) for i in clip.processed_indices()[:40]])
     d = torch.from_numpy(frames).cuda()
-    out0 = an.analyze_resident(d, chunk=40)
+    out0 = an.analyze_resident(d, chunk=40, pipeline=False)
     torch.cuda.synchronize()                       # the analyzer works on its own stream
     ref = {k: out0[k][:40].clone() for k in ("box", "valid", "emb", "sim", "below", "has_sim", "crops")}
     torch.cuda.synchronize()
     pinned = torch.from_numpy(frames).pin_memory()
     stage = torch.empty((3, 16, 720, 1280, 3), dtype=torch.uint8, device="cuda")
-    for kwargs in (dict(chunk=7), dict(chunk=16, h2d=True, dev_frames=stage)):
+    # pipeline=True (the default): the tail of chunk k runs on the library's internal stream under the pyramid of chunk
+    # k+1 (trl_detect_align_async); it must not change a bit either, with ragged last chunks and growing chunk sizes
+    for kwargs in (dict(chunk=7, pipeline=False), dict(chunk=7), dict(chunk=13), dict(chunk=40),
+                   dict(chunk=16, h2d=True, dev_frames=stage, pipeline=False), dict(chunk=16, h2d=True, dev_frames=stage),
+                   dict(chunk=9, h2d=True, dev_frames=stage[:2, :9])):
         src = pinned if kwargs.get("h2d") else d
         out = an.analyze_resident(src, **kwargs)
         an.stream.synchronize()

@@ -81,6 +81,9 @@ static void free_workspace(trl_ctx* c) {
 void trl_destroy(trl_ctx_t* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->tail_stream) { cudaStreamSynchronize(c->tail_stream); cudaStreamDestroy(c->tail_stream); }
+  if (c->ev_head) cudaEventDestroy(c->ev_head);
+  if (c->ev_tail) cudaEventDestroy(c->ev_tail);
   free_workspace(c);
   facenet_destroy(c);
   if (c->d_pnet_packed) cudaFree(c->d_pnet_packed);
@@ -194,6 +197,7 @@ int trl_onet(trl_ctx_t* c, const float* d_in, int n, float* d_prob, float* d_reg
 static int ensure_workspace(trl_ctx* c, int B, int H, int W) {
   if (c->ws_H == H && c->ws_W == W && c->ws_B >= B) return TRL_OK;
   const int Bc = (c->ws_H == H && c->ws_W == W && c->ws_B > B) ? c->ws_B : B;
+  if (c->tail_stream) TRL_CUDA(c, cudaStreamSynchronize(c->tail_stream));     // a pipelined tail may still read the old workspace
   free_workspace(c);
   int rc = compute_geometry(c->cfg, H, W, &c->geom);
   if (rc != TRL_OK) TRL_FAIL(c, rc, "bad frame geometry %dx%d", H, W);
@@ -222,22 +226,39 @@ static int ensure_workspace(trl_ctx* c, int B, int H, int W) {
   return TRL_OK;
 }
 
-static int detect_impl(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, int* d_nfaces, float* d_boxes, int* d_counts,
+// Makes `s` wait for the tail of the last pipelined cascade call (no-op when none is pending).
+static int join_tail(trl_ctx* c, cudaStream_t s) {
+  if (!c->tail_pending) return TRL_OK;
+  TRL_CUDA(c, cudaStreamWaitEvent(s, c->ev_tail, 0));
+  c->tail_pending = false;
+  return TRL_OK;
+}
+
+// The cascade in two parts.  Head = the two throughput stages (pyramid, P-Net: every SM busy); tail = the latency-bound
+// rest (NMS x4, crops, R-Net, O-Net, crop-align: a few hundred candidates).  `ts` is the stream of the tail: the
+// caller's stream (serial), or the context's internal stream (pipelined: the tail of chunk k runs under the pyramid of
+// chunk k+1; P-Net of chunk k+1 is held back until that tail is done, because it shares the candidate workspace and
+// because a persistent P-Net CTA that starts late on an SM still held by a tail kernel would finish late).
+static int detect_head(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, cudaStream_t s) {
+  const PyramidGeom& g = c->geom;
+  int rc;
+  TIMED(0, launch_pyramid(c, d_frames, B, H, W, g, c->d_pyr, true, s));
+  if ((rc = join_tail(c, s)) != TRL_OK) return rc;          // previous tail still reads the candidate workspace
+  TRL_CUDA(c, cudaMemsetAsync(c->d_cnt1, 0, (size_t)B * (g.n + 3) * sizeof(int), s));
+  TIMED(1, launch_pnet_candidates(c, c->d_pyr, B, g, c->cfg.thresholds[0], c->d_cand1, c->d_cnt1, c->cfg.cand_cap_scale, s));
+  return TRL_OK;
+}
+
+static int detect_tail(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, int* d_nfaces, float* d_boxes, int* d_counts,
                        cudaStream_t s) {
-  if (!c->d_pnet_packed || !c->d_rnet || !c->d_onet) TRL_FAIL(c, TRL_E_STATE, "MTCNN weights not loaded");
-  int rc = ensure_workspace(c, B, H, W);
-  if (rc != TRL_OK) return rc;
   const PyramidGeom& g = c->geom;
   const int c1 = c->cfg.cand_cap_scale, c2 = c->cfg.cand_cap_frame, c4 = c->cfg.box_cap_frame;
+  int rc;
   // counters are laid out for the *current* B: cnt1 [B][n], cnt2 [B], cnt3 [B], cnt4 [B]
   int* cnt1 = c->d_cnt1;
   int* cnt2 = cnt1 + (size_t)B * g.n;
   int* cnt3 = cnt2 + B;
   int* cnt4 = cnt3 + B;
-  TRL_CUDA(c, cudaMemsetAsync(cnt1, 0, (size_t)B * (g.n + 3) * sizeof(int), s));
-  TIMED(0, launch_pyramid(c, d_frames, B, H, W, g, c->d_pyr, true, s));
-  TIMED(1, launch_pnet_candidates(c, c->d_pyr, B, g, c->cfg.thresholds[0], c->d_cand1, cnt1, c1, s));
-
   nms::StageParams p{};
   p.W = W; p.H = H; p.capflag = c->d_cap;
   // stage 1: per (frame, level) NMS 0.5
@@ -272,15 +293,28 @@ static int detect_impl(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W,
   return TRL_OK;
 }
 
+static int detect_impl(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, int* d_nfaces, float* d_boxes, int* d_counts,
+                       cudaStream_t s) {
+  if (!c->d_pnet_packed || !c->d_rnet || !c->d_onet) TRL_FAIL(c, TRL_E_STATE, "MTCNN weights not loaded");
+  int rc = ensure_workspace(c, B, H, W);
+  if (rc != TRL_OK) return rc;
+  if ((rc = detect_head(c, d_frames, B, H, W, s)) != TRL_OK) return rc;
+  return detect_tail(c, d_frames, B, H, W, d_nfaces, d_boxes, d_counts, s);
+}
+
 int trl_detect(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, int* d_nfaces, float* d_boxes, int* d_counts,
                void* stream) {
   if (!c || !d_frames || !d_nfaces || !d_boxes || B <= 0) return TRL_E_INVALID;
+  int rc = join_tail(c, (cudaStream_t)stream);
+  if (rc != TRL_OK) return rc;
   return detect_impl(c, d_frames, B, H, W, d_nfaces, d_boxes, d_counts, (cudaStream_t)stream);
 }
 
 int trl_crop_align(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
                    const int* d_nfaces, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops, void* stream) {
   if (!c || !d_frames || !d_boxes || !d_nfaces || !d_box_int || !d_valid || !d_crops) return TRL_E_INVALID;
+  int rc = join_tail(c, (cudaStream_t)stream);
+  if (rc != TRL_OK) return rc;
   return launch_crop_align(c, d_frames, B, H, W, d_boxes, box_stride, d_nfaces, c->cfg.crop_size, d_box_int, d_valid, d_crops,
                            (cudaStream_t)stream);
 }
@@ -289,6 +323,7 @@ int trl_facenet(trl_ctx_t* c, const uint8_t* d_crops, int n, int S, float* d_emb
   if (!c || !d_crops || !d_emb || n < 0) return TRL_E_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
+  if ((rc = join_tail(c, s)) != TRL_OK) return rc;
   TIMED(11, facenet_forward(c, d_crops, n, S, d_emb, s));
   return TRL_OK;
 }
@@ -299,6 +334,7 @@ int trl_consistency(trl_ctx_t* c, const float* d_emb, const uint8_t* d_valid, in
   if (!c || !d_emb || !d_valid || !d_sim || !d_below || !d_has_sim) return TRL_E_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
+  if ((rc = join_tail(c, s)) != TRL_OK) return rc;
   TIMED(12, launch_consistency(c, d_emb, d_valid, B, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
                                d_last_valid, s));
   return TRL_OK;
@@ -308,13 +344,47 @@ int trl_detect_align(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W,
                      int* d_nfaces, uint8_t* d_crops, void* stream) {
   if (!c || !d_frames || !d_box_int || !d_valid || !d_crops || B <= 0) return TRL_E_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = ensure_workspace(c, B, H, W);
+  int rc = join_tail(c, s);
   if (rc != TRL_OK) return rc;
+  if ((rc = ensure_workspace(c, B, H, W)) != TRL_OK) return rc;
   int* nf = d_nfaces ? d_nfaces : c->d_nfaces;
   if ((rc = detect_impl(c, d_frames, B, H, W, nf, c->d_boxes, nullptr, s)) != TRL_OK) return rc;
   TIMED(10, launch_crop_align(c, d_frames, B, H, W, c->d_boxes, c->cfg.box_cap_frame * 5, nf, c->cfg.crop_size, d_box_int,
                               d_valid, d_crops, s));
   return TRL_OK;
+}
+
+int trl_detect_align_async(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, int* d_box_int, uint8_t* d_valid,
+                           int* d_nfaces, uint8_t* d_crops, void* stream) {
+  if (!c || !d_frames || !d_box_int || !d_valid || !d_crops || B <= 0) return TRL_E_INVALID;
+  if (c->profiling) return trl_detect_align(c, d_frames, B, H, W, d_box_int, d_valid, d_nfaces, d_crops, stream);   // stage times need a serial schedule
+  if (!c->d_pnet_packed || !c->d_rnet || !c->d_onet) TRL_FAIL(c, TRL_E_STATE, "MTCNN weights not loaded");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!c->tail_stream) {
+    int lo = 0, hi = 0;
+    TRL_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    TRL_CUDA(c, cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, hi));     // tail CTAs go first when an SM frees up
+    TRL_CUDA(c, cudaEventCreateWithFlags(&c->ev_head, cudaEventDisableTiming));
+    TRL_CUDA(c, cudaEventCreateWithFlags(&c->ev_tail, cudaEventDisableTiming));
+  }
+  int rc = ensure_workspace(c, B, H, W);
+  if (rc != TRL_OK) return rc;
+  int* nf = d_nfaces ? d_nfaces : c->d_nfaces;
+  if ((rc = detect_head(c, d_frames, B, H, W, s)) != TRL_OK) return rc;       // joins the previous tail before P-Net
+  TRL_CUDA(c, cudaEventRecord(c->ev_head, s));
+  cudaStream_t ts = c->tail_stream;
+  TRL_CUDA(c, cudaStreamWaitEvent(ts, c->ev_head, 0));
+  if ((rc = detect_tail(c, d_frames, B, H, W, nf, c->d_boxes, nullptr, ts)) != TRL_OK) return rc;
+  if ((rc = launch_crop_align(c, d_frames, B, H, W, c->d_boxes, c->cfg.box_cap_frame * 5, nf, c->cfg.crop_size, d_box_int,
+                              d_valid, d_crops, ts)) != TRL_OK) return rc;
+  TRL_CUDA(c, cudaEventRecord(c->ev_tail, ts));
+  c->tail_pending = true;
+  return TRL_OK;
+}
+
+int trl_pipeline_join(trl_ctx_t* c, void* stream) {
+  if (!c) return TRL_E_INVALID;
+  return join_tail(c, (cudaStream_t)stream);
 }
 
 int trl_process(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, const float* d_halo_emb,

@@ -181,6 +181,12 @@ struct trl_ctx {
   CapFlag* h_cap = nullptr;      // pinned, mapped
   CapFlag* d_cap = nullptr;      // device alias of h_cap
 
+  // pipelined cascade (trl_detect_align_async): the latency-bound tail of chunk k (NMS, crops, R-Net, O-Net, crop-align)
+  // runs on an internal high-priority stream under the pyramid of chunk k+1
+  cudaStream_t tail_stream = nullptr;
+  cudaEvent_t ev_head = nullptr, ev_tail = nullptr;
+  bool tail_pending = false;     // ev_tail has been recorded and no caller stream has waited for it yet
+
   bool profiling = false;
   struct ProfRec { int stage; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof_events;

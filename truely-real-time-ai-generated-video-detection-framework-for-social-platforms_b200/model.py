@@ -198,13 +198,14 @@ class Analyzer:
 
     # ------------------------------------------------------------------ clip-level API on staged frames
     def analyze_resident(self, frames, chunk: int = 90, host_out=None, halo=None, h2d: bool = False, dev_frames=None,
-                         thr: float = THRESHOLD_FACE_SIMILARITY):
+                         thr: float = THRESHOLD_FACE_SIMILARITY, pipeline: bool = True):
         """All processed frames of a clip (or of this rank's range) in one go.
 
         ``frames``: uint8 [N,H,W,3] tensor, either on the device (``h2d=False``) or in pinned host memory
         (``h2d=True``: chunks are copied to the device inside this call on a copy stream, multi-buffered in
         ``dev_frames`` [nbuf,chunk,H,W,3], so the copies of the next chunks overlap the cascade on chunk k).
-        The MTCNN cascade + crop-align run chunk by chunk (bounded workspace); all N crops are then embedded by ONE
+        The MTCNN cascade + crop-align run chunk by chunk (bounded workspace; with ``pipeline`` the latency-bound tail
+        of chunk k runs under the pyramid of chunk k+1, trl_detect_align_async); all N crops are then embedded by ONE
         FaceNet call (large-M GEMMs) and compared by one consistency call.  Nothing synchronises with the host.
         Returns the dict of device outputs [N, ...]; if ``host_out`` (pinned tensors keyed like the outputs) is given,
         those per-frame results are copied back asynchronously as well.
@@ -241,11 +242,17 @@ class Analyzer:
             with t.cuda.stream(self.stream):
                 if h2d:
                     self.stream.wait_event(copied[k])
-                self._check(self.lib.trl_detect_align(
+                fn = self.lib.trl_detect_align_async if pipeline else self.lib.trl_detect_align
+                self._check(fn(
                     self.ctx, _vp(d), b - a, H, Wd, _vp(out["box"][a:b]), _vp(out["valid"][a:b]), _vp(out["nfaces"][a:b]),
                     _vp(out["crops"][a:b]), self._sptr()))
                 if h2d:
-                    consumed[k].record(self.stream)
+                    # pipelined: the tail of chunk k still reads its frames until call k+1 has ordered it before its own
+                    # P-Net, so staging buffer k is released one call later (the last ones after the FaceNet call's join)
+                    if not pipeline:
+                        consumed[k].record(self.stream)
+                    elif k >= 1:
+                        consumed[k - 1].record(self.stream)
         with t.cuda.stream(self.stream):
             # one FaceNet batch for the whole range: per-chunk calls (tried, to hide FaceNet under the next copy) make the
             # step launch bound on the host (~110 launches per call) and were 8 ms slower end to end
