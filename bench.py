@@ -165,6 +165,10 @@ def make_frames(cfg_name, rank, world, torch, staging="wc"):
     if staging == "wc":
         from truely_b200.model import staging_empty
         pinned = staging_empty(torch, shape, write_combined=True)
+    elif staging.startswith("interleave"):
+        from truely_b200.dist import interleaved_staging
+        pinned, desc = interleaved_staging(torch, shape, "all" if staging.endswith("all") else "socket")
+        print(f"[bench] rank {rank}: staging {desc}", file=sys.stderr)
     else:
         pinned = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
     for k, i in enumerate(mine):
@@ -226,7 +230,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=48, help="processed frames in the cpu_baseline sample")
     ap.add_argument("--cpu-frames-per-step", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--staging", default="wc", choices=["wc", "pinned"],
+    ap.add_argument("--staging", default="wc", choices=["wc", "pinned", "interleave-socket", "interleave-all"],
                     help="host staging memory of the e2e path: write-combined page-locked (default) or plain page-locked")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -425,7 +429,7 @@ def main():
                    "cache": "inputs larger than L2 (%.2f GB of frames per step per GPU)" % (n_local * H * W * 3 / 1e9),
                    "sharding": "contiguous frame ranges + embedding halo all-gather" if world > 1 else "single GPU",
                    "host_cpus_bound_per_rank": numa,
-                   "host_staging": "page-locked write-combined (trl_host_alloc)" if args.staging == "wc" else "page-locked"},
+                   "host_staging": {"wc": "page-locked write-combined (trl_host_alloc)", "pinned": "page-locked"}.get(args.staging, args.staging)},
         "video_frames_per_s": value * stride,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps, "h2d_only_ms_per_step": ms_h2d_only,

@@ -248,3 +248,104 @@ def test_1080p_multi_face_matches_oracle(analyzer):
         assert int(res.counts[i, 3]) == n_ref, f"frame {i}: {int(res.counts[i, 3])} faces, oracle {n_ref}"
         if n_ref:
             _match_boxes(res.boxes[i, :n_ref, :4], boxes)
+
+
+def test_odd_frame_shapes_match_oracle(analyzer):
+    """Frame widths whose rows are neither 16- nor 4-byte aligned (3 W % 4 != 0) take the byte-aligned pyramid path and
+    the cp.async P-Net staging; the cascade must still agree with the oracle (the reference accepts any frame size)."""
+    mt = H.oracle_mtcnn()
+    for (h, w, seed) in ((363, 641, 21), (301, 403, 22)):
+        clip = SyntheticClip(h, w, 30, 40, n_faces=(1, 2), face_h=(70.0, 120.0), seed=seed)
+        frames = [clip.frame(i) for i in (0, 9, 23)]
+        res = analyzer.process_frames(np.stack(frames), detail=True)
+        for k, f in enumerate(frames):
+            boxes, _ = mt.detect(f)
+            n_ref = 0 if boxes is None else len(boxes)
+            assert res.nfaces[k] == n_ref, f"{h}x{w} frame {k}: {res.nfaces[k]} faces vs oracle {n_ref}"
+            if n_ref:
+                _match_boxes(res.boxes[k, :n_ref, :4], boxes)
+
+
+def test_faceless_and_tiny_frames(analyzer):
+    """mtcnn.detect returns (None, [None]) on frames without a face; the reference then skips the frame
+    (server/model.py:48): no embedding, no comparison, the run-length counter does not move, score 0.  On frames too small
+    for a single pyramid level (min side * 0.6 < 12) upstream detect_face raises (torch.cat of an empty list), and so does
+    the oracle; the library reports TRL_E_INVALID instead of launching anything."""
+    rng = np.random.default_rng(5)
+    noise = rng.integers(0, 256, size=(6, 360, 640, 3), dtype=np.uint8)
+    res = analyzer.process_frames(noise)
+    assert not res.valid.any() and (res.nfaces == 0).all()
+    d = torch.from_numpy(noise).cuda()
+    out = analyzer.analyze_resident(d, chunk=4)
+    analyzer.stream.synchronize()
+    assert int(out["valid"][:6].sum()) == 0 and int(out["has_sim"][:6].sum()) == 0 and int(out["below"][:6].sum()) == 0
+    score, flagged, _ = M.score_from_flags(out["valid"][:6].cpu().numpy(), out["has_sim"][:6].cpu().numpy(),
+                                           out["below"][:6].cpu().numpy(), 24, 30, 4)
+    assert score == 0 and not any(flagged)
+    tiny = rng.integers(0, 256, size=(3, 18, 31, 3), dtype=np.uint8)       # 18 * 0.6 = 10.8 < 12: zero pyramid levels
+    with pytest.raises((RuntimeError, ValueError)):
+        H.oracle_mtcnn().detect(tiny[0])
+    from truely_b200._lib import TrlError
+    with pytest.raises(TrlError) as ei:
+        analyzer.process_frames(tiny)
+    assert ei.value.code == -1 and "too small" in str(ei.value)
+    res = analyzer.process_frames(noise[:2])                               # the context is still usable afterwards
+    assert (res.nfaces == 0).all()
+
+
+def test_full_size_run_is_deterministic_and_schedule_independent(analyzer):
+    """BASELINE.json configs[1] at full size (450 processed 720p frames): two runs give identical bits, and neither the
+    number of frames per cascade call nor the two-stream schedule changes boxes, crops, embeddings or flags."""
+    an = analyzer
+    clip = SyntheticClip(720, 1280, 30, 1800, n_faces=(1, 1), jitter=1.2, seed=0)
+    idx = clip.processed_indices()
+    assert len(idx) == 450
+    d = torch.empty((450, 720, 1280, 3), dtype=torch.uint8, device="cuda")
+    for k, i in enumerate(idx):
+        d[k].copy_(torch.from_numpy(clip.frame(i)))
+    keys = ("box", "valid", "crops", "emb", "sim", "below", "has_sim")
+
+    def run(**kw):
+        out = an.analyze_resident(d, **kw)
+        an.stream.synchronize()
+        torch.cuda.synchronize()
+        return {k: torch.nan_to_num(out[k][:450].clone().float(), nan=-2.0) for k in keys}
+
+    ref = run(chunk=90, pipeline=False)
+    for kw in (dict(chunk=90, pipeline=False), dict(chunk=90), dict(chunk=225), dict(chunk=450)):
+        got = run(**kw)
+        for k in keys:
+            assert torch.equal(got[k], ref[k]), f"{k} differs with {kw}"
+    assert int(ref["valid"].sum()) >= 440 and int(ref["below"].sum()) > 0       # faces found, comparisons on both sides of 0.99
+
+
+def test_host_staging_buffers(analyzer):
+    """trl_host_alloc / trl_host_free: page-locked (write-combined) staging memory is a valid source of asynchronous copies
+    and the whole host-buffer path gives the same bits from it as from torch's pinned memory."""
+    from truely_b200.model import staging_empty
+    clip = SyntheticClip(360, 640, 30, 64, n_faces=(1, 1), face_h=(90.0, 130.0), seed=4)
+    frames = np.stack([clip.frame(i) for i in clip.processed_indices()[:12]])
+    stage = torch.empty((2, 5, 360, 640, 3), dtype=torch.uint8, device="cuda")
+    outs = []
+    for wc in (None, True, False):
+        if wc is None:
+            src = torch.from_numpy(frames).pin_memory()
+        else:
+            src = staging_empty(torch, frames.shape, write_combined=wc)
+            src.copy_(torch.from_numpy(frames))
+            assert src.is_pinned()
+        out = analyzer.analyze_resident(src, chunk=5, h2d=True, dev_frames=stage)
+        analyzer.stream.synchronize()
+        torch.cuda.synchronize()
+        outs.append({k: torch.nan_to_num(out[k][:12].clone().float(), nan=-2.0) for k in ("box", "valid", "emb", "sim", "below")})
+        del src
+    for o in outs[1:]:
+        for k, v in outs[0].items():
+            assert torch.equal(o[k], v), k
+    assert int(outs[0]["valid"].sum()) >= 10
+    import ctypes as C
+    lib = analyzer.lib
+    p = C.c_void_p()
+    assert lib.trl_host_alloc(0, 1, C.byref(p)) == -1                       # TRL_E_INVALID
+    assert lib.trl_host_alloc(1 << 20, 1, C.byref(p)) == 0 and p.value
+    assert lib.trl_host_free(p) == 0

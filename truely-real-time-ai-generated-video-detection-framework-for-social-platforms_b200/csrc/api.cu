@@ -196,11 +196,18 @@ int trl_onet(trl_ctx_t* c, const float* d_in, int n, float* d_prob, float* d_reg
 
 static int ensure_workspace(trl_ctx* c, int B, int H, int W) {
   if (c->ws_H == H && c->ws_W == W && c->ws_B >= B) return TRL_OK;
+  PyramidGeom geom;
+  int rc = compute_geometry(c->cfg, H, W, &geom);
+  if (rc != TRL_OK) TRL_FAIL(c, rc, "bad frame geometry %dx%d", H, W);
+  // upstream detect_face ends in torch.cat([]) -> RuntimeError when the scale list is empty; the reference's run() then
+  // raises (HTTP 500 in server.py).  Same error behaviour here, reported before anything is launched or freed.
+  if (geom.n == 0)
+    TRL_FAIL(c, TRL_E_INVALID, "frame %dx%d is too small for a single pyramid level at min_face_size %d (upstream detect_face raises on it)",
+             H, W, c->cfg.min_face_size);
   const int Bc = (c->ws_H == H && c->ws_W == W && c->ws_B > B) ? c->ws_B : B;
   if (c->tail_stream) TRL_CUDA(c, cudaStreamSynchronize(c->tail_stream));     // a pipelined tail may still read the old workspace
   free_workspace(c);
-  int rc = compute_geometry(c->cfg, H, W, &c->geom);
-  if (rc != TRL_OK) TRL_FAIL(c, rc, "bad frame geometry %dx%d", H, W);
+  c->geom = geom;
   const PyramidGeom& g = c->geom;
   const size_t c1 = c->cfg.cand_cap_scale, c2 = c->cfg.cand_cap_frame, c4 = c->cfg.box_cap_frame;
   const int S = c->cfg.crop_size;

@@ -39,7 +39,7 @@ __device__ __forceinline__ float area_norm(int s, int kh, int kw) {
 // ----------------------------------------------------------------------------- K1 pyramid
 
 // Separable exact area resample.  Window tables (host computed once per frame shape): for level k,
-// tab + tab_off[k] holds xw[ws] = x0 | kw << 16, rkw[ws] = bits of RN(1 / kw), y0[hs], y1[hs] -- no integer
+// tab + tab_off[k] holds ws pairs {x0 | kw << 16, bits of RN(1 / kw)}, then y0[hs], y1[hs] -- no integer
 // division on the device.
 //
 // One CTA = (frame, level, R consecutive output rows).
@@ -191,10 +191,15 @@ __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restr
     const int kh = __ldg(ty1 + jj) - __ldg(ty0 + jj);
     const float fkh = (float)kh, rkh = __frcp_rn(fkh);
     const uint16_t* vr = v16 + jj * (4 * nw);
-    float* orow = obase + jj * pitch;
-    for (int i = tid; i < ws; i += 256) {
-      const int xw = __ldg(t + i);
-      const float rkw = __int_as_float(__ldg(t + ws + i));
+    // per-thread running pointers: one 64-bit add per plane and step instead of rebuilding three addresses per pixel
+    float* o0 = obase + jj * pitch + tid;
+    float* o1 = o0 + plane;
+    float* o2 = o1 + plane;
+    const int2* tw = reinterpret_cast<const int2*>(t) + tid;      // {x0 | kw << 16, bits of RN(1 / kw)}
+    for (int i = tid; i < ws; i += 256, o0 += 256, o1 += 256, o2 += 256, tw += 256) {
+      const int2 e = __ldg(tw);
+      const int xw = e.x;
+      const float rkw = __int_as_float(e.y);
       const int kw = xw >> 16;
       const uint16_t* vp = vr + 3 * (xw & 0xFFFF);
       int s0 = 0, s1 = 0, s2 = 0;
@@ -210,9 +215,9 @@ __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restr
         a1 = __fdiv_rn(__fdiv_rn((float)s1, fkh), fkw);
         a2 = __fdiv_rn(__fdiv_rn((float)s2, fkh), fkw);
       }
-      orow[i] = __fmul_rn(__fsub_rn(a0, 127.5f), 0.0078125f);
-      orow[plane + i] = __fmul_rn(__fsub_rn(a1, 127.5f), 0.0078125f);
-      orow[2 * plane + i] = __fmul_rn(__fsub_rn(a2, 127.5f), 0.0078125f);
+      *o0 = __fmul_rn(__fsub_rn(a0, 127.5f), 0.0078125f);
+      *o1 = __fmul_rn(__fsub_rn(a1, 127.5f), 0.0078125f);
+      *o2 = __fmul_rn(__fsub_rn(a2, 127.5f), 0.0078125f);
     }
   }
   // pad columns [ws, pitch) stay untouched: readers clip at ws
@@ -240,8 +245,8 @@ static int build_pyramid_tables(trl_ctx* c, int H, int W, const PyramidGeom& g, 
     std::vector<int> x0, x1, y0, y1;
     window_table(W, g.ws[k], x0, x1);
     window_table(H, g.hs[k], y0, y1);
-    for (int i = 0; i < g.ws[k]; ++i) tab.push_back(x0[i] | ((x1[i] - x0[i]) << 16));
-    for (int i = 0; i < g.ws[k]; ++i) {
+    for (int i = 0; i < g.ws[k]; ++i) {                  // interleaved pairs: one 64-bit load per output pixel
+      tab.push_back(x0[i] | ((x1[i] - x0[i]) << 16));
       const float r = 1.0f / (float)(x1[i] - x0[i]);     // IEEE: correctly rounded reciprocal
       int bits;
       memcpy(&bits, &r, 4);

@@ -123,3 +123,71 @@ def bind_to_gpu_numa_node(index: int):
     except Exception:
         pass
     return None
+
+
+def numa_topology():
+    """{node: set(cpus)} and {node: socket} from sysfs (empty dicts when the kernel exposes no NUMA information)."""
+    import glob
+    import re
+    nodes, socket_of = {}, {}
+    for path in glob.glob("/sys/devices/system/node/node[0-9]*"):
+        n = int(re.search(r"node(\d+)$", path).group(1))
+        cpus = set()
+        try:
+            for part in open(os.path.join(path, "cpulist")).read().strip().split(","):
+                if not part:
+                    continue
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        except OSError:
+            continue
+        if not cpus:
+            continue
+        nodes[n] = cpus
+        try:
+            socket_of[n] = int(open(f"/sys/devices/system/cpu/cpu{min(cpus)}/topology/physical_package_id").read())
+        except OSError:
+            socket_of[n] = 0
+    return nodes, socket_of
+
+
+def interleaved_staging(torch, shape, scope: str = "socket"):
+    """Experimental host staging buffer whose pages are interleaved over several NUMA nodes (scope "socket": the nodes
+    of the socket this process runs on; "all": every node) and then page-locked with cudaHostRegister.  With sub-NUMA
+    clustering a rank bound to its GPU's local CPUs otherwise puts its whole staging buffer behind the two or three
+    memory channels of one sub-node.  Returns (tensor, description)."""
+    import ctypes as C
+    import mmap
+    nodes, socket_of = numa_topology()
+    here = None
+    cpus_now = os.sched_getaffinity(0)
+    for n, cpus in nodes.items():
+        if cpus & cpus_now:
+            here = n
+            break
+    if scope == "socket" and here is not None:
+        use = sorted(n for n in nodes if socket_of[n] == socket_of[here])
+    else:
+        use = sorted(nodes)
+    n_bytes = 1
+    for s in shape:
+        n_bytes *= int(s)
+    libc = C.CDLL(None, use_errno=True)
+    set_ok = False
+    if len(use) > 1:
+        mask = 0
+        for n in use:
+            mask |= 1 << n
+        maxnode = max(use) + 2
+        arr = (C.c_ulong * ((maxnode + 63) // 64))(*[(mask >> (64 * i)) & (2**64 - 1) for i in range((maxnode + 63) // 64)])
+        set_ok = libc.syscall(238, 3, arr, C.c_ulong(maxnode)) == 0          # set_mempolicy(MPOL_INTERLEAVE)
+    mm = mmap.mmap(-1, n_bytes)                                               # anonymous, first touch decides the node
+    ten = torch.frombuffer(mm, dtype=torch.uint8)
+    ten.zero_()                                                               # touch every page under the policy
+    if set_ok:
+        libc.syscall(238, 0, None, C.c_ulong(0))                              # back to MPOL_DEFAULT
+    addr = C.addressof(C.c_char.from_buffer(mm))
+    err = torch.cuda.cudart().cudaHostRegister(addr, n_bytes, 0)
+    if int(err) != 0:
+        raise RuntimeError(f"cudaHostRegister failed: {err}")
+    return ten.view(*shape), f"interleaved over NUMA nodes {use} (policy set: {set_ok}), cudaHostRegister"
