@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtruely_b200.so")
+LIB_PATH = os.environ.get("TRL_LIB_PATH") or os.path.join(_HERE, "libtruely_b200.so")      # override: experiment builds only
 
 TRL_OK, TRL_E_INVALID, TRL_E_CUDA, TRL_E_CAPACITY, TRL_E_NOMEM, TRL_E_STATE = 0, -1, -2, -3, -4, -5
 EMB_DIM = 512

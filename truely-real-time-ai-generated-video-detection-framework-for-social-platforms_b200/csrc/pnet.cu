@@ -189,6 +189,19 @@ __device__ __forceinline__ TileRef decode_tile(const Params& p, int id) {
   r.lvl = lvl; r.oy0 = ty * TOY; r.ox0 = (tile - ty * p.lv[lvl].tiles_x) * TOX;
   return r;
 }
+// conv2 M tiles per group-B warp (see the conv2 loop), one nibble per warp: 4 4 5 6 5 6 5 6 = 41.  Measured on 450 720p
+// frames: this split 10.35 ms, 3 3 6 6 6 6 6 5 10.36, 4 4 6 6 6 5 5 5 10.51, even 6 5 5 5 5 5 5 5 10.79 (strided even
+// split of the previous version: 10.43) -- a small gain only, because group A's conv1 sets the pace once B is balanced.
+#ifndef PNET_C2_COUNTS
+#define PNET_C2_COUNTS 0x65656544u
+#endif
+__host__ __device__ constexpr int c2_count(int warp) { return (int)((PNET_C2_COUNTS >> (4 * warp)) & 0xFu); }
+__host__ __device__ constexpr int c2_first(int warp) {
+  int f = 0;
+  for (int w = 0; w < warp; ++w) f += c2_count(w);
+  return f;
+}
+static_assert(NB_WARPS == 8 && c2_first(NB_WARPS) == C2TILES, "the conv2 tile split covers every M tile once");
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -558,13 +571,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
     const float inv = w_s[SC + 0];
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-      // tiles warp + NB_WARPS * i, i = 3 pass .. 3 pass + 2
-      const int mt0 = warp + 3 * NB_WARPS * pass;
-      const int nq = max(0, min(3, (C2TILES - mt0 + NB_WARPS - 1) / NB_WARPS));      // live M tiles of this warp in this pass (warp uniform)
+      // M tiles c2_first(warp) + 3 pass + q, q < 3.  The 41 tiles are not dealt evenly: warps 0-1 also carry three conv3
+      // head epilogues per tile (M tiles 0, 2 and the half tile 4) where the other warps carry two, and the slowest warp
+      // of group B sets the pace of the whole CTA, so they get 4 conv2 tiles and the others 6 or 5.
+      const int mt0 = c2_first(warp) + 3 * pass;
+      const int nq = max(0, min(3, c2_count(warp) - 3 * pass));      // live M tiles of this warp in this pass (warp uniform)
       if (nq == 0) break;
       int base[3];
 #pragma unroll
-      for (int q = 0; q < 3; ++q) base[q] = min(mt0 + NB_WARPS * q, C2TILES - 1) * 16 + g;
+      for (int q = 0; q < 3; ++q) base[q] = min(mt0 + q, C2TILES - 1) * 16 + g;
       float acc[3][2][4];
 #pragma unroll
       for (int q = 0; q < 3; ++q)
@@ -614,8 +629,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
       const float al0 = w_s[A2 + 2 * t], al1 = w_s[A2 + 2 * t + 1], al2 = w_s[A2 + 8 + 2 * t], al3 = w_s[A2 + 9 + 2 * t];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        const int mt = mt0 + NB_WARPS * q;
-        if (mt >= C2TILES) break;                 // warp uniform
+        const int mt = mt0 + q;
+        if (q >= nq) break;                       // warp uniform
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int n = mt * 16 + 8 * h + g;
