@@ -389,12 +389,11 @@ def main():
         ach = (3 * H * W) * n_local / (per_step[dom] * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": None}
-    if dom == "pnet" and args.workload == "720p30_single" and frames_per_launch in (90, 225):
-        # dram__bytes_read.sum + dram__bytes_write.sum of one pnet_kernel launch, ncu --set full captures summarised in
-        # profiles/r01d_pnet_full.md (225 frames: 1.8179 GB + 5.9 MB) and r01c_pnet_full.md (90 frames: 726.9 + 6.5 MB):
-        # the fp32 pyramid of the chunk read exactly once
-        roof["traffic"] = 1823.7e6 if frames_per_launch == 225 else 733.5e6
-        roof["traffic_unit"] = "bytes/launch (ncu, profiles/%s_pnet_full.md)" % ("r01d" if frames_per_launch == 225 else "r01c")
+    if dom == "pnet" and args.workload == "720p30_single" and frames_per_launch == 225:
+        # dram__bytes_read.sum + dram__bytes_write.sum of one pnet_kernel launch (225 frames), ncu --set full capture
+        # summarised in profiles/r01e_pnet_full.md (1.8176 GB + 4.5 MB): the fp32 pyramid of the chunk read exactly once
+        roof["traffic"] = 1822.1e6
+        roof["traffic_unit"] = "bytes/launch (ncu, profiles/r01e_pnet_full.md)"
         roof["algorithmic_bytes_per_launch"] = bytes_pnet * frames_per_launch
     roof["peak_source"] = pk["source"]
     roof["launch_ms"] = dom_ms_launch

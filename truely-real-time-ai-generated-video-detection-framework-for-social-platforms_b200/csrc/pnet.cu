@@ -1,5 +1,5 @@
 // K2 + K3: fused P-Net (conv1+PReLU+maxpool, conv2+PReLU, conv3+PReLU, conv4_1 -> softmax, conv4_2) and
-// generateBoundingBox.  One CTA computes a 16x32 tile of output cells; every intermediate lives in shared memory, the
+// generateBoundingBox.  One CTA computes a 20x28 tile of output cells at a time; every intermediate lives in shared memory, the
 // only HBM traffic is the input tile and the (rare) candidates.
 //
 // upstream: models/mtcnn.py PNet.forward, models/utils/detect_face.py generateBoundingBox.
@@ -28,19 +28,31 @@
 
 namespace pnet {
 
-constexpr int TOY = 16, TOX = 32;            // output cells per CTA
-constexpr int P1H = TOY + 4, P1W = TOX + 4;  // pooled conv1 tile (20 x 36), flat pixel index n = row * 36 + col
-constexpr int P1PL = 744;                    // pixels per p1 plane: 720 + slack read by conv2's last (partial) M tile; 744 % 32 = 8
+// Tile shape.  Group A's conv1 sets the pace of the kernel and runs one pooled pixel per thread in rounds of 256:
+// 20 x 28 cells need (20 + 4) x (28 + 4) = 768 pooled pixels = exactly three full rounds for 560 cells, and conv3's
+// 20 x 32 flat pixels are exactly five M tiles.  16 x 32 (720 pooled pixels = three rounds, the last one 81 % full, for
+// 512 cells; 4.5 M tiles) measured 10.35-10.6 ms per 450 720p frames against 9.74 ms for 20 x 28.
+#ifndef PNET_TOY
+#define PNET_TOY 20
+#define PNET_TOX 28
+#endif
+constexpr int TOY = PNET_TOY, TOX = PNET_TOX;   // output cells per CTA
+constexpr int P1H = TOY + 4, P1W = TOX + 4;  // pooled conv1 tile (20 x 36), flat pixel index n = row * P1W + col
+constexpr int C2TILES_ = ((TOY + 2) * P1W + 15) / 16;
+// pixels per p1 plane: the tile + slack read by conv2's last (partial) M tile, rounded up to 8 mod 32 (744 for 16 x 32)
+constexpr int P1PL = ((C2TILES_ * 16 + 2 * P1W + 2 - 8 + 31) / 32) * 32 + 8;
+static_assert(P1PL >= P1H * P1W && P1PL >= C2TILES_ * 16 + 2 * P1W + 2, "p1 plane covers the tile and conv2's slack reads");
                                              // spreads the four channel-pair planes a warp reads at once over the banks
 constexpr int P1WORDS = 5;                   // 10 channels = 5 half2 planes [pair][pixel] (hi set, lo set)
-constexpr int C2H = TOY + 2, C2P = 36;       // conv2 tile: 18 rows at the same pitch as its input (flat indexing)
+constexpr int C2H = TOY + 2, C2P = P1W;      // conv2 tile: 18 rows at the same pitch as its input (flat indexing)
 constexpr int C2PX = C2H * C2P;              // 648 pixels (columns 34, 35 of a row are never read)
 constexpr int C2TILES = (C2PX + 15) / 16;    // 41 M tiles of two 8-pixel segments
 // conv2 output = conv3's UMMA A operand: four planes [hi k0, hi k1, lo k0, lo k1] of [pixel][8 channels = 16 B]
 // (no-swizzle K-major core matrices: 8 consecutive pixels x 16 B; k-half stride = plane, 8-pixel stride = 128 B)
-constexpr int C2NP = 720;                    // pixels per plane: 648 computed + slack read by the last (partial) M tile
+constexpr int C3TILES = (TOY * C2P + 127) / 128;   // conv3 M tiles of 128 flat pixels (16 rows x pitch 36 = 576 = 4.5 tiles -> 5)
+constexpr int C2NP = ((C3TILES * 128 + 2 * C2P + 2 + 15) / 16) * 16;   // pixels per plane: computed + slack read by the last (partial) M tile (720 for 16 x 32)
+static_assert(C2NP >= C2PX, "c2 plane covers the conv2 tile");
 constexpr int C2PLANE = C2NP * 4;            // words per plane
-constexpr int C3TILES = 5;                   // conv3 M tiles of 128 flat pixels (16 rows x pitch 36 = 576 = 4.5 tiles)
 constexpr int TMEM_COLS = 512;
 // DEFER_EPILOGUE = true: two accumulator sets of 256 columns (tiles 0-2 x 64, tiles 3-4 x 32 with a third MMA per tap) and
 // the head epilogue of tile k-1 runs under the MMAs of tile k.  Measured slower on B200 (15.1 vs 12.0 ms per 450 frames):
@@ -59,7 +71,8 @@ constexpr int ISSUE_WARP = NA_WARPS + NB_WARPS;
 constexpr int NTHREADS = 32 * (ISSUE_WARP + 1);   // group A warps: staging + conv1, then group B: conv2 + heads, last warp: conv3 MMA issue
 static_assert(NB_WARPS % 4 == 0 && NA_WARPS % 4 == 0, "group B covers the four TMEM lane groups evenly and starts at a multiple of 4");
 constexpr int INH = 2 * TOY + 10, INW = 2 * TOX + 10;   // 42 x 74 input tile
-constexpr int INP = 76;
+constexpr int INP = (INW + 3) / 4 * 4;       // row pitch: 16-byte multiple (76 for 16 x 32)
+static_assert(C3TILES * 64 <= 512, "conv3 accumulators fit TMEM");
 
 constexpr float SA = 64.f;                   // activation scale (p1 and c2 tiles)
 constexpr float ACT_MAX = 1000.f;            // |activation| bound for the fp16 hi part (64 * 1000 < 65504)
@@ -189,12 +202,13 @@ __device__ __forceinline__ TileRef decode_tile(const Params& p, int id) {
   r.lvl = lvl; r.oy0 = ty * TOY; r.ox0 = (tile - ty * p.lv[lvl].tiles_x) * TOX;
   return r;
 }
-// conv2 M tiles per group-B warp (see the conv2 loop), one nibble per warp: 4 4 5 6 5 6 5 6 = 41.  Measured on 450 720p
-// frames: this split 10.35 ms, 3 3 6 6 6 6 6 5 10.36, 4 4 6 6 6 5 5 5 10.51, even 6 5 5 5 5 5 5 5 10.79 (strided even
-// split of the previous version: 10.43) -- a small gain only, because group A's conv1 sets the pace once B is balanced.
+// conv2 M tiles per group-B warp (see the conv2 loop), one nibble per warp, warp 0 lowest: 5 5 5 5 6 6 6 6 = 44 for the
+// 20 x 28 tile (warps 0-3 carry three conv3 head epilogues per tile, warps 4-7 two; the reverse split measured 9.91
+// against 9.74 ms).  On the 16 x 32 tile (41 M tiles) 4 4 5 6 5 6 5 6 gave 10.35 ms, an even split 10.79 ms.
 #ifndef PNET_C2_COUNTS
-#define PNET_C2_COUNTS 0x65656544u
+#define PNET_C2_COUNTS (PNET_TOY == 20 && PNET_TOX == 28 ? 0x66665555u : 0x65656544u)
 #endif
+static_assert(C2TILES_ == (C2PX + 15) / 16, "");
 __host__ __device__ constexpr int c2_count(int warp) { return (int)((PNET_C2_COUNTS >> (4 * warp)) & 0xFu); }
 __host__ __device__ constexpr int c2_first(int warp) {
   int f = 0;
@@ -202,6 +216,12 @@ __host__ __device__ constexpr int c2_first(int warp) {
   return f;
 }
 static_assert(NB_WARPS == 8 && c2_first(NB_WARPS) == C2TILES, "the conv2 tile split covers every M tile once");
+__host__ __device__ constexpr int c2_max_count() {
+  int m = 0;
+  for (int w = 0; w < 8; ++w) m = c2_count(w) > m ? c2_count(w) : m;
+  return m;
+}
+constexpr int C2PASSES = (c2_max_count() + 2) / 3;     // conv2 passes of up to three M tiles per warp
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -480,7 +500,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
 #ifdef PNET_TIMING
         tmma += clock64() - tq;
 #endif
-        if (tile == 4 && lg >= 2) break;              // flat pixels >= 576 do not exist
+        if (tile * 128 + lg * 32 >= TOY * C2P) break;   // flat pixels >= TOY * C2P do not exist (the half tile of 16 x 32)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + tile_col(kk, tile);
       float h[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -570,7 +590,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
     const uint32_t* p1l = p1_s + P1WORDS * P1PL;
     const float inv = w_s[SC + 0];
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < C2PASSES; ++pass) {
       // M tiles c2_first(warp) + 3 pass + q, q < 3.  The 41 tiles are not dealt evenly: warps 0-1 also carry three conv3
       // head epilogues per tile (M tiles 0, 2 and the half tile 4) where the other warps carry two, and the slowest warp
       // of group B sets the pace of the whole CTA, so they get 4 conv2 tiles and the others 6 or 5.
