@@ -266,20 +266,28 @@ class Analyzer:
         return out
 
 
+# tail rule of chunk_schedule (next = SCHED_A * size + SCHED_B frames); environment overrides are for tuning runs only
+SCHED_A = float(os.environ.get("TRL_SCHED_A", 0.6))
+SCHED_B = float(os.environ.get("TRL_SCHED_B", 8))
+SCHED_STEPS = int(os.environ.get("TRL_SCHED_STEPS", 6))
+SCHED_MIN_DIV = int(os.environ.get("TRL_SCHED_MIN_DIV", 4))
+
+
 def chunk_schedule(n: int, chunk: int, ramp: bool = False):
     """[(start, end)] ranges of at most ``chunk`` frames.  With ``ramp`` (host frames: the H2D copy of chunk k+1 overlaps
     the cascade on chunk k) the chunks grow at the start and shrink towards the end: the copy of the first chunk and the
     cascade of the last one are the parts of the pipeline that nothing overlaps.  A cascade costs about
-    0.47 ms + 0.0325 ms/frame and a copy 0.05 ms/frame (720p, B200, experiments/e2e_timeline.py), so a chunk keeps up
-    with the copy of its successor only if the successor is at least ~0.65 of its size + 10 frames: the tail shrinks by
-    that rule (at most five steps, not below a third of a chunk)."""
+    0.4 ms + 0.028 ms/frame and a copy 0.05 ms/frame (720p, B200, experiments/e2e_timeline.py), so a chunk keeps up
+    with the copy of its successor only if the successor is at least ~0.57 of its size + 8 frames: the tail shrinks by
+    next = 0.6 size + 8 (at most six steps, not below a quarter of a chunk; 90 -> 62, 45, 35, 29, 25, 23 frames).
+    Measured on the bench clip: 25.0 ms per 450 frames against 25.4 ms with the earlier 0.65 size + 10 rule."""
     if not ramp or n <= chunk:
         return [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
     head = [max(1, chunk // 4), max(1, chunk // 2)]
     tail, t = [], chunk
     while True:
-        t = int(0.65 * t + 10)
-        if t >= chunk or t < chunk // 3 or (tail and t >= tail[-1]) or len(tail) == 5:
+        t = int(SCHED_A * t + SCHED_B)
+        if t >= chunk or t < chunk // SCHED_MIN_DIV or (tail and t >= tail[-1]) or len(tail) == SCHED_STEPS:
             break
         tail.append(t)
     if sum(head) + sum(tail) + chunk > n:
