@@ -24,6 +24,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# offline there are no upstream weight files: the bench runs on the seeded stand-ins and says so in config.weights
+os.environ.setdefault("TRUELY_ALLOW_SYNTHETIC", "1")
 
 # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on file
 # descriptor 1 when the first communicator is created), so everything that is not the result line goes to stderr.

@@ -62,9 +62,9 @@ typedef struct {
   float thresholds[3];    /* 0.6, 0.7, 0.7 */
   double factor;          /* 0.709 */
   int crop_size;          /* 80: side of the FaceNet input (server/model.py:41) */
-  int cand_cap_scale;     /* capacity: P-Net candidates per (frame, scale) */
-  int cand_cap_frame;     /* capacity: R-Net inputs per frame (candidates surviving stage-1 NMS) */
-  int box_cap_frame;      /* capacity: O-Net inputs / final boxes per frame */
+  int cand_cap_scale;     /* capacity: P-Net candidates per (frame, scale); default 2048, at most 16384 */
+  int cand_cap_frame;     /* capacity: R-Net inputs per frame (candidates surviving stage-1 NMS); default 1024, at most 16384 */
+  int box_cap_frame;      /* capacity: O-Net inputs / final boxes per frame; default 128, at most 2048 */
   int facenet_impl;       /* 0 = tcgen05 implicit-GEMM path (product); 1 = SIMT direct-conv kernels (validation) */
 } trl_config_t;
 
@@ -135,6 +135,31 @@ int trl_consistency(trl_ctx_t* ctx, const float* d_emb, const uint8_t* d_valid, 
                     const uint8_t* d_halo_valid, float thr, float* d_sim, uint8_t* d_below, uint8_t* d_has_sim, float* d_last_emb,
                     uint8_t* d_last_valid, void* stream);
 
+/* K12 for a batch that holds several clips back to back (BASELINE.json configs[4]): d_clip_start uint8 [B] (or NULL =
+ * one clip) marks the first processed frame of every clip.  `previous_face_encoding` is a local of one run() call
+ * (server/model.py:37), so a frame is only compared with a face-bearing frame of its own clip, the incoming halo is used
+ * only for frames of the clip that reaches in from the previous range, and d_last_emb / d_last_valid describe the last
+ * clip of the range.  With d_clip_start == NULL identical to trl_consistency. */
+int trl_consistency_clips(trl_ctx_t* ctx, const float* d_emb, const uint8_t* d_valid, int B, const uint8_t* d_clip_start,
+                          const float* d_halo_emb, const uint8_t* d_halo_valid, float thr, float* d_sim, uint8_t* d_below,
+                          uint8_t* d_has_sim, float* d_last_emb, uint8_t* d_last_valid, void* stream);
+
+/* Frame-range sharding over the GPUs of a box (no counterpart in the single-process reference).
+ * Rank r runs trl_consistency[_clips] on its range WITHOUT a halo, condenses the result into a fixed-size record
+ * (trl_shard_pack: per-frame flags valid / has_sim / below, the embedding of the first frame still waiting for a
+ * predecessor and the outgoing halo), the host all-gathers the records of all ranks with ONE collective
+ * (world * trl_shard_record_bytes(n_max) bytes, n_max = the largest local range), and trl_shard_resolve finishes the
+ * comparisons that cross shard boundaries on the gathered buffer -- exact across shards without a face and across clip
+ * boundaries -- patching the per-frame flags of every rank's section and this rank's local d_sim / d_below / d_has_sim
+ * (any of which may be NULL).  Layout of a record: int32 hdr[8] = {n_local, first_idx, last_has, blocked, 0...},
+ * float first_emb[512], float last_emb[512], uint8 flags[3][n_pad] (valid, has_sim, below; n_pad = n_max rounded up to
+ * 16).  d_record / d_all_records must be 16-byte aligned device memory. */
+size_t trl_shard_record_bytes(int n_max);
+int trl_shard_pack(trl_ctx_t* ctx, const float* d_emb, const uint8_t* d_valid, const uint8_t* d_has_sim, const uint8_t* d_below,
+                   const uint8_t* d_clip_start, int n_local, int n_max, void* d_record, void* stream);
+int trl_shard_resolve(trl_ctx_t* ctx, void* d_all_records, int world, int rank, int n_max, float thr, float* d_sim,
+                      uint8_t* d_below, uint8_t* d_has_sim, void* stream);
+
 /* The fused per-batch hot path: detect -> crop-align -> facenet (valid frames only) -> consistency.
  * Equivalent to the body of the reference loop (server/model.py:47-65) for B processed frames. */
 int trl_process(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, const float* d_halo_emb,
@@ -162,6 +187,13 @@ int trl_pipeline_join(trl_ctx_t* ctx, void* stream);
 /* After the stream has been synchronised by the caller: TRL_E_CAPACITY if any candidate buffer overflowed
  * since the last check (h_detail, optional int32[4]: which stage, frame, count, capacity). */
 int trl_check_capacity(trl_ctx_t* ctx, int* h_detail);
+
+/* Changes the candidate capacities of a live context (the workspace is released and re-allocated by the next call;
+ * this synchronises the device: slow path).  cand_cap_scale / cand_cap_frame up to 16384 -- groups above 2048 candidates
+ * then run through a global-memory NMS instead of the shared-memory one -- box_cap_frame up to 2048.  Upstream
+ * detect_face has no cap at all: a host that sees TRL_E_CAPACITY raises the capacities, re-runs the affected frames one
+ * at a time and restores the fast-path capacities (model.analyze_stream does this). */
+int trl_set_capacity(trl_ctx_t* ctx, int cand_cap_scale, int cand_cap_frame, int box_cap_frame);
 
 /* Per-stage device timing of trl_process (measurement only; off by default).  With profiling on, CUDA events are
  * recorded on the launching stream around each stage; trl_read_stage_times (after the caller synchronised the

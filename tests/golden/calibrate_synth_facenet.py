@@ -20,6 +20,8 @@ from __future__ import annotations
 import os
 import sys
 
+os.environ.setdefault("TRUELY_ALLOW_SYNTHETIC", "1")
+
 import cv2
 import numpy as np
 import torch

@@ -9,6 +9,8 @@ Run:  python tests/golden/make_golden.py
 import os
 import sys
 
+os.environ.setdefault("TRUELY_ALLOW_SYNTHETIC", "1")
+
 import numpy as np
 import torch
 

@@ -16,6 +16,8 @@ from __future__ import annotations
 
 import os
 import sys
+
+os.environ.setdefault("TRUELY_ALLOW_SYNTHETIC", "1")
 import time
 
 import cv2

@@ -97,3 +97,36 @@ def box_iou(a, b):
     inter = max(0.0, x2 - x1) * max(0.0, y2 - y1)
     ua = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
     return inter / ua if ua > 0 else 0.0
+
+
+def assert_flags_match_outside_band(valid, sim, flagged, score, frame_count, stride, fps, ref_valid, ref_sim, ref_flagged,
+                                    ref_score, thr: float = 0.99, band: float = 1e-3):
+    """BASELINE.json tolerance: 'identical flagged-frame set except frames whose distance lies within 1e-3 of the
+    threshold'.  Only the `sim < thr` decision of an in-band frame is free; everything else must be identical.  The
+    run-length counter couples frames, so the check replays the reference's machine (server/model.py:62-70) on the
+    reference decisions with the in-band ones replaced by the tested path's, and requires the tested flagged list and
+    score to equal that replay exactly.  With no in-band frame this is plain equality with the reference.
+    Returns the number of in-band frames (never skips an assertion)."""
+    from truely_b200.model import RunLength, final_score
+    assert [bool(v) for v in valid] == [bool(v) for v in ref_valid], "face-bearing frames differ"
+    rl = RunLength()
+    replay, n_band = [], 0
+    for k in range(len(ref_valid)):
+        if not ref_valid[k] or ref_sim[k] is None:
+            assert sim[k] is None or (isinstance(sim[k], float) and np.isnan(sim[k])), f"frame {k}: unexpected comparison"
+            replay.append(False)
+            continue
+        assert sim[k] is not None, f"frame {k}: comparison missing"
+        below_ref, below_got = ref_sim[k] < thr, sim[k] < thr
+        if abs(ref_sim[k] - thr) < band:
+            n_band += 1
+            decision = below_got
+        else:
+            assert below_got == below_ref, f"frame {k}: sim {sim[k]} vs reference {ref_sim[k]} on different sides of {thr}"
+            decision = below_ref
+        replay.append(rl.step(bool(decision)))
+    assert [bool(f) for f in flagged] == replay, "flagged-frame set differs outside the tolerance band"
+    assert score == final_score(rl.deep_fake_frame_count, rl.deepfake_count, frame_count, fps, stride)
+    if n_band == 0:
+        assert replay == [bool(f) for f in ref_flagged] and score == ref_score
+    return n_band

@@ -121,3 +121,141 @@ def test_chunk_schedule_covers_every_frame_once():
     assert sz[0] == 22 and 90 // 4 <= sz[-1] < 45                       # short first copy, last cascade on a quarter of a chunk
     k = sz.index(max(sz))
     assert all(sz[i] >= sz[i + 1] for i in range(k, len(sz) - 1))       # after the full-size chunks the tail only shrinks
+
+
+def test_synthetic_weights_are_opt_in(monkeypatch, tmp_path):
+    """run() must never score a video with stand-in networks silently.  Without upstream files and
+    without TRUELY_ALLOW_SYNTHETIC=1 the loaders raise; an installed facenet_pytorch wheel's data/ dir is searched."""
+    monkeypatch.setenv("TRUELY_WEIGHTS_DIR", str(tmp_path))          # empty
+    monkeypatch.setenv("TORCH_HOME", str(tmp_path / "torch_home"))   # empty
+    monkeypatch.delenv("TRUELY_ALLOW_SYNTHETIC", raising=False)
+    with pytest.raises(W.MissingWeightsError):
+        W.load_mtcnn_state()
+    with pytest.raises(W.MissingWeightsError):
+        W.load_facenet_state()
+    monkeypatch.setenv("TRUELY_ALLOW_SYNTHETIC", "1")
+    assert W.load_mtcnn_state()[1] == "synthetic" and W.load_facenet_state()[1] == "synthetic"
+    # upstream-format files are picked up: two of three MTCNN nets present is still "missing" (no half-upstream cascade)
+    state, _ = W.load_mtcnn_state()
+    for net in ("pnet", "rnet"):
+        torch.save({k[len(net) + 1:]: torch.from_numpy(v) for k, v in state.items() if k.startswith(net + ".")},
+                   str(tmp_path / f"{net}.pt"))
+    monkeypatch.delenv("TRUELY_ALLOW_SYNTHETIC", raising=False)
+    with pytest.raises(W.MissingWeightsError) as e:
+        W.load_mtcnn_state()
+    assert "onet.pt" in str(e.value)
+    torch.save({k[5:]: torch.from_numpy(v) for k, v in state.items() if k.startswith("onet.")}, str(tmp_path / "onet.pt"))
+    got, src = W.load_mtcnn_state()
+    assert src == "upstream" and all(np.array_equal(got[k], state[k]) for k in state)
+    # an installed facenet_pytorch wheel keeps {p,r,o}net.pt in <package>/data: that directory is on the search path
+    pkg = tmp_path / "site" / "facenet_pytorch"
+    (pkg / "data").mkdir(parents=True)
+    (pkg / "__init__.py").write_text("")
+    monkeypatch.syspath_prepend(str(tmp_path / "site"))
+    import importlib
+    importlib.invalidate_caches()
+    assert str(pkg / "data") in W._weights_dirs()
+
+
+def test_annotation_pixels_equal_the_reference_drawing():
+    """a12 (server/model.py:66-74): model.annotate_frame draws exactly what the reference loop draws -- checked by running
+    the oracle loop with stub models that dictate box and similarity, annotate=True, against annotate_frame on copies."""
+    rng = np.random.default_rng(3)
+    frames = [rng.integers(0, 256, size=(120, 160, 3), dtype=np.uint8) for _ in range(40)]
+    boxes = [np.array([20 + k % 7, 30 + k % 5, 90 + k % 11, 100 + k % 3], np.float32) for k in range(40)]
+
+    class StubMtcnn:
+        k = 0
+
+        def detect(self, frame):
+            b = boxes[self.k][None]
+            self.k += 1
+            return b, np.array([0.99], np.float32)
+
+    class StubFacenet:
+        """alternating embeddings: every comparison is far below 0.99 -> the run passes 15 and frames get flagged"""
+        k = 0
+
+        def __call__(self, x):
+            e = torch.zeros(1, 512)
+            e[0, self.k % 2] = 1.0
+            self.k += 1
+            return e
+
+    class Sink:
+        def __init__(self):
+            self.frames = []
+
+        def write(self, f):
+            self.frames.append(f.copy())
+
+    sink = Sink()
+    ref = R.reference_run_frames(iter([f.copy() for f in frames]), 7, 160, 120, StubMtcnn(), StubFacenet(), writer=sink, annotate=True)
+    assert sum(f.flagged for f in ref.frames) > 0 and sum((not f.flagged) and f.sim is not None for f in ref.frames) > 0
+    for k, ft in enumerate(ref.frames):
+        mine = frames[k].copy()
+        if ft.sim is not None:
+            M.annotate_frame(mine, ft.box, ft.flagged, ft.frame_index)
+        assert np.array_equal(mine, sink.frames[k]), f"frame {k}: annotated pixels differ"
+
+
+def test_score_clips_equals_per_clip_scores():
+    rng = np.random.default_rng(11)
+    lens = [40, 1, 75, 0, 33]
+    clips = [(m, 8 * m) for m in lens]
+    n = sum(lens)
+    valid = (rng.random(n) > 0.1).astype(np.uint8)
+    below = (rng.random(n) > 0.2).astype(np.uint8)
+    has = valid.copy()
+    a = 0
+    for m in lens:                       # a clip's first face-bearing frame has nothing to compare with
+        idx = np.flatnonzero(valid[a:a + m])
+        if len(idx):
+            has[a + idx[0]] = 0
+        a += m
+    scores, flagged = M.score_clips(valid, has, below, clips, 60, 8)
+    a = 0
+    for i, m in enumerate(lens):
+        sc, fl, _ = M.score_from_flags(valid[a:a + m], has[a:a + m], below[a:a + m], 8 * m, 60, 8)
+        assert scores[i] == sc and flagged[a:a + m] == fl
+        a += m
+    assert M.clip_start_mask(clips).tolist() == [1 if i in (0, 40, 41, 116) else 0 for i in range(n)]
+    with pytest.raises(ValueError):
+        M.score_clips(valid[:-1], has[:-1], below[:-1], clips, 60, 8)
+
+
+def test_shard_record_layout_agrees_with_the_library():
+    from truely_b200 import dist as D
+    lib = L.load()
+    for n_max in (0, 1, 15, 16, 17, 451, 2401):
+        assert lib.trl_shard_record_bytes(n_max) == D.record_bytes(n_max)
+        assert D.record_bytes(n_max) % 16 == 0
+
+
+def test_flag_comparison_helper_only_frees_in_band_decisions():
+    import helpers as Hh
+    rng = np.random.default_rng(0)
+    n = 200
+    valid = [True] * n
+    ref_sim = [None] + [float(rng.choice([0.95, 0.995, 0.9895])) for _ in range(n - 1)]
+
+    def machine(sims):
+        rl, fl = M.RunLength(), [False]
+        for s in sims[1:]:
+            fl.append(rl.step(s < 0.99))
+        return fl, M.final_score(rl.deep_fake_frame_count, rl.deepfake_count, n * 4, 30, 4)
+
+    fl, sc = machine(ref_sim)
+    assert Hh.assert_flags_match_outside_band(valid, ref_sim, fl, sc, n * 4, 4, 30, valid, ref_sim, fl, sc) > 0
+    moved = [None] + [(s + 0.001 if abs(s - 0.99) < 1e-3 else s) for s in ref_sim[1:]]      # in-band frames flip side
+    fl2, sc2 = machine(moved)
+    assert fl2 != fl
+    Hh.assert_flags_match_outside_band(valid, moved, fl2, sc2, n * 4, 4, 30, valid, ref_sim, fl, sc)
+    with pytest.raises(AssertionError):                                                      # flags not following the sims
+        Hh.assert_flags_match_outside_band(valid, moved, fl, sc2, n * 4, 4, 30, valid, ref_sim, fl, sc)
+    far = list(ref_sim)
+    far[5] = 0.5 if ref_sim[5] > 0.99 else 0.999                                            # an out-of-band flip
+    fl3, sc3 = machine(far)
+    if abs(ref_sim[5] - 0.99) >= 1e-3:
+        with pytest.raises(AssertionError):
+            Hh.assert_flags_match_outside_band(valid, far, fl3, sc3, n * 4, 4, 30, valid, ref_sim, fl, sc)

@@ -178,3 +178,24 @@ def test_bf16_storage_keeps_embeddings_within_tolerance():
             e16 = fn(x).numpy()
     for a, b in zip(e32, e16):
         assert H.cosine(a, b) > 0.9995
+
+
+def test_bundled_clip_golden_pins_the_oracle():
+    """BASELINE.json configs[0]: the reference's bundled clip (fixture copy, tests/golden/make_bundled_golden.py).  The
+    oracle, re-run here on the first 20 processed frames of the same OpenCV decode, reproduces the committed trace."""
+    import cv2
+    from oracle.reference_run import reference_run
+    gold_dir = os.path.join(os.path.dirname(__file__), "golden")
+    g = np.load(os.path.join(gold_dir, "bundled_clip_run.npz"))
+    assert int(g["frame_count"]) == 960 and len(g["frame_index"]) == 240 and int(g["stride"]) == 4
+    assert (int(g["width"]), int(g["height"]), int(g["fps"])) == (640, 360, 30)
+    tr = reference_run(os.path.join(gold_dir, "bundled_veo3_360p.mp4"), None, H.oracle_mtcnn(), H.oracle_facenet(), max_frames=80)
+    assert len(tr.frames) == 20
+    for k, f in enumerate(tr.frames):
+        assert f.frame_index == int(g["frame_index"][k]) and f.n_faces == int(g["n_faces"][k])
+        assert f.embedded == bool(g["embedded"][k])
+        if f.embedded:
+            assert np.array_equal(f.box, g["box"][k])
+            assert np.allclose(f.emb, g["emb"][k], atol=2e-5)
+            if f.sim is not None:
+                assert abs(f.sim - float(g["sim"][k])) < 1e-5

@@ -52,10 +52,15 @@ SIGNATURES = {
     "trl_crop_align": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
     "trl_facenet": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "trl_consistency": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P]),
+    "trl_consistency_clips": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P]),
+    "trl_shard_record_bytes": (C.c_size_t, [C.c_int]),
+    "trl_shard_pack": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "trl_shard_resolve": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P]),
     "trl_process": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trl_detect_align": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "trl_detect_align_async": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "trl_pipeline_join": (C.c_int, [_P, _P]),
+    "trl_set_capacity": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "trl_check_capacity": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "trl_launch_count": (C.c_longlong, [_P]),
     "trl_set_profiling": (C.c_int, [_P, C.c_int]),

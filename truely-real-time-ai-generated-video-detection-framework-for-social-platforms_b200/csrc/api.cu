@@ -66,15 +66,23 @@ int trl_host_free(void* p) {
   return cudaFreeHost(p) == cudaSuccess ? TRL_OK : TRL_E_CUDA;
 }
 
+// P-Net / R-Net candidate lists may be raised up to the global-memory NMS limit (16384 per group); the final box list
+// stays within the shared-memory limit (its epilogue ranks the boxes by area in O(n^2)).
+static bool capacities_ok(int cap_scale, int cap_frame, int box_cap) {
+  return cap_scale >= 1 && cap_frame >= 1 && box_cap >= 1 && cap_scale <= nms_big_max_n() && cap_frame <= nms_big_max_n() &&
+         box_cap <= nms_max_n();
+}
+
 static void free_workspace(trl_ctx* c) {
   void* ptrs[] = {c->d_pyr, c->d_cand1, c->d_cnt1, c->d_cand2, c->d_cnt2, c->d_cand3, c->d_cnt3, c->d_pad3, c->d_rin,
                   c->d_cand4, c->d_cnt4, c->d_pad4, c->d_oin, c->d_rprob, c->d_rreg, c->d_oprob, c->d_oreg,
-                  c->d_boxes, c->d_nfaces, c->d_crops};
+                  c->d_boxes, c->d_nfaces, c->d_crops, c->d_nms_big};
   for (void* p : ptrs) if (p) cudaFree(p);
   c->d_pyr = nullptr; c->d_cand1 = nullptr; c->d_cnt1 = nullptr; c->d_cand2 = nullptr; c->d_cnt2 = nullptr;
   c->d_cand3 = nullptr; c->d_cnt3 = nullptr; c->d_pad3 = nullptr; c->d_rin = nullptr; c->d_cand4 = nullptr;
   c->d_cnt4 = nullptr; c->d_pad4 = nullptr; c->d_oin = nullptr; c->d_rprob = nullptr; c->d_rreg = nullptr;
   c->d_oprob = nullptr; c->d_oreg = nullptr; c->d_boxes = nullptr; c->d_nfaces = nullptr; c->d_crops = nullptr;
+  c->d_nms_big = nullptr;
   c->ws_B = c->ws_H = c->ws_W = 0;
 }
 
@@ -109,9 +117,9 @@ int trl_create(int device, const trl_weights_t* w, const trl_config_t* cfg, trl_
   c->device = device;
   if (cfg) c->cfg = *cfg; else trl_default_config(&c->cfg);
   auto fail = [&](int rc) { g_create_err = c->err; trl_destroy(c); return rc; };
-  if (c->cfg.cand_cap_scale > nms_max_n() || c->cfg.cand_cap_frame > nms_max_n() || c->cfg.box_cap_frame > nms_max_n() ||
-      c->cfg.cand_cap_scale < 1 || c->cfg.cand_cap_frame < 1 || c->cfg.box_cap_frame < 1) {
-    c->err = "trl_create: candidate capacities must be in [1, 2048]";
+  if (!capacities_ok(c->cfg.cand_cap_scale, c->cfg.cand_cap_frame, c->cfg.box_cap_frame)) {
+    c->err = "trl_create: candidate capacities must be in [1, " + std::to_string(nms_big_max_n()) + "], box_cap_frame in [1, " +
+             std::to_string(nms_max_n()) + "]";
     return fail(TRL_E_INVALID);
   }
   if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(TRL_E_CUDA); }
@@ -229,6 +237,11 @@ static int ensure_workspace(trl_ctx* c, int B, int H, int W) {
   WS_ALLOC(c->d_boxes, (size_t)Bc * c4 * 5 * sizeof(float));
   WS_ALLOC(c->d_nfaces, (size_t)Bc * sizeof(int));
   WS_ALLOC(c->d_crops, (size_t)Bc * S * S * 3 + 256);
+  {
+    const int cmax = (int)(c1 > c2 ? c1 : c2);
+    const size_t big = nms_big_scratch_bytes(Bc * g.n, cmax);
+    if (big) WS_ALLOC(c->d_nms_big, big);
+  }
   c->ws_B = Bc; c->ws_H = H; c->ws_W = W;
   return TRL_OK;
 }
@@ -342,9 +355,41 @@ int trl_consistency(trl_ctx_t* c, const float* d_emb, const uint8_t* d_valid, in
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
   if ((rc = join_tail(c, s)) != TRL_OK) return rc;
-  TIMED(12, launch_consistency(c, d_emb, d_valid, B, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
+  TIMED(12, launch_consistency(c, d_emb, d_valid, B, nullptr, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
                                d_last_valid, s));
   return TRL_OK;
+}
+
+int trl_consistency_clips(trl_ctx_t* c, const float* d_emb, const uint8_t* d_valid, int B, const uint8_t* d_clip_start,
+                          const float* d_halo_emb, const uint8_t* d_halo_valid, float thr, float* d_sim, uint8_t* d_below,
+                          uint8_t* d_has_sim, float* d_last_emb, uint8_t* d_last_valid, void* stream) {
+  if (!c || !d_emb || !d_valid || !d_sim || !d_below || !d_has_sim) return TRL_E_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if ((rc = join_tail(c, s)) != TRL_OK) return rc;
+  TIMED(12, launch_consistency(c, d_emb, d_valid, B, d_clip_start, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim,
+                               d_last_emb, d_last_valid, s));
+  return TRL_OK;
+}
+
+size_t trl_shard_record_bytes(int n_max) { return n_max < 0 ? 0 : shard_record_size(n_max); }
+
+int trl_shard_pack(trl_ctx_t* c, const float* d_emb, const uint8_t* d_valid, const uint8_t* d_has_sim, const uint8_t* d_below,
+                   const uint8_t* d_clip_start, int n_local, int n_max, void* d_record, void* stream) {
+  if (!c || !d_record || n_local < 0 || n_local > n_max) return TRL_E_INVALID;
+  if (n_local > 0 && (!d_emb || !d_valid || !d_has_sim || !d_below)) return TRL_E_INVALID;
+  if ((reinterpret_cast<uintptr_t>(d_record) & 15) != 0) TRL_FAIL(c, TRL_E_INVALID, "trl_shard_pack: record must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = join_tail(c, s);
+  if (rc != TRL_OK) return rc;
+  return launch_shard_pack(c, d_emb, d_valid, d_has_sim, d_below, d_clip_start, n_local, n_max, (unsigned char*)d_record, s);
+}
+
+int trl_shard_resolve(trl_ctx_t* c, void* d_all_records, int world, int rank, int n_max, float thr, float* d_sim,
+                      uint8_t* d_below, uint8_t* d_has_sim, void* stream) {
+  if (!c || !d_all_records || world < 1 || rank < 0 || rank >= world || n_max < 0) return TRL_E_INVALID;
+  return launch_shard_resolve(c, (unsigned char*)d_all_records, world, rank, n_max, thr, d_sim, d_below, d_has_sim,
+                              (cudaStream_t)stream);
 }
 
 int trl_detect_align(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, int* d_box_int, uint8_t* d_valid,
@@ -389,6 +434,17 @@ int trl_detect_align_async(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, 
   return TRL_OK;
 }
 
+int trl_set_capacity(trl_ctx_t* c, int cand_cap_scale, int cand_cap_frame, int box_cap_frame) {
+  if (!c) return TRL_E_INVALID;
+  if (!capacities_ok(cand_cap_scale, cand_cap_frame, box_cap_frame))
+    TRL_FAIL(c, TRL_E_INVALID, "trl_set_capacity: capacities must be in [1, %d] (box_cap_frame: [1, %d])", nms_big_max_n(), nms_max_n());
+  if (c->tail_stream) TRL_CUDA(c, cudaStreamSynchronize(c->tail_stream));
+  free_workspace(c);                        // cudaFree waits for outstanding work that may still use the old workspace (slow path)
+  c->tail_pending = false;
+  c->cfg.cand_cap_scale = cand_cap_scale; c->cfg.cand_cap_frame = cand_cap_frame; c->cfg.box_cap_frame = box_cap_frame;
+  return TRL_OK;
+}
+
 int trl_pipeline_join(trl_ctx_t* c, void* stream) {
   if (!c) return TRL_E_INVALID;
   return join_tail(c, (cudaStream_t)stream);
@@ -406,7 +462,7 @@ int trl_process(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, cons
   // FaceNet runs on all B crops (faceless frames carry a zero crop; their embeddings are never compared):
   // this keeps the whole batch free of host synchronisation.
   TIMED(11, facenet_forward(c, c->d_crops, B, c->cfg.crop_size, d_emb, s));
-  TIMED(12, launch_consistency(c, d_emb, d_valid, B, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
+  TIMED(12, launch_consistency(c, d_emb, d_valid, B, nullptr, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
                                d_last_valid, s));
   return TRL_OK;
 }

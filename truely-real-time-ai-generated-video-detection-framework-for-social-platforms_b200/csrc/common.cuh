@@ -193,6 +193,8 @@ struct trl_ctx {
 
   // scratch for the stand-alone trl_nms entry point
   Cand* d_nms_tmp = nullptr; int nms_tmp_cap = 0;
+  // global-memory scratch of cascade_nms_big_kernel (allocated with the workspace only when a capacity exceeds 2048)
+  unsigned char* d_nms_big = nullptr;
 };
 
 #define TRL_FAIL(ctx, code, ...)                                   \
@@ -244,6 +246,8 @@ int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, float* d_e
 
 int nms_init(trl_ctx* c);
 int nms_max_n();
+int nms_big_max_n();
+size_t nms_big_scratch_bytes(int groups, int cap);
 int launch_plain_nms(trl_ctx* c, const float* d_boxes, const float* d_scores, int n, float thr, int mode, int* d_keep,
                      int* d_nkeep, cudaStream_t s);
 int launch_cascade_stage(trl_ctx* c, int stage, const nms::StageParams& p, int B, cudaStream_t s);
@@ -254,7 +258,12 @@ int launch_rnet_ex(trl_ctx* c, const float* d_in, int n_slots, const int* d_coun
 int launch_onet_ex(trl_ctx* c, const float* d_in, int n_slots, const int* d_count, int per_frame_cap, float* d_prob,
                    float* d_reg, cudaStream_t s);
 
-int launch_consistency(trl_ctx* c, const float* d_emb, const uint8_t* d_valid, int B, const float* d_halo,
-                       const uint8_t* d_halo_valid, float thr,
+int launch_consistency(trl_ctx* c, const float* d_emb, const uint8_t* d_valid, int B, const uint8_t* d_clip_start,
+                       const float* d_halo, const uint8_t* d_halo_valid, float thr,
                        float* d_sim, uint8_t* d_below, uint8_t* d_has_sim, float* d_last_emb, uint8_t* d_last_valid,
                        cudaStream_t s);
+size_t shard_record_size(int n_max);
+int launch_shard_pack(trl_ctx* c, const float* d_emb, const uint8_t* d_valid, const uint8_t* d_has_sim, const uint8_t* d_below,
+                      const uint8_t* d_clip_start, int n_local, int n_max, unsigned char* d_record, cudaStream_t s);
+int launch_shard_resolve(trl_ctx* c, unsigned char* d_all, int world, int my_rank, int n_max, float thr, float* d_sim,
+                         uint8_t* d_below, uint8_t* d_has_sim, cudaStream_t s);

@@ -5,6 +5,10 @@
 //   mode 0  torchvision.ops.nms : stable sort by score descending, area (x2-x1)(y2-y1), suppress IoU > thr
 //   mode 1  nms_numpy(.., 'Min'): argsort ascending taken from the back (ties: later index first),
 //           area (x2-x1+1)(y2-y1+1), overlap inter/min(area), keep o <= thr
+// Groups of up to MAXN = 2048 candidates run entirely in shared memory (the product path: capacities <= 2048).  When the
+// host raises the capacities beyond that (trl_set_capacity, the overflow-retry path of model.analyze_stream: upstream
+// detect_face has no cap at all), groups with more than MAXN live candidates are handled by cascade_nms_big_kernel, the
+// same algorithm with its arrays in a global-memory scratch region (up to BIGN = 16384 per group).
 // Box arithmetic is written with explicit round-to-nearest intrinsics so that nvcc cannot contract a*b+c into an FMA:
 // the reference evaluates every product and sum as a separate fp32 op, and pad() truncates the result to pixels.
 #include "common.cuh"
@@ -12,6 +16,7 @@
 namespace nms {
 
 constexpr int MAXN = 2048;
+constexpr int BIGN = 16384;   // largest group the global-memory variant accepts
 constexpr int THREADS = 512;
 constexpr int PER_T = MAXN / THREADS;
 
@@ -184,6 +189,75 @@ __device__ __forceinline__ void flag_overflow(CapFlag* f, int stage, int frame, 
 }
 
 
+// Epilogue of one cascade stage, shared by the shared-memory and the global-memory kernels: kept[0..nkeep) = sorted
+// positions in pick order, sslot = sorted position -> input slot, sbox = sorted boxes, sscore = score by input slot.
+template <int STAGE>
+__device__ __forceinline__ void stage_epilogue(const StageParams& p, int b, int lvl, int seg, const Cand* in, int nkeep,
+                                               const int* kept, const int* sslot, const float4* sbox, const float* sscore,
+                                               int* s_base) {
+  const int tid = threadIdx.x;
+  if (STAGE == 1) {
+    if (tid == 0) (*s_base) = atomicAdd(&p.cnt_out[b], nkeep);
+    __syncthreads();
+    const int base = (*s_base);
+    if (base + nkeep > p.cap_out && tid == 0) flag_overflow(p.capflag, 2, b, base + nkeep, p.cap_out);
+    for (int r = tid; r < nkeep; r += THREADS) {
+      if (base + r >= p.cap_out) break;
+      const int sp = kept[r];
+      Cand c = in[sslot[sp]];
+      c.key = ((uint32_t)lvl << 16) | (uint32_t)r;   // position in upstream's concatenated scale_picks list
+      p.out[(size_t)b * p.cap_out + base + r] = c;
+    }
+  } else if (STAGE == 2 || STAGE == 3) {
+    if (nkeep > p.cap_out && tid == 0) flag_overflow(p.capflag, STAGE == 2 ? 2 : 3, b, nkeep, p.cap_out);
+    const int nk = min(nkeep, p.cap_out);
+    for (int r = tid; r < nk; r += THREADS) {
+      const int sp = kept[r];
+      const int slot = sslot[sp];
+      const float4 bx = sbox[sp];
+      float4 q;
+      if (STAGE == 2) {
+        const Cand c = in[slot];
+        const float regw = __fsub_rn(bx.z, bx.x), regh = __fsub_rn(bx.w, bx.y);
+        q.x = __fadd_rn(bx.x, __fmul_rn(c.r0, regw));
+        q.y = __fadd_rn(bx.y, __fmul_rn(c.r1, regh));
+        q.z = __fadd_rn(bx.z, __fmul_rn(c.r2, regw));
+        q.w = __fadd_rn(bx.w, __fmul_rn(c.r3, regh));
+      } else {
+        const float* rg = p.reg + ((size_t)seg * p.cap_in + slot) * 4;
+        q = bbreg_plus1(bx, rg[0], rg[1], rg[2], rg[3]);
+      }
+      q = rerec(q);
+      Cand o;
+      o.x1 = q.x; o.y1 = q.y; o.x2 = q.z; o.y2 = q.w;
+      o.score = sscore[slot];
+      o.r0 = o.r1 = o.r2 = o.r3 = 0.f;
+      o.key = (uint32_t)r;
+      p.out[(size_t)b * p.cap_out + r] = o;
+      pad_box(q, p.W, p.H, p.pad_out + ((size_t)b * p.cap_out + r) * 4);
+    }
+    if (tid == 0) p.cnt_out[b] = nk;
+  } else {   // STAGE 4
+    const int nk = min(nkeep, p.cap_out);
+    if (nkeep > p.cap_out && tid == 0) flag_overflow(p.capflag, 4, b, nkeep, p.cap_out);
+    // MTCNN.detect select_largest: order = argsort(area)[::-1]  (ties: later pick index first)
+    for (int r = tid; r < nk; r += THREADS) {
+      const float4 bx = sbox[kept[r]];
+      const float ar = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+      int pos = 0;
+      for (int q = 0; q < nk; ++q) {
+        const float4 bq = sbox[kept[q]];
+        const float aq = __fmul_rn(__fsub_rn(bq.z, bq.x), __fsub_rn(bq.w, bq.y));
+        pos += (aq > ar || (aq == ar && q > r)) ? 1 : 0;
+      }
+      float* o = p.boxes_out + ((size_t)b * p.cap_out + pos) * 5;
+      o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+      o[4] = sscore[sslot[kept[r]]];
+    }
+    if (tid == 0) p.cnt_out[b] = nk;
+  }
+}
+
 // STAGE 1: per (frame, level) NMS 0.5 on P-Net candidates -> append to the frame list
 // STAGE 2: per frame NMS 0.7 across levels -> stage-1 regression, rerec, pad  (R-Net inputs)
 // STAGE 3: per frame: R-Net score > thr, NMS 0.7 -> bbreg, rerec, pad         (O-Net inputs)
@@ -199,6 +273,7 @@ __global__ void __launch_bounds__(THREADS) cascade_nms_kernel(const StageParams 
   const int seg = (STAGE == 1) ? b * p.n_levels + lvl : b;
   int n = p.cnt_in[seg];
   if (n > p.cap_in) n = p.cap_in;   // overflow already flagged by the producer
+  if (n > MAXN) return;             // raised capacities only: cascade_nms_big_kernel owns this group
   const Cand* in = p.in + (size_t)seg * p.cap_in;
 
   float4 mybox[PER_T];
@@ -244,66 +319,137 @@ __global__ void __launch_bounds__(THREADS) cascade_nms_kernel(const StageParams 
   }
   __syncthreads();
 
-  if (STAGE == 1) {
-    if (tid == 0) sm.base = atomicAdd(&p.cnt_out[b], nkeep);
-    __syncthreads();
-    const int base = sm.base;
-    if (base + nkeep > p.cap_out && tid == 0) flag_overflow(p.capflag, 2, b, base + nkeep, p.cap_out);
-    for (int r = tid; r < nkeep; r += THREADS) {
-      if (base + r >= p.cap_out) break;
-      const int sp = sm.kept[r];
-      Cand c = in[sm.sslot[sp]];
-      c.key = ((uint32_t)lvl << 16) | (uint32_t)r;   // position in upstream's concatenated scale_picks list
-      p.out[(size_t)b * p.cap_out + base + r] = c;
-    }
-  } else if (STAGE == 2 || STAGE == 3) {
-    if (nkeep > p.cap_out && tid == 0) flag_overflow(p.capflag, STAGE == 2 ? 2 : 3, b, nkeep, p.cap_out);
-    const int nk = min(nkeep, p.cap_out);
-    for (int r = tid; r < nk; r += THREADS) {
-      const int sp = sm.kept[r];
-      const int slot = sm.sslot[sp];
-      const float4 bx = sm.sbox[sp];
-      float4 q;
-      if (STAGE == 2) {
-        const Cand c = in[slot];
-        const float regw = __fsub_rn(bx.z, bx.x), regh = __fsub_rn(bx.w, bx.y);
-        q.x = __fadd_rn(bx.x, __fmul_rn(c.r0, regw));
-        q.y = __fadd_rn(bx.y, __fmul_rn(c.r1, regh));
-        q.z = __fadd_rn(bx.z, __fmul_rn(c.r2, regw));
-        q.w = __fadd_rn(bx.w, __fmul_rn(c.r3, regh));
-      } else {
-        const float* rg = p.reg + ((size_t)seg * p.cap_in + slot) * 4;
-        q = bbreg_plus1(bx, rg[0], rg[1], rg[2], rg[3]);
+  stage_epilogue<STAGE>(p, b, lvl, seg, in, nkeep, sm.kept, sm.sslot, sm.sbox, sscore, &sm.base);
+}
+
+// ---- global-memory variant for groups of MAXN < n <= BIGN candidates (raised capacities, see the file header).
+// Same rank sort + blocked greedy NMS, arrays in a per-group scratch region instead of shared memory.
+struct BigScratch {       // one group's arrays, each `cap` entries
+  unsigned long long* key;   // by input slot
+  float4* ubox;              // by input slot
+  float* uscore;             // by input slot
+  float4* sbox;              // sorted
+  float* sarea;
+  int* sslot;
+  int* kept;
+  unsigned char* removed;
+};
+constexpr size_t BIG_BYTES_PER_ENTRY = 64;   // 8 + 16 + 4 + 16 + 4 + 4 + 4 + 1, rounded up
+__device__ __forceinline__ BigScratch big_scratch(unsigned char* base, int group, int cap) {
+  unsigned char* q = base + (size_t)group * cap * BIG_BYTES_PER_ENTRY;
+  BigScratch g;
+  g.ubox = reinterpret_cast<float4*>(q);                 q += (size_t)cap * 16;
+  g.sbox = reinterpret_cast<float4*>(q);                 q += (size_t)cap * 16;
+  g.key = reinterpret_cast<unsigned long long*>(q);      q += (size_t)cap * 8;
+  g.uscore = reinterpret_cast<float*>(q);                q += (size_t)cap * 4;
+  g.sarea = reinterpret_cast<float*>(q);                 q += (size_t)cap * 4;
+  g.sslot = reinterpret_cast<int*>(q);                   q += (size_t)cap * 4;
+  g.kept = reinterpret_cast<int*>(q);                    q += (size_t)cap * 4;
+  g.removed = q;
+  return g;
+}
+
+template <int STAGE>
+__global__ void __launch_bounds__(THREADS) cascade_nms_big_kernel(const StageParams p, unsigned char* scratch) {
+  constexpr int MODE = (STAGE == 4) ? 1 : 0;
+  __shared__ unsigned int s_keepmask;
+  __shared__ int s_nkeep, s_nlive, s_base;
+  const int tid = threadIdx.x;
+  const int b = (STAGE == 1) ? blockIdx.y : blockIdx.x;
+  const int lvl = (STAGE == 1) ? blockIdx.x : 0;
+  const int seg = (STAGE == 1) ? b * p.n_levels + lvl : b;
+  int n = p.cnt_in[seg];
+  if (n > p.cap_in) n = p.cap_in;
+  if (n <= MAXN) return;            // the shared-memory kernel owns this group
+  const Cand* in = p.in + (size_t)seg * p.cap_in;
+  const BigScratch g = big_scratch(scratch, seg, p.cap_in);
+  for (int i = tid; i < n; i += THREADS) {
+    const Cand c = in[i];
+    float4 bx = make_float4(c.x1, c.y1, c.x2, c.y2);
+    float score = c.score;
+    bool pass = true;
+    uint32_t tie = c.key;
+    if (STAGE == 3 || STAGE == 4) {
+      score = p.prob[(size_t)seg * p.cap_in + i];
+      const int* pd = p.pad_in + ((size_t)seg * p.cap_in + i) * 4;
+      const bool crop_ok = (pd[1] > pd[0] - 1) && (pd[3] > pd[2] - 1);
+      pass = crop_ok && (score > p.thr_score);
+      tie = (uint32_t)i;
+      if (STAGE == 4) {
+        const float* r = p.reg + ((size_t)seg * p.cap_in + i) * 4;
+        bx = bbreg_plus1(bx, r[0], r[1], r[2], r[3]);
+        tie = 0xffffffffu - (uint32_t)i;
       }
-      q = rerec(q);
-      Cand o;
-      o.x1 = q.x; o.y1 = q.y; o.x2 = q.z; o.y2 = q.w;
-      o.score = sscore[slot];
-      o.r0 = o.r1 = o.r2 = o.r3 = 0.f;
-      o.key = (uint32_t)r;
-      p.out[(size_t)b * p.cap_out + r] = o;
-      pad_box(q, p.W, p.H, p.pad_out + ((size_t)b * p.cap_out + r) * 4);
     }
-    if (tid == 0) p.cnt_out[b] = nk;
-  } else {   // STAGE 4
-    const int nk = min(nkeep, p.cap_out);
-    if (nkeep > p.cap_out && tid == 0) flag_overflow(p.capflag, 4, b, nkeep, p.cap_out);
-    // MTCNN.detect select_largest: order = argsort(area)[::-1]  (ties: later pick index first)
-    for (int r = tid; r < nk; r += THREADS) {
-      const float4 bx = sm.sbox[sm.kept[r]];
-      const float ar = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
-      int pos = 0;
-      for (int q = 0; q < nk; ++q) {
-        const float4 bq = sm.sbox[sm.kept[q]];
-        const float aq = __fmul_rn(__fsub_rn(bq.z, bq.x), __fsub_rn(bq.w, bq.y));
-        pos += (aq > ar || (aq == ar && q > r)) ? 1 : 0;
-      }
-      float* o = p.boxes_out + ((size_t)b * p.cap_out + pos) * 5;
-      o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-      o[4] = sscore[sm.sslot[sm.kept[r]]];
-    }
-    if (tid == 0) p.cnt_out[b] = nk;
+    g.ubox[i] = bx;
+    g.uscore[i] = score;
+    g.key[i] = pass ? make_key(score, tie) : KEY_DEAD;
   }
+  if (tid == 0) { s_nkeep = 0; s_nlive = 0; }
+  __syncthreads();
+  int live = 0;
+  for (int i = tid; i < n; i += THREADS) {
+    const unsigned long long ki = g.key[i];
+    if (ki == KEY_DEAD) continue;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (g.key[j] < ki) ? 1 : 0;
+    const float4 bx = g.ubox[i];
+    g.sbox[rank] = bx;
+    g.sarea[rank] = box_area<MODE>(bx);
+    g.sslot[rank] = i;
+    g.removed[rank] = 0;
+    ++live;
+  }
+  if (live) atomicAdd(&s_nlive, live);
+  __syncthreads();
+  const int nl = s_nlive;
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int blk = 0; blk * 32 < nl; ++blk) {
+    if (warp == 0) {
+      const int i = blk * 32 + lane;
+      const bool valid = i < nl;
+      float4 bx = valid ? g.sbox[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float ar = valid ? g.sarea[i] : 0.f;
+      bool alive = valid && !g.removed[i];
+      unsigned int supby = 0;
+      for (int k = 0; k < 32; ++k) {
+        float4 o;
+        o.x = __shfl_sync(0xffffffffu, bx.x, k);
+        o.y = __shfl_sync(0xffffffffu, bx.y, k);
+        o.z = __shfl_sync(0xffffffffu, bx.z, k);
+        o.w = __shfl_sync(0xffffffffu, bx.w, k);
+        const float oa = __shfl_sync(0xffffffffu, ar, k);
+        if (valid && lane > k && suppresses<MODE>(o, oa, bx, ar, p.thr_nms)) supby |= 1u << k;
+      }
+      for (int k = 0; k < 32; ++k) {
+        const bool ak = __shfl_sync(0xffffffffu, (int)alive, k) != 0;
+        if (ak && ((supby >> k) & 1u)) alive = false;
+      }
+      const unsigned int km = __ballot_sync(0xffffffffu, alive);
+      const int pos = s_nkeep + __popc(km & ((1u << lane) - 1u));
+      if (alive) g.kept[pos] = i;
+      __syncwarp();
+      if (lane == 0) { s_keepmask = km; s_nkeep += __popc(km); }
+    }
+    __syncthreads();
+    const unsigned int km = s_keepmask;
+    if (km) {
+      for (int j = (blk + 1) * 32 + tid; j < nl; j += THREADS) {
+        if (g.removed[j]) continue;
+        const float4 bj = g.sbox[j];
+        const float aj = g.sarea[j];
+        unsigned int mk = km;
+        while (mk) {
+          const int k = __ffs(mk) - 1;
+          mk &= mk - 1;
+          const int i = blk * 32 + k;
+          if (suppresses<MODE>(g.sbox[i], g.sarea[i], bj, aj, p.thr_nms)) { g.removed[j] = 1; break; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  stage_epilogue<STAGE>(p, b, lvl, seg, in, s_nkeep, g.kept, g.sslot, g.sbox, g.uscore, &s_base);
 }
 
 // stand-alone NMS over arrays (trl_nms)
@@ -346,6 +492,8 @@ int nms_init(trl_ctx* c) {
 }
 
 int nms_max_n() { return nms::MAXN; }
+int nms_big_max_n() { return nms::BIGN; }
+size_t nms_big_scratch_bytes(int groups, int cap) { return cap > nms::MAXN ? (size_t)groups * cap * nms::BIG_BYTES_PER_ENTRY : 0; }
 
 int launch_plain_nms(trl_ctx* c, const float* d_boxes, const float* d_scores, int n, float thr, int mode, int* d_keep,
                      int* d_nkeep, cudaStream_t s) {
@@ -369,5 +517,16 @@ int launch_cascade_stage(trl_ctx* c, int stage, const nms::StageParams& p, int B
     default: TRL_FAIL(c, TRL_E_INVALID, "bad cascade stage %d", stage);
   }
   TRL_LAUNCH_CHECK(c);
+  if (p.cap_in > MAXN) {
+    // raised capacities (overflow retry): groups beyond the shared-memory limit go through the global-memory variant
+    if (!c->d_nms_big) TRL_FAIL(c, TRL_E_STATE, "cascade stage %d: no scratch for groups above %d candidates", stage, MAXN);
+    switch (stage) {
+      case 1: cascade_nms_big_kernel<1><<<dim3(p.n_levels, B), THREADS, 0, s>>>(p, c->d_nms_big); break;
+      case 2: cascade_nms_big_kernel<2><<<B, THREADS, 0, s>>>(p, c->d_nms_big); break;
+      case 3: cascade_nms_big_kernel<3><<<B, THREADS, 0, s>>>(p, c->d_nms_big); break;
+      default: cascade_nms_big_kernel<4><<<B, THREADS, 0, s>>>(p, c->d_nms_big); break;
+    }
+    TRL_LAUNCH_CHECK(c);
+  }
   return TRL_OK;
 }

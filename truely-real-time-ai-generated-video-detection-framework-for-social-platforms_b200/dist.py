@@ -1,18 +1,20 @@
-"""Frame-range sharding of one clip over the GPUs of a box.
+"""Frame-range sharding over the GPUs of a box.
 
-Per-frame work (MTCNN, crop, FaceNet) is independent, so rank r simply takes a contiguous range of the
-processed frames.  Two pieces of state cross shard boundaries (reference server/model.py:37-39):
+Per-frame work (MTCNN, crop, FaceNet) is independent, so rank r simply takes a contiguous range of the processed
+frames -- of one long clip, or of a batch of clips laid end to end (BASELINE.json configs[4]).  Two pieces of state
+cross shard boundaries (reference server/model.py:37-39), and both stop at clip boundaries:
 
-* ``previous_face_encoding``: the first face-bearing frame of a shard is compared with the last face-bearing
-  frame *before* the shard -- usually the previous rank's last frame, but if that shard's tail (or all of it)
-  has no face, one further back (frames without a face are skipped, server/model.py:56-75).  Every rank
-  publishes ``(has_any, last_valid_embedding)``; one all-gather of 513 floats per rank; each rank picks the
-  nearest preceding rank that has one.  This is the "one-frame embedding halo", exact across faceless gaps.
-* ``deepfake_count``: a run-length over the whole clip.  Per-frame flags (3 bytes per processed frame) are
-  all-gathered and the scan + score (exact integer logic) run on the host, identically on every rank.
+* ``previous_face_encoding``: the first face-bearing frame of a shard is compared with the last face-bearing frame
+  *before* the shard -- usually the previous rank's last frame, but if that shard's tail (or all of it) has no face,
+  one further back (frames without a face are skipped, server/model.py:56-75) -- unless a clip starts in between.
+* ``deepfake_count``: a run-length over a whole clip.  Per-frame flags (3 bytes per processed frame) are gathered and
+  the scan + score (exact integer logic) run on the host, identically on every rank, per clip.
 
-The collectives go through ``torch.distributed`` (NCCL over NVLink on the box, gloo in the CPU tests); they move
-kilobytes, so they are latency bound and there is nothing to fuse them with.
+One collective per analysis: every rank condenses its range into a fixed-size record (``trl_shard_pack``: flags, the
+embedding of the first frame still waiting for a predecessor, the outgoing halo), the records are all-gathered
+(``torch.distributed``: NCCL over NVLink on the box, gloo in the CPU tests; a few KB per rank, latency bound, nothing to
+fuse with), ``trl_shard_resolve`` finishes the cross-shard comparisons on the gathered buffer on the device, and ONE
+device->host copy brings the flags of the whole batch back.  No host synchronisation before that copy.
 """
 from __future__ import annotations
 
@@ -20,63 +22,40 @@ import os
 
 import numpy as np
 
+EMB_DIM = 512
+_HDR_BYTES = 8 * 4
+
 
 def shard_range(n: int, rank: int, world: int):
     """Contiguous, balanced split of n processed frames."""
     return (n * rank) // world, (n * (rank + 1)) // world
 
 
-def exchange_halo(last_emb, last_valid, group=None):
-    """All-gather (valid, embedding) and return (halo_emb [512] or None, gathered [world, 513]).
-
-    ``last_emb``: float32 [512] tensor, ``last_valid``: uint8/bool [1] tensor, both on the device the backend
-    needs (CUDA for NCCL, CPU for gloo).
-    """
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    mine = torch.cat([last_valid.to(torch.float32).reshape(1), last_emb.to(torch.float32).reshape(-1)])
-    allv = torch.empty((world, mine.numel()), dtype=torch.float32, device=mine.device)
-    if mine.is_cuda:
-        dist.all_gather_into_tensor(allv, mine, group=group)
-    else:
-        dist.all_gather(list(allv.unbind(0)), mine, group=group)
-    halo = None
-    flags = allv[:, 0].cpu().numpy()                # one tiny D2H on CUDA: choosing the source rank is host logic
-    for r in range(rank - 1, -1, -1):
-        if flags[r] != 0:
-            halo = allv[r, 1:].contiguous()
-            break
-    return halo, allv
+def record_pad(n_max: int) -> int:
+    return (n_max + 15) & ~15
 
 
-def gather_flags(valid, has_sim, below, n_local: int, n_max: int, group=None):
-    """All-gather the per-frame flags.  Each rank contributes uint8 [3, n_max] (padded); returns three numpy
-    arrays for the whole clip in frame order, using the true local lengths."""
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    dev = valid.device
-    buf = torch.zeros((3, n_max + 4), dtype=torch.uint8, device=dev)
-    buf[0, :n_local], buf[1, :n_local], buf[2, :n_local] = valid[:n_local], has_sim[:n_local], below[:n_local]
-    # local length rides along in the last 4 bytes (little endian)
-    buf[0, n_max:] = torch.tensor(list(int(n_local).to_bytes(4, "little")), dtype=torch.uint8, device=dev)
-    allb = torch.empty((world,) + tuple(buf.shape), dtype=torch.uint8, device=dev)
-    if buf.is_cuda:
-        dist.all_gather_into_tensor(allb, buf, group=group)
-    else:
-        dist.all_gather(list(allb.unbind(0)), buf, group=group)
-    h = allb.cpu().numpy()
+def record_bytes(n_max: int) -> int:
+    """Size of one rank's record (mirrors trl_shard_record_bytes, include/truely_b200.h; checked in tests/test_host.py)."""
+    return _HDR_BYTES + 2 * EMB_DIM * 4 + 3 * record_pad(n_max)
+
+
+def unpack_flags(all_records: np.ndarray, n_max: int):
+    """``all_records``: uint8 [world, record_bytes(n_max)] (host).  -> (valid, has_sim, below) of the whole batch in frame
+    order, using every rank's true length."""
+    world = all_records.shape[0]
+    npad = record_pad(n_max)
+    off = _HDR_BYTES + 2 * EMB_DIM * 4
     v, s, b = [], [], []
     for r in range(world):
-        n = int.from_bytes(bytes(h[r, 0, n_max:].tolist()), "little")
-        v.append(h[r, 0, :n]); s.append(h[r, 1, :n]); b.append(h[r, 2, :n])
+        n = int(all_records[r, :4].view(np.int32)[0])
+        fl = all_records[r, off:off + 3 * npad].reshape(3, npad)
+        v.append(fl[0, :n]); s.append(fl[1, :n]); b.append(fl[2, :n])
     return np.concatenate(v), np.concatenate(s), np.concatenate(b)
 
 
 class ShardedAnalyzer:
-    """One process per GPU; each rank analyses its contiguous range of the clip's processed frames."""
+    """One process per GPU; each rank analyses its contiguous range of the batch's processed frames."""
 
     def __init__(self, analyzer, group=None):
         import torch.distributed as dist
@@ -84,24 +63,67 @@ class ShardedAnalyzer:
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self._bufs = {}
 
-    def analyze(self, local_frames, n_max: int, frame_count: int, fps: int, stride: int, chunk: int = 90,
-                h2d: bool = False, dev_frames=None, thr: float = 0.99):
-        """``local_frames``: this rank's processed frames (device tensor, or pinned host tensor with h2d=True).
-        Returns (score, flagged list for the whole clip, device outputs of the local range)."""
-        import ctypes as C
+    # ---- the three device steps around the collective (CUDA: C ABI; the CPU tests substitute numpy restatements)
+    def _pack(self, out, n_local, n_max, clip_start):
         from . import model as M
         an, t = self.an, self.an.torch
+        key = ("rec", n_max)
+        if key not in self._bufs:
+            rb = record_bytes(n_max)
+            assert rb == an.lib.trl_shard_record_bytes(n_max)
+            dev = f"cuda:{an.device}"
+            self._bufs[key] = (t.empty(rb, dtype=t.uint8, device=dev), t.empty((self.world, rb), dtype=t.uint8, device=dev),
+                               t.empty((self.world, rb), dtype=t.uint8, pin_memory=True))
+        rec, _, _ = self._bufs[key]
+        an._check(an.lib.trl_shard_pack(an.ctx, M._vp(out["emb"]), M._vp(out["valid"]), M._vp(out["has_sim"]), M._vp(out["below"]),
+                                        M._vp(clip_start), n_local, n_max, M._vp(rec), an._sptr()))
+        return rec
+
+    def _gather(self, rec, n_max):
+        import torch.distributed as dist
+        _, allr, _ = self._bufs[("rec", n_max)]
+        dist.all_gather_into_tensor(allr, rec, group=self.group)
+        return allr
+
+    def _resolve(self, allr, n_max, thr, out):
+        from . import model as M
+        an = self.an
+        an._check(an.lib.trl_shard_resolve(an.ctx, M._vp(allr), self.world, self.rank, n_max, thr, M._vp(out["sim"]),
+                                           M._vp(out["below"]), M._vp(out["has_sim"]), an._sptr()))
+
+    def _stream_ctx(self):
+        return self.an.torch.cuda.stream(self.an.stream)
+
+    def _to_host(self, allr, n_max):
+        _, _, host = self._bufs[("rec", n_max)]
+        host.copy_(allr, non_blocking=True)
+        self.an.stream.synchronize()          # the only host synchronisation of the analysis
+        return host.numpy()
+
+    def analyze(self, local_frames, n_max: int, frame_count: int, fps: int, stride: int, chunk: int = 90,
+                h2d: bool = False, dev_frames=None, thr: float = 0.99, clip_start=None, clips=None):
+        """``local_frames``: this rank's processed frames (device tensor, or pinned host tensor with h2d=True).
+        One clip: returns (score, flagged list for the whole clip, device outputs of the local range).
+        A batch of clips (``clips`` = [(n_processed, frame_count), ...] for the WHOLE batch, ``clip_start`` = this rank's
+        slice of model.clip_start_mask(clips) on the device): returns (list of per-clip scores, flagged, outputs)."""
+        from . import model as M
+        an = self.an
         n_local = local_frames.shape[0]
-        out = an.analyze_resident(local_frames, chunk=chunk, halo=None, h2d=h2d, dev_frames=dev_frames)
-        with t.cuda.stream(an.stream):
-            halo, _ = exchange_halo(out["last_emb"], out["last_valid"], self.group)
-            if halo is not None:
-                # re-evaluate K12 on the local range with the halo: only the first face-bearing frame changes
-                an._check(an.lib.trl_consistency(
-                    an.ctx, M._vp(out["emb"]), M._vp(out["valid"]), n_local, M._vp(halo), C.c_void_p(0), thr,
-                    M._vp(out["sim"]), M._vp(out["below"]), M._vp(out["has_sim"]), C.c_void_p(0), C.c_void_p(0), an._sptr()))
-            v, s, b = gather_flags(out["valid"], out["has_sim"], out["below"], n_local, n_max, self.group)
+        if n_local > n_max:
+            raise ValueError(f"local range of {n_local} frames exceeds n_max={n_max}")
+        out = an.analyze_resident(local_frames, chunk=chunk, halo=None, h2d=h2d, dev_frames=dev_frames, thr=thr,
+                                  clip_start=clip_start)
+        with self._stream_ctx():
+            rec = self._pack(out, n_local, n_max, clip_start)
+            allr = self._gather(rec, n_max)
+            self._resolve(allr, n_max, thr, out)
+            host = self._to_host(allr, n_max)
+        v, s, b = unpack_flags(host, n_max)
+        if clips is not None:
+            scores, flagged = M.score_clips(v, s, b, clips, fps, stride)
+            return scores, flagged, out
         score, flagged, _ = M.score_from_flags(v, s, b, frame_count, fps, stride)
         return score, flagged, out
 

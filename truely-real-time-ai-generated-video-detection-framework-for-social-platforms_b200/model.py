@@ -112,6 +112,35 @@ class Analyzer:
         detail = (C.c_int * 4)()
         self._check(self.lib.trl_check_capacity(self.ctx, detail))
 
+    # capacities of the overflow-retry path: the global-memory NMS limit of the library (include/truely_b200.h)
+    BIG_CAPS = (16384, 16384, 2048)
+
+    def set_capacity(self, cand_cap_scale: int, cand_cap_frame: int, box_cap_frame: int):
+        """trl_set_capacity: slow (synchronises, drops the workspace)."""
+        self._check(self.lib.trl_set_capacity(self.ctx, cand_cap_scale, cand_cap_frame, box_cap_frame))
+        self.cfg.cand_cap_scale, self.cfg.cand_cap_frame, self.cfg.box_cap_frame = cand_cap_scale, cand_cap_frame, box_cap_frame
+        self.box_cap = box_cap_frame
+
+    def detect_align_uncapped(self, d_frames, box, valid, nfaces, crops):
+        """Overflow retry (upstream detect_face has no candidate cap; the fast path has): the cascade + crop-align of
+        ``d_frames`` again, one frame per call, with the capacities raised to the library's maximum -- groups above 2048
+        candidates then run through the global-memory NMS.  Synchronous and slow by design; the fast-path capacities
+        are restored afterwards.  Raises TRL_E_CAPACITY only if even 16384 candidates per group are not enough."""
+        saved = (self.cfg.cand_cap_scale, self.cfg.cand_cap_frame, self.cfg.box_cap_frame)
+        B, H, Wd, _ = d_frames.shape
+        self.stream.synchronize()
+        self.set_capacity(*self.BIG_CAPS)
+        try:
+            with self.torch.cuda.stream(self.stream):
+                for i in range(B):
+                    self._check(self.lib.trl_detect_align(
+                        self.ctx, _vp(d_frames[i:i + 1]), 1, H, Wd, _vp(box[i:i + 1]), _vp(valid[i:i + 1]),
+                        _vp(nfaces[i:i + 1]), _vp(crops[i:i + 1]), self._sptr()))
+            self.stream.synchronize()
+            self.check_capacity()
+        finally:
+            self.set_capacity(*saved)
+
     def launch_count(self) -> int:
         return int(self.lib.trl_launch_count(self.ctx))
 
@@ -198,7 +227,7 @@ class Analyzer:
 
     # ------------------------------------------------------------------ clip-level API on staged frames
     def analyze_resident(self, frames, chunk: int = 90, host_out=None, halo=None, h2d: bool = False, dev_frames=None,
-                         thr: float = THRESHOLD_FACE_SIMILARITY, pipeline: bool = True):
+                         thr: float = THRESHOLD_FACE_SIMILARITY, pipeline: bool = True, clip_start=None):
         """All processed frames of a clip (or of this rank's range) in one go.
 
         ``frames``: uint8 [N,H,W,3] tensor, either on the device (``h2d=False``) or in pinned host memory
@@ -207,6 +236,9 @@ class Analyzer:
         The MTCNN cascade + crop-align run chunk by chunk (bounded workspace; with ``pipeline`` the latency-bound tail
         of chunk k runs under the pyramid of chunk k+1, trl_detect_align_async); all N crops are then embedded by ONE
         FaceNet call (large-M GEMMs) and compared by one consistency call.  Nothing synchronises with the host.
+        ``clip_start`` (uint8 [N] device tensor, optional): 1 on the first processed frame of every clip when the range
+        holds several clips back to back (BASELINE.json configs[4]); the embedding chain is cut there, like the locals of
+        a fresh run() call (server/model.py:37-39).
         Returns the dict of device outputs [N, ...]; if ``host_out`` (pinned tensors keyed like the outputs) is given,
         those per-frame results are copied back asynchronously as well.
         """
@@ -224,6 +256,9 @@ class Analyzer:
         he, hv = (halo if halo is not None else (None, None))
         chunks = chunk_schedule(N, chunk, ramp=h2d)
         nbuf = dev_frames.shape[0] if h2d else 0
+        if h2d and pipeline and nbuf < 2:
+            # a pipelined tail still reads staging buffer k while chunk k+1 is copied in: one buffer cannot be recycled safely
+            raise ValueError("analyze_resident(h2d=True, pipeline=True) needs at least two staging buffers (dev_frames.shape[0] >= 2)")
         if h2d:
             cs = self._copy_stream
             copied = [t.cuda.Event() for _ in chunks]
@@ -257,9 +292,9 @@ class Analyzer:
             # one FaceNet batch for the whole range: per-chunk calls (tried, to hide FaceNet under the next copy) make the
             # step launch bound on the host (~110 launches per call) and were 8 ms slower end to end
             self._check(self.lib.trl_facenet(self.ctx, _vp(out["crops"]), N, S, _vp(out["emb"]), self._sptr()))
-            self._check(self.lib.trl_consistency(
-                self.ctx, _vp(out["emb"]), _vp(out["valid"]), N, _vp(he), _vp(hv), thr, _vp(out["sim"]), _vp(out["below"]),
-                _vp(out["has_sim"]), _vp(out["last_emb"]), _vp(out["last_valid"]), self._sptr()))
+            self._check(self.lib.trl_consistency_clips(
+                self.ctx, _vp(out["emb"]), _vp(out["valid"]), N, _vp(clip_start), _vp(he), _vp(hv), thr, _vp(out["sim"]),
+                _vp(out["below"]), _vp(out["has_sim"]), _vp(out["last_emb"]), _vp(out["last_valid"]), self._sptr()))
             if host_out is not None:
                 for key, h in host_out.items():
                     h[:N].copy_(out[key][:N], non_blocking=True)
@@ -312,6 +347,33 @@ def score_from_flags(valid, has_sim, below, frame_count: int, fps: int, stride: 
     for v, h, b in zip(valid, has_sim, below):
         flagged.append(rl.step(bool(b)) if (v and h) else False)
     return final_score(rl.deep_fake_frame_count, rl.deepfake_count, frame_count, fps, stride), flagged, rl
+
+
+def score_clips(valid, has_sim, below, clips, fps: int, stride: int):
+    """Many clips back to back (BASELINE.json configs[4]): ``clips`` = [(n_processed, frame_count), ...] in batch order.
+    Each clip gets the score a separate run() call would return: the run-length counters start from zero at every clip
+    (server/model.py:37-39).  -> (scores [n_clips], flagged list for the whole batch)."""
+    scores, flagged, a = [], [], 0
+    for n_proc, frame_count in clips:
+        sc, fl, _ = score_from_flags(valid[a:a + n_proc], has_sim[a:a + n_proc], below[a:a + n_proc], frame_count, fps, stride)
+        scores.append(sc)
+        flagged.extend(fl)
+        a += n_proc
+    if a != len(valid):
+        raise ValueError(f"clips cover {a} processed frames, the flag arrays hold {len(valid)}")
+    return scores, flagged
+
+
+def clip_start_mask(clips):
+    """uint8 numpy mask over the processed frames of the batch: 1 on the first processed frame of every clip."""
+    n = sum(c[0] for c in clips)
+    m = np.zeros(n, np.uint8)
+    a = 0
+    for n_proc, _ in clips:
+        if n_proc > 0:
+            m[a] = 1
+        a += n_proc
+    return m
 
 
 _ANALYZER = None
@@ -408,8 +470,23 @@ def staging_empty(torch, shape, write_combined: bool = True):
     return ten
 
 
+_PER_FRAME = ("nfaces", "box", "valid", "emb", "sim", "below", "has_sim", "frames", "crops")
+
+
+def annotate_frame(frame, box, flagged: bool, frame_index: int):
+    """server/model.py:66-74, in place: a compared frame gets the red box + "AI Detected - Frame n" when it is counted as
+    suspicious, the green box + "Real Frame" otherwise (same colours, thickness, fonts, scales and anchor points)."""
+    x1, y1, x2, y2 = int(box[0]), int(box[1]), int(box[2]), int(box[3])
+    if flagged:
+        cv2.rectangle(frame, (x1, y1), (x2, y2), (0, 0, 255), 2)
+        cv2.putText(frame, f"AI Detected - Frame {frame_index}", (10, 30), cv2.FONT_HERSHEY_SIMPLEX, 1, (0, 0, 255), 2, cv2.LINE_AA)
+    else:
+        cv2.rectangle(frame, (x1, y1), (x2, y2), (0, 255, 0), 2)
+        cv2.putText(frame, "Real Frame", (x1, y1 - 10), cv2.FONT_HERSHEY_SIMPLEX, 0.5, (0, 255, 0), 2, cv2.LINE_AA)
+
+
 class _Chunk:
-    __slots__ = ("frames", "proc_pos", "proc_idx", "pinned", "out", "host", "event", "n")
+    __slots__ = ("frames", "proc_pos", "proc_idx", "pinned", "out", "host", "event", "n", "halo")
 
 
 def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, analyzer: Analyzer | None = None,
@@ -426,7 +503,7 @@ def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, a
     if chunk is None:
         chunk = max(4, min(64, int(96e6 // max(1, width * height * 3))))   # ~96 MB of pinned frames per chunk
     tr = Trace(stride=stride, frame_index=[], valid=[], box=[], sim=[], flagged=[], nfaces=[], emb=[] if keep_emb else None,
-               timings=dict(decode_s=0.0, submit_s=0.0, finish_s=0.0))
+               timings=dict(decode_s=0.0, submit_s=0.0, finish_s=0.0, capacity_retries=0))
     rl = RunLength()
     dev = f"cuda:{an.device}"
     pending = deque()
@@ -436,13 +513,16 @@ def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, a
 
     def new_chunk():
         c = _Chunk()
-        c.frames, c.proc_pos, c.proc_idx, c.n = [], [], [], 0
+        c.frames, c.proc_pos, c.proc_idx, c.n, c.halo = [], [], [], 0, None
         if free_bufs:
             c.pinned, c.out, c.host = free_bufs.pop()
         else:
             c.pinned = staging_empty(t, (chunk, height, width, 3))
             c.out = an.alloc_outputs(chunk)
             c.out["frames"] = t.empty((chunk, height, width, 3), dtype=t.uint8, device=dev)
+            # this chunk's own copy of the incoming halo (the producing chunk's buffers are recycled two chunks later)
+            c.out["halo_emb"] = t.zeros(L.EMB_DIM, dtype=t.float32, device=dev)
+            c.out["halo_valid"] = t.zeros(1, dtype=t.uint8, device=dev)
             c.host = {k: t.empty(c.out[k].shape, dtype=c.out[k].dtype, pin_memory=True)
                       for k in ("nfaces", "box", "valid", "sim", "below", "has_sim")}
             if keep_emb:
@@ -457,8 +537,14 @@ def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, a
             with t.cuda.stream(an.stream):
                 d_frames = c.out["frames"][:n]
                 d_frames.copy_(c.pinned[:n], non_blocking=True)
-                view = {k: (v[:n] if k not in ("last_emb", "last_valid", "frames") else v) for k, v in c.out.items()}
-                an.process_device(d_frames, view, halo)
+                if halo is not None:
+                    c.out["halo_emb"].copy_(halo[0], non_blocking=True)
+                    c.out["halo_valid"].copy_(halo[1], non_blocking=True)
+                else:
+                    c.out["halo_valid"].zero_()
+                c.halo = (c.out["halo_emb"], c.out["halo_valid"])
+                view = {k: (v[:n] if k in _PER_FRAME else v) for k, v in c.out.items()}
+                an.process_device(d_frames, view, c.halo)
                 halo = (c.out["last_emb"], c.out["last_valid"])
                 for k, h in c.host.items():
                     h[:n].copy_(c.out[k][:n], non_blocking=True)
@@ -469,11 +555,44 @@ def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, a
         pending.append(c)
         tr.timings["submit_s"] += time.perf_counter() - t0
 
+    def redo_uncapped(q, halo_in):
+        """capacity overflow: chunk q again through the uncapped slow path, chained on ``halo_in``"""
+        n = q.n
+        if n == 0:
+            return halo_in
+        S = an.crop_size
+        if "crops" not in q.out:
+            q.out["crops"] = t.empty((chunk, S, S, 3), dtype=t.uint8, device=dev)
+        o = q.out
+        an.detect_align_uncapped(o["frames"][:n], o["box"][:n], o["valid"][:n], o["nfaces"][:n], o["crops"][:n])
+        he, hv = halo_in if halo_in is not None else (None, None)
+        with t.cuda.stream(an.stream):
+            an._check(an.lib.trl_facenet(an.ctx, _vp(o["crops"]), n, S, _vp(o["emb"]), an._sptr()))
+            an._check(an.lib.trl_consistency(
+                an.ctx, _vp(o["emb"]), _vp(o["valid"]), n, _vp(he), _vp(hv), THRESHOLD_FACE_SIMILARITY, _vp(o["sim"]),
+                _vp(o["below"]), _vp(o["has_sim"]), _vp(o["last_emb"]), _vp(o["last_valid"]), an._sptr()))
+            for k, h in q.host.items():
+                h[:n].copy_(o[k][:n], non_blocking=True)
+        an.stream.synchronize()
+        q.event = None
+        return (o["last_emb"], o["last_valid"])
+
     def finish(c):
         t0 = time.perf_counter()
         if c.event is not None:
             c.event.synchronize()
-            an.check_capacity()
+            try:
+                an.check_capacity()
+            except L.TrlError as e:
+                if e.code != L.TRL_E_CAPACITY:
+                    raise
+                # A candidate list overflowed somewhere in the chunks submitted so far (the flag is per context, and a
+                # truncated list may also have produced the halo of the next chunk): redo this chunk and every chunk
+                # already in flight behind it through the uncapped path, in order, re-chaining the halo.
+                tr.timings["capacity_retries"] += 1
+                h = c.halo if c.n > 0 else None
+                for q in [c] + list(pending):
+                    h = redo_uncapped(q, h) if q.n > 0 else h
         host = {k: v[:c.n].numpy() for k, v in c.host.items()}
         k = 0
         for pos, frame in enumerate(c.frames):
@@ -484,15 +603,8 @@ def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, a
                 flagged = False
                 if valid and host["has_sim"][k]:
                     flagged = rl.step(bool(host["below"][k]))
-                    if writer is not None:                       # server/model.py:66-74
-                        if flagged:
-                            cv2.rectangle(frame, (int(box[0]), int(box[1])), (int(box[2]), int(box[3])), (0, 0, 255), 2)
-                            cv2.putText(frame, f"AI Detected - Frame {fidx}", (10, 30), cv2.FONT_HERSHEY_SIMPLEX, 1,
-                                        (0, 0, 255), 2, cv2.LINE_AA)
-                        else:
-                            cv2.rectangle(frame, (int(box[0]), int(box[1])), (int(box[2]), int(box[3])), (0, 255, 0), 2)
-                            cv2.putText(frame, "Real Frame", (int(box[0]), int(box[1]) - 10), cv2.FONT_HERSHEY_SIMPLEX, 0.5,
-                                        (0, 255, 0), 2, cv2.LINE_AA)
+                    if writer is not None:
+                        annotate_frame(frame, box, flagged, fidx)
                 tr.frame_index.append(fidx)
                 tr.valid.append(valid)
                 tr.box.append(box.copy())
@@ -576,13 +688,18 @@ def run_trace(video_path_one: str, video_path_two: str | None, analyzer: Analyze
         print(f"Error: Invalid video properties: width={width}, height={height}, fps={fps}")
         cap.release()
         return Trace()
-    out = _open_writer(video_path_two, fps, width, height) if video_path_two is not None else None
-    tr = analyze_stream(_video_frames(cap), fps, width, height, writer=out, analyzer=analyzer, keep_emb=keep_emb)
-    execution_time = time.time() - start_time
-    print(f"Total Execution Time: {execution_time} seconds")
-    cap.release()
-    if out is not None:
-        out.release()
+    out = None
+    try:
+        out = _open_writer(video_path_two, fps, width, height) if video_path_two is not None else None
+        tr = analyze_stream(_video_frames(cap), fps, width, height, writer=out, analyzer=analyzer, keep_emb=keep_emb)
+        execution_time = time.time() - start_time
+        print(f"Total Execution Time: {execution_time} seconds")
+    finally:
+        # the reference releases both on its only exit path (server/model.py:81-82); an exception from the GPU path
+        # (mapped to HTTP 500 by server.py) must not leak the capture or leave the writer's file handle open
+        cap.release()
+        if out is not None:
+            out.release()
     if tr.frame_count == 0:
         print("Error: No frames were processed")
         tr.score = 0

@@ -5,12 +5,19 @@ The reference obtains its weights from facenet_pytorch (``MTCNN()`` loads the
 downloads ``20180402-114759-vggface2.pt``; server/model.py:18-19).  Offline those
 files are absent, so this module provides, in order of preference:
 
-1. the upstream state dicts if present (``$TRUELY_WEIGHTS_DIR`` or
-   ``$TORCH_HOME/checkpoints``), key names as in SURVEY.md Appendix C;
-2. seeded stand-ins: ``data/synth_mtcnn.npz`` (P/R/O-Net fitted to the synthetic
-   faces by tests/golden/train_synth_mtcnn.py) and a He-normal InceptionResnetV1
-   (numpy PCG64, machine independent) whose BatchNorm running statistics come
-   from ``data/synth_facenet_bn.npz`` (tests/golden/calibrate_synth_facenet.py).
+1. the upstream state dicts if present (``$TRUELY_WEIGHTS_DIR``, the ``data/`` directory
+   of an installed ``facenet_pytorch`` wheel -- where ``MTCNN()`` itself reads
+   ``{p,r,o}net.pt`` from -- or ``$TORCH_HOME/checkpoints``, where
+   ``InceptionResnetV1(pretrained=...)`` caches its download), key names as in
+   SURVEY.md Appendix C;
+2. ONLY when ``TRUELY_ALLOW_SYNTHETIC=1`` (set by the tests, ``bench.py`` and
+   ``smoke()``; never by ``run``): seeded stand-ins: ``data/synth_mtcnn.npz``
+   (P/R/O-Net fitted to the synthetic faces by tests/golden/train_synth_mtcnn.py)
+   and a He-normal InceptionResnetV1 (numpy PCG64, machine independent) whose
+   BatchNorm running statistics come from ``data/synth_facenet_bn.npz``
+   (tests/golden/calibrate_synth_facenet.py).  Without that switch a missing
+   upstream file raises ``MissingWeightsError``: a user-facing 0-100 score must never
+   come from stand-in networks silently.
 
 Everything here is host-side tensor bookkeeping (fold BatchNorm into the conv
 weights in fp32, reorder to the layouts ``include/truely_b200.h`` documents, and
@@ -98,13 +105,48 @@ MTCNN_SHAPES = {
 # ------------------------------------------------------------------ loading
 
 
+class MissingWeightsError(FileNotFoundError):
+    """Upstream weight files are absent and the synthetic stand-ins were not explicitly allowed."""
+
+
+def synthetic_allowed() -> bool:
+    return os.environ.get("TRUELY_ALLOW_SYNTHETIC", "").strip().lower() in ("1", "true", "yes")
+
+
+def _facenet_pytorch_data_dir():
+    """``<site-packages>/facenet_pytorch/data`` if that wheel is installed (located without importing it)."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("facenet_pytorch")
+    except (ImportError, ValueError):
+        return None
+    if spec is None or not spec.submodule_search_locations:
+        return None
+    for loc in spec.submodule_search_locations:
+        d = os.path.join(loc, "data")
+        if os.path.isdir(d):
+            return d
+    return None
+
+
 def _weights_dirs():
     dirs = []
     if os.environ.get("TRUELY_WEIGHTS_DIR"):
         dirs.append(os.environ["TRUELY_WEIGHTS_DIR"])
+    d = _facenet_pytorch_data_dir()
+    if d:
+        dirs.append(d)
     torch_home = os.environ.get("TORCH_HOME", os.path.join(os.path.expanduser("~"), ".cache", "torch"))
     dirs.append(os.path.join(torch_home, "checkpoints"))
     return dirs
+
+
+def _require_synthetic(what, names):
+    if not synthetic_allowed():
+        raise MissingWeightsError(
+            f"{what}: upstream weight file(s) {names} not found in {_weights_dirs()}.  Put them there (or set "
+            "TRUELY_WEIGHTS_DIR); the seeded synthetic stand-ins are for tests and benchmarks only and are used "
+            "only when TRUELY_ALLOW_SYNTHETIC=1.")
 
 
 def _find(name):
@@ -131,6 +173,8 @@ def load_mtcnn_state():
                 out[f"{n}.{k}"] = v.astype(np.float32)
         src = "upstream"
     else:
+        # all three or none: a half-upstream cascade would be neither the reference's detector nor the test fixture
+        _require_synthetic("MTCNN", [f"{n}.pt" for n, q in paths.items() if q is None])
         p = os.path.join(DATA_DIR, "synth_mtcnn.npz")
         if not os.path.isfile(p):
             raise FileNotFoundError(f"{p} missing: run tests/golden/train_synth_mtcnn.py")
@@ -187,6 +231,7 @@ def load_facenet_state():
         sd = {k: v.astype(np.float32) for k, v in _torch_load_np(p).items()
               if not k.startswith("logits") and not k.endswith("num_batches_tracked")}
         return sd, "upstream"
+    _require_synthetic("InceptionResnetV1", ["20180402-114759-vggface2.pt"])
     return synth_facenet_state(), "synthetic"
 
 
