@@ -47,13 +47,24 @@ def _emit(line):
 
 import numpy as np  # noqa: E402
 
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 WORKLOADS = {
-    "720p30_single": dict(cfg="720p30_single", desc="synthetic 720p 30 fps 60 s clip, single face (BASELINE.json configs[1])"),
-    "1080p60_multi": dict(cfg="1080p60_multi", desc="synthetic 1080p 60 fps clip, 4-8 faces (BASELINE.json configs[3])"),
-    "360p30_single": dict(cfg="360p30_single", desc="synthetic 360p 30 fps clip, single face (shape of the bundled test clip)"),
+    "720p30_single": dict(kind="synth", cfg="720p30_single", baseline_config=1,
+                          desc="synthetic 720p 30 fps 60 s clip, single face (BASELINE.json configs[1])"),
+    "1080p60_multi": dict(kind="synth", cfg="1080p60_multi", baseline_config=3,
+                          desc="synthetic 1080p 60 fps clip, 4-8 faces (BASELINE.json configs[3])"),
+    "360p30_single": dict(kind="synth", cfg="360p30_single", baseline_config=None,
+                          desc="synthetic 360p 30 fps clip, single face (shape of the bundled test clip)"),
+    "bundled_360p": dict(kind="file", path=os.path.join(GOLDEN, "bundled_veo3_360p.mp4"), baseline_config=0,
+                         desc="the reference's bundled test clip 'Veo 3' 360p h264, 960 frames -> 240 processed "
+                              "(BASELINE.json configs[0]; fixture copy tests/golden/bundled_veo3_360p.mp4)"),
+    "clips1080p": dict(kind="clips", cfg="1080p60_multi", baseline_config=4, processed_per_clip=75, distinct=4,
+                       desc="batch of synthetic 1080p 60 fps 10 s clips (600 frames -> 75 processed each, 4-8 faces), laid end to "
+                            "end and frame-sharded with clip-boundary reset (BASELINE.json configs[4]: 256 clips at 8 GPUs)"),
 }
 METRIC = "frames/sec MTCNN+FaceNet consistency"
 UNIT = "processed frames/s"
+REF_SAMPLE_NOTE = "reference arm: a bounded sample of the first processed frames of this workload per step, all host threads"
 
 
 def peaks():
@@ -63,6 +74,22 @@ def peaks():
         return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
                     source="measured (MEASURED_PEAKS.json)")
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def recorded_traffic(kernel, workload, frames_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the newest profiles/r*_traffic.json
+    (written by profiles/summarize_ncu.py traffic from an `ncu --set full` capture).  None when no capture of this
+    kernel at this launch shape is on record -- never a stale literal."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        try:
+            recs = json.load(open(path))
+        except (OSError, ValueError):
+            continue
+        for r in recs:
+            if r.get("kernel") == kernel and r.get("workload") == workload and abs(r.get("frames_per_launch", -1) - frames_per_launch) < 0.5:
+                return dict(bytes=float(r["dram_bytes_per_launch"]), source=f"{os.path.relpath(path, ROOT)} <- {r.get('source', '?')}")
+    return None
 
 
 class ClockSampler:
@@ -135,12 +162,11 @@ class ClockSampler:
                     reasons=sorted(self.reasons), samples=len(self.sm), source=self.source)
 
 
-def pnet_work(H, W):
-    """Algorithmic FLOPs and compulsory bytes of the P-Net pyramid per frame (2 x MACs of conv1..conv4)."""
-    from oracle.mtcnn import pyramid_scales  # geometry only
+def pnet_work(geom):
+    """Algorithmic FLOPs and compulsory bytes of the P-Net pyramid per frame (2 x MACs of conv1..conv4), from the
+    library's own pyramid geometry (trl_pyramid_geometry: one (hs, ws) per scale)."""
     macs = byts = cells = tmacs = 0
-    for s in pyramid_scales(H, W):
-        hs, ws = int(H * s + 1), int(W * s + 1)
+    for hs, ws in geom:
         c1h, c1w = hs - 2, ws - 2
         ph, pw = (c1h + 1) // 2, (c1w + 1) // 2
         oh, ow = ph - 4, pw - 4
@@ -151,54 +177,154 @@ def pnet_work(H, W):
     return 2 * macs, byts, cells, 2 * tmacs
 
 
-def make_frames(cfg_name, rank, world, torch, staging="wc"):
-    """This rank's processed frames of the (world x longer) clip, in page-locked host staging memory
-    (staging="wc": write-combined, the product's default staging buffer, model.staging_empty; "pinned": plain)."""
-    from truely_b200.synth import CONFIGS, SyntheticClip
-    cfg = dict(CONFIGS[cfg_name])
-    per_rank_frames = cfg["n_frames"]
-    cfg["n_frames"] = per_rank_frames * world
-    clip = SyntheticClip(**cfg, jitter=1.2, seed=0)
-    stride = max(1, int(clip.fps / 7))
-    idx = list(range(0, cfg["n_frames"], stride))
-    per = len(idx) // world
-    mine = idx[rank * per:(rank + 1) * per]
-    shape = (len(mine), clip.height, clip.width, 3)
+def pyramid_geometry(an, H, W):
+    import ctypes as C
+    from truely_b200 import _lib as L
+    hs, ws = (C.c_int * L.MAX_SCALES)(), (C.c_int * L.MAX_SCALES)()
+    n = an.lib.trl_pyramid_geometry(an.ctx, H, W, None, hs, ws, None, None)
+    if n < 0:
+        raise RuntimeError(f"trl_pyramid_geometry({H}x{W}) -> {n}")
+    return [(hs[k], ws[k]) for k in range(n)]
+
+
+class Workload:
+    """This rank's share of the workload: processed frames in page-locked staging memory + what the scoring needs."""
+
+    def __init__(self, name, args, rank, world, torch):
+        from truely_b200.synth import CONFIGS, SyntheticClip
+        w = WORKLOADS[name]
+        self.name, self.desc, self.kind = name, w["desc"], w["kind"]
+        self.clips = None                  # [(n_processed, frame_count)] of the WHOLE batch (clip workloads)
+        self.clip_start_local = None       # numpy uint8 [n_local]
+        if w["kind"] == "synth":
+            cfg = dict(CONFIGS[w["cfg"]])
+            cfg["n_frames"] *= world                                   # weak scaling: one N-times longer clip
+            clip = SyntheticClip(**cfg, jitter=1.2, seed=0)
+            self.H, self.W, self.fps = clip.height, clip.width, clip.fps
+            self.stride = max(1, int(clip.fps / 7))
+            idx = list(range(0, cfg["n_frames"], self.stride))
+            per = len(idx) // world
+            mine = idx[rank * per:(rank + 1) * per]
+            self.n_local, self.n_total, self.frame_count = len(mine), per * world, cfg["n_frames"]
+            self._render = [(clip, i) for i in mine]
+            self._sample = [(clip, i) for i in idx[:per]]              # rank 0's range: what the CPU arm samples
+        elif w["kind"] == "file":
+            import cv2
+            cap = cv2.VideoCapture(w["path"])
+            if not cap.isOpened():
+                raise FileNotFoundError(w["path"])
+            self.fps = int(cap.get(cv2.CAP_PROP_FPS))
+            self.W, self.H = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+            self.stride = max(1, int(self.fps / 7))
+            frames, k = [], 0
+            t0 = time.perf_counter()
+            while True:
+                ok, f = cap.read()
+                if not ok:
+                    break
+                if k % self.stride == 0:
+                    frames.append(f)
+                k += 1
+            cap.release()
+            self.decode_s = time.perf_counter() - t0
+            # every rank analyses one copy of the clip; with N ranks the batch is N clips (clip-boundary reset)
+            self.n_local, self.n_total, self.frame_count = len(frames), len(frames) * world, k
+            self._frames = frames
+            if world > 1:
+                self.clips = [(len(frames), k)] * world
+        else:
+            cfg = dict(CONFIGS[w["cfg"]])
+            ppc, distinct, cpg = w["processed_per_clip"], w["distinct"], args.clips_per_gpu
+            self.fps, self.H, self.W = cfg["fps"], cfg["height"], cfg["width"]
+            self.stride = max(1, int(self.fps / 7))
+            cfg["n_frames"] = ppc * self.stride                         # 600 frames = 10 s at 60 fps
+            self._distinct = [SyntheticClip(**cfg, jitter=1.2, seed=100 + d) for d in range(distinct)]
+            self.clips = [(ppc, cfg["n_frames"])] * (cpg * world)
+            self.n_local, self.n_total, self.frame_count = cpg * ppc, cpg * ppc * world, cfg["n_frames"]
+            self._clip_ids = [(rank * cpg + j) % distinct for j in range(cpg)]
+            self._ppc = ppc
+        if self.clips is not None:
+            from truely_b200.model import clip_start_mask
+            m = clip_start_mask(self.clips)
+            a = rank * self.n_local
+            self.clip_start_local = m[a:a + self.n_local].copy()
+
+    def fill(self, pinned, torch):
+        if self.kind == "synth":
+            for k, (clip, i) in enumerate(self._render):
+                pinned[k].copy_(torch.from_numpy(clip.frame(i)))
+        elif self.kind == "file":
+            for k, f in enumerate(self._frames):
+                pinned[k].copy_(torch.from_numpy(f))
+        else:
+            cache = {}                                                  # distinct clip -> its processed frames, rendered once
+            for j, d in enumerate(self._clip_ids):
+                if d not in cache:
+                    clip = self._distinct[d]
+                    cache[d] = [torch.from_numpy(clip.frame(i)) for i in clip.processed_indices()]
+                for k in range(self._ppc):
+                    pinned[j * self._ppc + k].copy_(cache[d][k])
+
+    def sample_frames(self, n):
+        """The first n processed frames of rank 0's range as numpy arrays (regenerated: write-combined staging memory is
+        slow to read back) -- what the CPU arm and the parity check run the oracle on."""
+        if self.kind == "synth":
+            return [clip.frame(i) for clip, i in self._sample[:n]]
+        if self.kind == "file":
+            return [f.copy() for f in self._frames[:n]]
+        clip = self._distinct[0]                                        # rank 0's first clip is distinct clip 0
+        return [clip.frame(i) for i in clip.processed_indices()[:n]]
+
+    def config(self, crop, weights):
+        """Describes the WORKLOAD only, identically in both arms (`--impl ours` / `--impl reference`)."""
+        return {"workload": self.desc, "baseline_config": WORKLOADS[self.name]["baseline_config"], "frame": [self.H, self.W],
+                "fps": self.fps, "stride": self.stride, "processed_frames_per_gpu": self.n_local,
+                "clips_per_gpu": (len(self.clips) // max(1, self.n_total // self.n_local)) if self.clips else None,
+                "crop": crop, "weights": weights, "reference_arm_sample": REF_SAMPLE_NOTE}
+
+
+def staging_tensor(torch, shape, staging, rank):
     if staging == "wc":
         from truely_b200.model import staging_empty
-        pinned = staging_empty(torch, shape, write_combined=True)
-    elif staging.startswith("interleave"):
+        return staging_empty(torch, shape, write_combined=True)
+    if staging.startswith("interleave"):
         from truely_b200.dist import interleaved_staging
         pinned, desc = interleaved_staging(torch, shape, "all" if staging.endswith("all") else "socket")
         print(f"[bench] rank {rank}: staging {desc}", file=sys.stderr)
-    else:
-        pinned = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
-    for k, i in enumerate(mine):
-        pinned[k].copy_(torch.from_numpy(clip.frame(i)))
-    return clip, stride, pinned, len(idx), per
+        return pinned
+    return torch.empty(shape, dtype=torch.uint8, pin_memory=True)
 
 
-def run_reference(args, rank):
-    """--impl reference: the reference's CPU path (oracle port) on the host cores, bounded sample per step."""
+def oracle_models():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    return helpers.oracle_mtcnn(), helpers.oracle_facenet(), helpers
+
+
+def weight_sources():
+    from truely_b200 import weights as W
+    return {"mtcnn": W.load_mtcnn_state()[1], "facenet": W.load_facenet_state()[1]}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path on the host cores.  facenet_pytorch (the reference's arithmetic) cannot
+    be installed offline, so this is the oracle port of it (oracle/, `kind: port`), with every host thread, on a bounded
+    sample of the same workload per step."""
     if rank != 0:
         return
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import helpers
     from oracle.reference_run import reference_run_frames
-    from truely_b200.synth import CONFIGS, SyntheticClip
+    import truely_b200  # noqa: F401
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = dict(CONFIGS[WORKLOADS[args.workload]["cfg"]])
-    clip = SyntheticClip(**cfg, jitter=1.2, seed=0)
-    stride = max(1, int(clip.fps / 7))
-    per_step = args.cpu_frames_per_step
-    mt, fn = helpers.oracle_mtcnn(), helpers.oracle_facenet()
-    frames = [clip.frame(i * stride) for i in range(per_step)]
+    wl = Workload(args.workload, args, 0, world, torch)
+    per_step = min(args.cpu_frames_per_step, wl.n_local)
+    mt, fn, _ = oracle_models()
+    frames = wl.sample_frames(per_step)
 
     def step():
         # fps=7 -> stride 1: every frame handed in is a processed frame (the sample already is every stride-th frame)
-        return reference_run_frames(iter([f.copy() for f in frames]), 7, clip.width, clip.height, mt, fn)
+        return reference_run_frames(iter([f.copy() for f in frames]), 7, wl.W, wl.H, mt, fn)
 
     for _ in range(args.warmup):
         step()
@@ -207,16 +333,80 @@ def run_reference(args, rank):
         step()
     dt = time.perf_counter() - t0
     v = args.steps * per_step / dt
-    sample = f"{per_step} processed frames of the workload clip per step (oracle MTCNN+FaceNet+consistency, torch CPU fp32)"
+    sample = (f"first {per_step} processed frames of the workload per step, {args.steps} steps; oracle port of the reference path "
+              f"(MTCNN + crop + InceptionResnetV1 + consistency, torch CPU fp32, {cores} threads)")
     _emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload]["desc"], "frame": [clip.height, clip.width], "stride": stride},
+        "vs_baseline": None, "dtype": "f32", "data": "bundled clip" if wl.kind == "file" else "synthetic",
+        "config": wl.config(80, weight_sources()),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
+
+
+def parity_check(wl, mt, fn, helpers, ref_trace, out, n, thr=0.99):
+    """North-star tolerances on the bench's own frames: the oracle trace of the cpu_baseline sample against the GPU
+    outputs of the same processed frames (the first n of rank 0's range, taken from the last timed `value` step)."""
+    from oracle.reference_run import clamp_box
+    g = {k: out[k][:n].cpu().numpy() for k in ("nfaces", "box", "valid", "emb", "sim", "has_sim", "below")}
+    res = dict(frames=n, face_count_equal=0, frames_with_face=0, min_box_iou=None, max_box_px_diff=0, min_emb_cosine=None,
+               max_sim_abs_diff=0.0, in_band_frames=0, flag_mismatches_outside_band=0)
+    ious, coss = [], []
+    for k, f in enumerate(ref_trace.frames[:n]):
+        res["face_count_equal"] += int(int(g["nfaces"][k]) == f.n_faces)
+        if f.embedded != bool(g["valid"][k]):
+            res["flag_mismatches_outside_band"] += 1
+            continue
+        if not f.embedded:
+            continue
+        res["frames_with_face"] += 1
+        ious.append(helpers.box_iou(g["box"][k].astype(np.float64), f.box.astype(np.float64)))
+        res["max_box_px_diff"] = max(res["max_box_px_diff"], int(np.abs(g["box"][k] - f.box).max()))
+        coss.append(helpers.cosine(g["emb"][k], f.emb))
+        if f.sim is not None:
+            if not g["has_sim"][k]:
+                res["flag_mismatches_outside_band"] += 1
+                continue
+            res["max_sim_abs_diff"] = max(res["max_sim_abs_diff"], abs(float(g["sim"][k]) - f.sim))
+            if abs(f.sim - thr) < 1e-3:
+                res["in_band_frames"] += 1
+            elif bool(g["below"][k]) != (f.sim < thr):
+                res["flag_mismatches_outside_band"] += 1
+    res["min_box_iou"] = min(ious) if ious else None
+    res["min_emb_cosine"] = min(coss) if coss else None
+    res["pass"] = bool(res["face_count_equal"] == n and res["flag_mismatches_outside_band"] == 0 and
+                       (not ious or min(ious) >= 0.95) and (not coss or min(coss) >= 0.999) and res["max_sim_abs_diff"] < 1e-3)
+    res["tolerances"] = "same face count; box IoU >= 0.95; embedding cosine >= 0.999; |sim diff| < 1e-3; identical sim<0.99 decisions outside the 1e-3 band"
+    return res
+
+
+def facenet_sweep(an, torch, pk, batches=(64, 128, 256, 512, 1024, 2048, 4096), sizes=(160,), iters=5):
+    """BASELINE.json configs[2]: InceptionResnetV1-only sweep over crop batches resident in HBM (random uint8 crops)."""
+    from truely_b200.model import _vp
+    rows = []
+    for S in sizes:
+        flops = 2 * (1417.7e6 if S == 160 else 233.3e6)
+        for B in batches:
+            g = torch.Generator(device="cuda").manual_seed(0)
+            crops = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, device="cuda", generator=g)
+            emb = torch.empty((B, 512), dtype=torch.float32, device="cuda")
+            with torch.cuda.stream(an.stream):
+                for _ in range(3):
+                    an._check(an.lib.trl_facenet(an.ctx, _vp(crops), B, S, _vp(emb), an._sptr()))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(an.stream)
+                for _ in range(iters):
+                    an._check(an.lib.trl_facenet(an.ctx, _vp(crops), B, S, _vp(emb), an._sptr()))
+                e1.record(an.stream)
+            an.stream.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            tf = flops * B / (ms * 1e-3) / 1e12
+            rows.append({"crop": S, "batch": B, "ms": ms, "tflops_bf16": tf, "frac_of_sustained": tf / pk["bf16_sustained"],
+                         "frac_of_burst": tf / pk["bf16_burst"]})
+            del crops, emb
+    return rows
 
 
 def main():
@@ -226,12 +416,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="720p30_single", choices=list(WORKLOADS))
-    ap.add_argument("--chunk", type=int, default=90, help="frames per host->device copy / cascade call of the e2e path")
-    ap.add_argument("--resident-chunk", type=int, default=225,
-                    help="frames per cascade call when the frames are already in HBM (`value`); bounded by the workspace only")
-    ap.add_argument("--cpu-frames", type=int, default=48, help="processed frames in the cpu_baseline sample")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per host->device copy / cascade call of the e2e path (0 = by frame size)")
+    ap.add_argument("--resident-chunk", type=int, default=0,
+                    help="frames per cascade call when the frames are already in HBM (`value`); 0 = by frame size")
+    ap.add_argument("--clips-per-gpu", type=int, default=32, help="clips1080p: clips per GPU (32 x 8 GPUs = the 256 of configs[4])")
+    ap.add_argument("--cpu-frames", type=int, default=48, help="processed frames in the cpu_baseline / parity_check sample")
     ap.add_argument("--cpu-frames-per-step", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-facenet-sweep", action="store_true")
     ap.add_argument("--staging", default="wc", choices=["wc", "pinned", "interleave-socket", "interleave-all"],
                     help="host staging memory of the e2e path: write-combined page-locked (default) or plain page-locked")
     args = ap.parse_args()
@@ -242,7 +434,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
 
     import torch
@@ -258,29 +450,38 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     an = M.Analyzer(device=local_rank)
-    clip, stride, pinned, n_proc_total, n_local = make_frames(WORKLOADS[args.workload]["cfg"], rank, world, torch, args.staging)
-    H, W = clip.height, clip.width
-    frame_count = clip.n_frames
+    wl = Workload(args.workload, args, rank, world, torch)
+    H, W, stride, n_local = wl.H, wl.W, wl.stride, wl.n_local
+    # frames per cascade call: sized so a call's frames stay near 250 MB (e2e) / 620 MB (resident), as tuned at 720p
+    if not args.chunk:
+        args.chunk = max(8, min(90, int(round(90 * (720 * 1280) / (H * W)))))
+    if not args.resident_chunk:
+        args.resident_chunk = max(8, min(225, int(round(225 * (720 * 1280) / (H * W)))))
     dev = f"cuda:{local_rank}"
+    pinned = staging_tensor(torch, (n_local, H, W, 3), args.staging, rank)
+    wl.fill(pinned, torch)
     d_frames = pinned.to(dev)                                   # resident in HBM before the timed region
     stage_buf = torch.empty((3, args.chunk, H, W, 3), dtype=torch.uint8, device=dev)     # triple-buffered H2D staging
     host_out = {k: torch.empty(n_local, dtype=torch.uint8, pin_memory=True) for k in ("valid", "has_sim", "below")}
+    clip_start = torch.from_numpy(wl.clip_start_local).to(dev) if wl.clip_start_local is not None else None
     sharded = ShardedAnalyzer(an, None) if world > 1 else None
     last = {}
 
     def step(h2d):
         src = pinned if h2d else d_frames
+        chunk = args.chunk if h2d else args.resident_chunk
         if sharded is not None:
-            score, flagged, _ = sharded.analyze(src, n_local + 1, frame_count, clip.fps, stride,
-                                                chunk=args.chunk if h2d else args.resident_chunk, h2d=h2d,
-                                                dev_frames=stage_buf)
+            score, flagged, out = sharded.analyze(src, n_local, wl.frame_count, wl.fps, stride, chunk=chunk, h2d=h2d,
+                                                  dev_frames=stage_buf, clip_start=clip_start, clips=wl.clips)
         else:
-            an.analyze_resident(src, chunk=args.chunk if h2d else args.resident_chunk, host_out=host_out, h2d=h2d,
-                                dev_frames=stage_buf)
+            out = an.analyze_resident(src, chunk=chunk, host_out=host_out, h2d=h2d, dev_frames=stage_buf, clip_start=clip_start)
             an.stream.synchronize()
-            score, flagged, _ = M.score_from_flags(host_out["valid"].numpy(), host_out["has_sim"].numpy(),
-                                                   host_out["below"].numpy(), frame_count, clip.fps, stride)
-        last["score"], last["flagged"] = score, int(sum(flagged))
+            v, s, b = host_out["valid"].numpy(), host_out["has_sim"].numpy(), host_out["below"].numpy()
+            if wl.clips is not None:
+                score, flagged = M.score_clips(v, s, b, wl.clips, wl.fps, stride)
+            else:
+                score, flagged, _ = M.score_from_flags(v, s, b, wl.frame_count, wl.fps, stride)
+        last["score"], last["flagged"], last["out"] = score, int(sum(flagged)), out
 
     def barrier():
         if world > 1:
@@ -309,6 +510,8 @@ def main():
     launches = an.launch_count() - launches0
     clocks = cs.summary()
     value = args.steps * n_local * world / (ms_total / 1e3)
+    resident = {"score": last["score"], "flagged": last["flagged"]}
+    out_resident = {k: last["out"][k][:n_local].clone() for k in ("nfaces", "box", "valid", "emb", "sim", "has_sim", "below")}
     # per-stage device times: a second pass of the same steps with CUDA events around every stage.  The events need a
     # serial schedule, so this pass runs the cascade un-pipelined (trl_detect_align_async degrades to trl_detect_align
     # while profiling is on); the stage times therefore add up to a little more than ms_per_step.
@@ -328,6 +531,12 @@ def main():
     e2e_value = args.steps * n_local * world / (ms_e2e / 1e3)
     h2d_bytes = n_local * H * W * 3
     d2h_bytes = 3 * n_local
+    # the two paths (frames resident / frames from the host) must agree on the result, and so must all ranks
+    result_consistent = (resident["score"] == last["score"] and resident["flagged"] == last["flagged"])
+    if world > 1:
+        scores = [None] * world
+        dist.all_gather_object(scores, (last["score"], last["flagged"]))
+        result_consistent = result_consistent and all(sc == scores[0] for sc in scores)
     # the PCIe floor of the e2e number: the same pinned -> device copies with no compute behind them
     barrier()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -343,11 +552,13 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    assert result_consistent, f"scores differ between paths / ranks: resident {resident}, e2e {last.get('score')}"
 
     # ---- per-stage numbers and the dominant kernel's roofline
     pk = peaks()
     per_step = {k: v / args.steps for k, v in stage_ms.items()}
-    flops_pnet, bytes_pnet, _, tflops_pnet = pnet_work(H, W)
+    geom = pyramid_geometry(an, H, W)
+    flops_pnet, bytes_pnet, _, tflops_pnet = pnet_work(geom)
     S = an.crop_size
     flops_facenet = 2 * (233.3e6 if S == 80 else 1417.7e6)
     stages = {}
@@ -358,6 +569,7 @@ def main():
                 pyr_px = bytes_pnet // 12
                 d["algo_bytes_per_frame"] = 3 * H * W + pyr_px * 12
                 d["achieved_gbs"] = d["algo_bytes_per_frame"] * n_local / (ms * 1e-3) / 1e9
+                d["frac_of_hbm_peak"] = d["achieved_gbs"] / pk["hbm_gbs"]
             if name == "pnet":
                 d["algo_flops_per_frame"] = flops_pnet
                 d["achieved_tflops_fp32"] = flops_pnet * n_local / (ms * 1e-3) / 1e12
@@ -366,6 +578,7 @@ def main():
             if name == "facenet":
                 d["algo_flops_per_crop"] = flops_facenet
                 d["achieved_tflops_bf16"] = flops_facenet * n_local / (ms * 1e-3) / 1e12
+                d["frac_of_sustained_bf16"] = d["achieved_tflops_bf16"] / pk["bf16_sustained"]
         stages[name] = d
     dom = max(per_step, key=per_step.get)
     n_chunks = len(M.chunk_schedule(n_local, args.resident_chunk))
@@ -376,8 +589,8 @@ def main():
         roof = {"kernel": "facenet (conv_umma_kernel x103 + stem/pool/head)", "bound": "tensor", "achieved": ach,
                 "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None}
     elif dom == "pnet":
-        # conv2 + conv3 (85 % of the FLOPs) run on the tensor pipe (conv2 mma.sync, conv3 tcgen05), conv1 on the FMA pipe;
-        # HBM traffic is the pyramid read once (ncu: traffic == algorithmic bytes), far from the HBM roof
+        # conv2 + conv3 (85 % of the FLOPs) run on the tensor pipe, conv1 on the FMA pipe; HBM traffic is the pyramid read
+        # once (ncu: traffic == algorithmic bytes), far from the HBM roof
         ach = flops_pnet * n_local / (per_step[dom] * 1e-3) / 1e12
         roof = {"kernel": "pnet_kernel", "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_sustained"], "traffic": None,
@@ -387,50 +600,55 @@ def main():
                         "the HBM peak" % (3 * tflops_pnet * n_local / (per_step[dom] * 1e-3) / 1e12,
                                           bytes_pnet * n_local / (per_step[dom] * 1e-3) / 1e9,
                                           bytes_pnet * n_local / (per_step[dom] * 1e-3) / 1e9 / pk["hbm_gbs"])}
+        roof["algorithmic_bytes_per_launch"] = bytes_pnet * frames_per_launch
     else:
         ach = (3 * H * W) * n_local / (per_step[dom] * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": None}
-    if dom == "pnet" and args.workload == "720p30_single" and frames_per_launch == 225:
-        # dram__bytes_read.sum + dram__bytes_write.sum of one pnet_kernel launch (225 frames), ncu --set full capture
-        # summarised in profiles/r01e_pnet_full.md (1.8176 GB + 4.5 MB): the fp32 pyramid of the chunk read exactly once
-        roof["traffic"] = 1822.1e6
-        roof["traffic_unit"] = "bytes/launch (ncu, profiles/r01e_pnet_full.md)"
-        roof["algorithmic_bytes_per_launch"] = bytes_pnet * frames_per_launch
+    kname = {"pnet": "pnet_kernel", "pyramid": "pyramid_sep_kernel", "facenet": "conv_umma_kernel"}.get(dom, dom)
+    rec = recorded_traffic(kname, args.workload, frames_per_launch)
+    if rec is not None:
+        roof["traffic"] = rec["bytes"]
+        roof["traffic_unit"] = "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+        roof["traffic_source"] = rec["source"]
     roof["peak_source"] = pk["source"]
     roof["launch_ms"] = dom_ms_launch
     roof["frames_per_launch"] = frames_per_launch
 
-    cpu_baseline = None
+    cpu_baseline = parity = None
     if world == 1 and not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import helpers
         from oracle.reference_run import reference_run_frames
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        mt, fn = helpers.oracle_mtcnn(), helpers.oracle_facenet()
+        mt, fn, helpers = oracle_models()
         nfr = min(args.cpu_frames, n_local)
-        frames = [clip.frame(i * stride) for i in range(nfr)]       # regenerated: the staging buffer is write-combined (slow to read back)
+        frames = wl.sample_frames(nfr)
         reference_run_frames(iter(frames[:2]), 7, W, H, mt, fn)            # warm-up
         t0 = time.perf_counter()
-        reference_run_frames(iter(frames), 7, W, H, mt, fn)
+        ref_trace = reference_run_frames(iter(frames), 7, W, H, mt, fn)
         dt = time.perf_counter() - t0
         cpu_baseline = {"value": nfr / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"first {nfr} processed frames of the workload clip, oracle MTCNN+FaceNet+consistency (torch CPU fp32)"}
+                        "sample": f"first {nfr} processed frames of the workload, oracle MTCNN+FaceNet+consistency (torch CPU fp32, {cores} threads)"}
+        # the same trace is the checker of the GPU numbers above (never the thing measured)
+        parity = parity_check(wl, mt, fn, helpers, ref_trace, out_resident, nfr)
+    sweep = None
+    if world == 1 and not args.no_facenet_sweep:
+        sweep = facenet_sweep(an, torch, pk)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16 tensor-core FaceNet (fp32 accumulate) + fp32 MTCNN + u8/int pre-processing", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload]["desc"], "frame": [H, W], "fps": clip.fps, "stride": stride,
-                   "processed_frames_per_gpu": n_local, "chunk": args.resident_chunk, "e2e_chunk": args.chunk,
-                   "cascade": "tail of chunk k (NMS, crops, R-Net, O-Net, crop-align) on a second stream under the pyramid of chunk k+1",
-                   "crop": S,
-                   "weights": {"mtcnn": an.mtcnn_source, "facenet": an.facenet_source},
-                   "cache": "inputs larger than L2 (%.2f GB of frames per step per GPU)" % (n_local * H * W * 3 / 1e9),
-                   "sharding": "contiguous frame ranges + embedding halo all-gather" if world > 1 else "single GPU",
-                   "host_cpus_bound_per_rank": numa,
-                   "host_staging": {"wc": "page-locked write-combined (trl_host_alloc)", "pinned": "page-locked"}.get(args.staging, args.staging)},
+        "dtype": "bf16 tensor-core FaceNet (fp32 accumulate) + fp32 MTCNN + u8/int pre-processing",
+        "data": "bundled clip" if wl.kind == "file" else "synthetic",
+        "config": wl.config(S, {"mtcnn": an.mtcnn_source, "facenet": an.facenet_source}),
+        "run_config": {"chunk": args.resident_chunk, "e2e_chunk": args.chunk,
+                       "cascade": "tail of chunk k (NMS, crops, R-Net, O-Net, crop-align) on a second stream under the pyramid of chunk k+1",
+                       "cache": "inputs larger than L2 (%.2f GB of frames per step per GPU)" % (n_local * H * W * 3 / 1e9),
+                       "sharding": ("contiguous frame ranges; one all-gather of shard records (flags + boundary embeddings), "
+                                    "cross-shard comparisons resolved on device") if world > 1 else "single GPU",
+                       "clips_in_batch": len(wl.clips) if wl.clips else 1,
+                       "host_cpus_bound_per_rank": numa,
+                       "host_staging": {"wc": "page-locked write-combined (trl_host_alloc)", "pinned": "page-locked"}.get(args.staging, args.staging)},
         "video_frames_per_s": value * stride,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps, "h2d_only_ms_per_step": ms_h2d_only,
@@ -440,8 +658,14 @@ def main():
         "roofline": roof,
         "stages": stages,
         "cpu_baseline": cpu_baseline,
-        "result": {"score": last.get("score"), "flagged_frames": last.get("flagged")},
+        "parity_check": parity,
+        "facenet_sweep": sweep,
+        "result": {"score": last.get("score") if wl.clips is None else None,
+                   "clip_scores": (last.get("score")[:8] if wl.clips is not None else None),
+                   "flagged_frames": last.get("flagged"), "paths_and_ranks_agree": bool(result_consistent)},
     }
+    if wl.kind == "file":
+        line["host_decode_s"] = wl.decode_s
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -125,6 +125,7 @@ int trl_create(int device, const trl_weights_t* w, const trl_config_t* cfg, trl_
   if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(TRL_E_CUDA); }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { c->err = "cudaGetDeviceProperties failed"; return fail(TRL_E_CUDA); }
+  c->num_sms = prop.multiProcessorCount;
   if (prop.major != 10) {
     c->err = "trl_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ", this library is built for sm_100a only";
     return fail(TRL_E_CUDA);

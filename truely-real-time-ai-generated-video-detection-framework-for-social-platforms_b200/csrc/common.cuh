@@ -9,7 +9,6 @@
 
 #include "../../include/truely_b200.h"
 
-#define TRL_NUM_SMS 148
 
 // ----------------------------------------------------------------------------- candidates
 // One detection candidate as it travels through the cascade (40 bytes).
@@ -137,6 +136,7 @@ struct FaceNetEngine;   // facenet_plan.cu
 
 struct trl_ctx {
   int device = 0;
+  int num_sms = 0;               // cudaDeviceProp::multiProcessorCount of `device` (148 on B200): persistent-kernel grid size
   trl_config_t cfg{};
   std::string err;
   long long launches = 0;

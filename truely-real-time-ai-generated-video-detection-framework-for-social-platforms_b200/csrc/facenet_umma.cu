@@ -7,8 +7,9 @@
 //   elements (the zero padding) are filled by the TMA unit, strided convs use the map's element strides.
 //   1x1 stride-1 convs use a flat (channels x pixels) view, so tiles carry no spatial padding at all.
 // * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) is issued by one thread; accumulators live in TMEM.
-// * warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue (tcgen05.ld -> bias / residual /
-//   ReLU -> bf16 -> channel slice of the destination: concat-free Inception blocks).
+// * warp 0 = TMA producer of the A operand, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue (two warps per
+//   TMEM lane group, one per column half: tcgen05.ld -> bias / residual / ReLU -> bf16 -> channel slice of the
+//   destination: concat-free Inception blocks), warp 10 = TMA producer of the weight and residual tiles.
 // * smem ring of `stages` {A,B} tiles guarded by full/empty mbarriers; tcgen05.commit releases a stage.
 // Every mbarrier wait is bounded (trap after ~2 s) so a protocol bug surfaces as a CUDA error, never as a hang.
 #include "facenet.cuh"
@@ -537,7 +538,7 @@ int launch_conv_umma(trl_ctx* c, const ConvOp& op, int n, cudaStream_t s) {
   const uint32_t acc_cols = op.block_n <= 32 ? 32u : op.block_n <= 64 ? 64u : op.block_n <= 128 ? 128u : 256u;
   const int n_ntiles = op.Cout / op.block_n;
   const long long total = (long long)tiles_w * tiles_h * tiles_n * n_ntiles;
-  const int grid = (int)(total < TRL_NUM_SMS ? total : TRL_NUM_SMS);
+  const int grid = (int)(total < c->num_sms ? total : c->num_sms);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);

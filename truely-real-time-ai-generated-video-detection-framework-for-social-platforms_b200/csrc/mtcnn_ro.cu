@@ -431,7 +431,7 @@ int launch_rnet_ex(trl_ctx* c, const float* d_in, int n_slots, const int* d_coun
   if (n_slots <= 0) return TRL_OK;
   const int n_frames = per_frame_cap > 0 ? n_slots / per_frame_cap : 0;
   const bool compact = per_frame_cap > 0 && n_frames <= SLOTMAP_MAX_FRAMES;
-  const int grid = compact ? std::min(n_slots, TRL_NUM_SMS * 6) : n_slots;       // ~37 KB of shared memory per CTA: 6 CTAs / SM
+  const int grid = compact ? std::min(n_slots, c->num_sms * 6) : n_slots;       // ~37 KB of shared memory per CTA: 6 CTAs / SM
   ro::rnet_kernel<<<grid, 256, ro::r::S_TOTAL * 4, s>>>(d_in, c->d_rnet, d_count, per_frame_cap, n_frames, n_slots, d_prob, d_reg);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
@@ -442,7 +442,7 @@ int launch_onet_ex(trl_ctx* c, const float* d_in, int n_slots, const int* d_coun
   if (n_slots <= 0) return TRL_OK;
   const int n_frames = per_frame_cap > 0 ? n_slots / per_frame_cap : 0;
   const bool compact = per_frame_cap > 0 && n_frames <= SLOTMAP_MAX_FRAMES;
-  const int grid = compact ? std::min(n_slots, TRL_NUM_SMS) : n_slots;           // ~168 KB of shared memory per CTA: 1 CTA / SM
+  const int grid = compact ? std::min(n_slots, c->num_sms) : n_slots;           // ~168 KB of shared memory per CTA: 1 CTA / SM
   ro::onet_kernel<<<grid, 512, ro::o::S_TOTAL * 4, s>>>(d_in, c->d_onet, d_count, per_frame_cap, n_frames, n_slots, d_prob, d_reg);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;

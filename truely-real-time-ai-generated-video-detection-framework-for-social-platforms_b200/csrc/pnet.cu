@@ -854,9 +854,9 @@ static void fill_head(const trl_ctx* c, pnet::Params* p) {
 }
 
 // persistent grid: one CTA per SM (or per tile when there are fewer tiles)
-static int grid_for(int blocks, int B) {
+static int grid_for(const trl_ctx* c, int blocks, int B) {
   const long long total = (long long)blocks * B;
-  return (int)(total < TRL_NUM_SMS ? total : TRL_NUM_SMS);
+  return (int)(total < c->num_sms ? total : c->num_sms);
 }
 
 int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float* d_prob, float* d_reg, cudaStream_t s) {
@@ -884,7 +884,7 @@ int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float
   }
   p.thr = 2.f; p.cap = 0; p.capflag = c->d_cap;
   if (B == 0) return TRL_OK;
-  pnet_kernel<<<grid_for(L.tiles, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
+  pnet_kernel<<<grid_for(c, L.tiles, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
@@ -921,7 +921,7 @@ int launch_pnet_candidates(trl_ctx* c, const float* d_pyr, int B, const PyramidG
     if (rc != TRL_OK) return rc;
   }
   if (blocks == 0 || B == 0) return TRL_OK;
-  pnet_kernel<<<grid_for(blocks, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
+  pnet_kernel<<<grid_for(c, blocks, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }

@@ -1,7 +1,8 @@
 // K1 pyramid (area resample + normalise), K7 candidate crop-resample, K10 crop-align.
 // All three are HBM/L2-bound byte kernels with exact integer window arithmetic.
 //
-// Parity notes (checked on CPU against torch 2.11 / OpenCV 4.13, see tests/test_host_numerics.py):
+// Parity notes (checked on CPU against torch 2.11 / OpenCV 4.13, see tests/test_oracle.py: the numpy restatements of
+// interpolate(area) and cv2.resize are proven bit exact there, tests/test_gpu_stages.py then holds the kernels to them):
 //  * F.interpolate(mode="area") == adaptive_avg_pool2d: window [floor(i*H/oh), ceil((i+1)*H/oh)),
 //    value = (sum / kh) / kw in fp32 (two divisions, in that order) -- bit exact with ATen.
 //  * (x - 127.5) * 0.0078125 : one rounding (the subtract), the multiply is exact.
@@ -419,7 +420,7 @@ int launch_crop_resample_ex(trl_ctx* c, const uint8_t* d_frames, int B, int H, i
   const bool compact = per_frame_cap > 0 && n_frames <= SLOTMAP_MAX_FRAMES;
   const int split = compact ? (size == 24 ? 4 : 8) : 1;
   const long long slots = (long long)n_slots * split;
-  const int grid = compact ? (int)(slots < TRL_NUM_SMS * 8 ? slots : TRL_NUM_SMS * 8) : n_slots;
+  const int grid = compact ? (int)(slots < c->num_sms * 8 ? slots : c->num_sms * 8) : n_slots;
   crop_resample_kernel<<<grid, 256, 0, s>>>(d_frames, H, W, d_pad, d_img, d_count, per_frame_cap, n_frames, n_slots, split, size, d_out);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
