@@ -66,6 +66,9 @@ typedef struct {
   int cand_cap_frame;     /* capacity: R-Net inputs per frame (candidates surviving stage-1 NMS); default 1024, at most 16384 */
   int box_cap_frame;      /* capacity: O-Net inputs / final boxes per frame; default 128, at most 2048 */
   int facenet_impl;       /* 0 = tcgen05 implicit-GEMM path (product); 1 = SIMT direct-conv kernels (validation) */
+  int pnet_precision;     /* P-Net conv2/conv3 tensor-core operands: 0 = 3-term fp16 split (maps within 2e-5 of the fp32
+                             reference); 1 = single-pass fp16 (a third of the tensor work; maps within ~2e-3, parity judged at
+                             cascade level: same face count, IoU >= 0.95) */
 } trl_config_t;
 
 void trl_default_config(trl_config_t* cfg);

@@ -29,7 +29,7 @@ class Weights(C.Structure):
 class Config(C.Structure):
     _fields_ = [("min_face_size", C.c_int), ("thresholds", C.c_float * 3), ("factor", C.c_double),
                 ("crop_size", C.c_int), ("cand_cap_scale", C.c_int), ("cand_cap_frame", C.c_int),
-                ("box_cap_frame", C.c_int), ("facenet_impl", C.c_int)]
+                ("box_cap_frame", C.c_int), ("facenet_impl", C.c_int), ("pnet_precision", C.c_int)]
 
 
 _P = C.c_void_p

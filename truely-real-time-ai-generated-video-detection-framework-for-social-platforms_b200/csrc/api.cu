@@ -47,6 +47,7 @@ void trl_default_config(trl_config_t* cfg) {
   cfg->cand_cap_frame = 1024;
   cfg->box_cap_frame = 128;
   cfg->facenet_impl = 0;
+  cfg->pnet_precision = 0;
 }
 
 const char* trl_last_error(const trl_ctx_t* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }

@@ -231,6 +231,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // (tcgen05) and do the head epilogue.  The pooled conv1 tile is double buffered between the groups (full / empty
 // mbarriers), so conv1 of tile k+1 overlaps conv2 / conv3 of tile k and the FMA pipe, the tensor pipe and the
 // issue slots are busy at the same time.  Weights are loaded once per CTA.
+// TERMS = 3: the 3-term fp16 operand split (fp32-equivalent maps).  TERMS = 1: single-pass fp16 operands (hi parts only,
+// fp32 accumulate) for conv2 / conv3 -- a third of the tensor work, maps within ~1e-3 of the fp32 oracle instead of 2e-6;
+// selected by trl_config_t.pnet_precision and judged at cascade level (same face count, IoU >= 0.95).
+template <int TERMS>
 __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restrict__ wpacked, const __grid_constant__ Params p) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t mma_bar[2 * C3TILES];   // [accumulator set][conv3 M tile]: tcgen05.commit arrives
@@ -431,10 +435,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
       }
 #pragma unroll
       for (int cp = 0; cp < 5; ++cp) {
-        uint32_t hi, lo;
-        split_h2(m[2 * cp] * SA, m[2 * cp + 1] * SA, hi, lo);
-        p1_s[cp * P1PL + item] = hi;
-        p1_s[(P1WORDS + cp) * P1PL + item] = lo;
+        if (TERMS == 3) {
+          uint32_t hi, lo;
+          split_h2(m[2 * cp] * SA, m[2 * cp + 1] * SA, hi, lo);
+          p1_s[cp * P1PL + item] = hi;
+          p1_s[(P1WORDS + cp) * P1PL + item] = lo;
+        } else {
+          const __half2 h = __floats2half2_rn(m[2 * cp] * SA, m[2 * cp + 1] * SA);
+          p1_s[cp * P1PL + item] = *reinterpret_cast<const uint32_t*>(&h);
+        }
       }
     }
       mbar_arrive(&p1_full[k & 1]);
@@ -467,7 +476,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
               const uint64_t a_hi = umma_desc(a_base + a_off, APL, 128u);
               const uint64_t a_lo = umma_desc(a_base + 2u * APL + a_off, APL, 128u);
               const uint64_t b_hl = umma_desc(b_base + (uint32_t)tap * 2048u, 1024u, 128u);        // rows 0-31 w_hi, 32-63 w_lo
-              if (tile_n64(tile)) {
+              if (TERMS == 1) {
+                umma_f16(d, a_hi, b_hl, IDESC32, tap > 0 ? 1u : 0u);        // rows 0-31 of the B tile: w_hi
+              } else if (tile_n64(tile)) {
                 umma_f16(d, a_hi, b_hl, IDESC64, tap > 0 ? 1u : 0u);
                 umma_f16(d, a_lo, b_hl, IDESC32, 1u);
               } else {
@@ -508,7 +519,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
       for (int c0 = 0; c0 < 32; c0 += 16) {
         float dh[16];
         tmem_ld16(taddr + c0, dh);
-        if (tile_n64(tile)) {                           // N = 64 tiles: add the a_hi x w_lo column block
+        if (TERMS == 3 && tile_n64(tile)) {             // N = 64 tiles: add the a_hi x w_lo column block
           float dl[16];
           tmem_ld16(taddr + 32 + c0, dl);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -611,29 +622,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
       for (int s = 0; s < 6; ++s) {
         const int o0 = tab[8 * s + t], o1 = tab[8 * s + t + 4];
         const uint4 bh = *reinterpret_cast<const uint4*>(&wu[W2 + ((2 * s + 0) * 32 + lane) * 4]);
-        const uint4 bl = *reinterpret_cast<const uint4*>(&wu[W2 + ((2 * s + 1) * 32 + lane) * 4]);
+        uint4 bl = make_uint4(0u, 0u, 0u, 0u);
+        if (TERMS == 3) bl = *reinterpret_cast<const uint4*>(&wu[W2 + ((2 * s + 1) * 32 + lane) * 4]);
         uint32_t ah[3][4], al[3][4];
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
           if (q >= nq) continue;               // warp uniform
-          ah[q][0] = p1h[base[q] + o0];        al[q][0] = p1l[base[q] + o0];
-          ah[q][1] = p1h[base[q] + 8 + o0];    al[q][1] = p1l[base[q] + 8 + o0];
-          ah[q][2] = p1h[base[q] + o1];        al[q][2] = p1l[base[q] + o1];
-          ah[q][3] = p1h[base[q] + 8 + o1];    al[q][3] = p1l[base[q] + 8 + o1];
-        }
-        // the three terms of one accumulator are dependent: issue the 6 independent accumulators between them
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          if (q < nq) {
-            mma_f16(acc[q][0], al[q][0], al[q][1], al[q][2], al[q][3], bh.x, bh.y);
-            mma_f16(acc[q][1], al[q][0], al[q][1], al[q][2], al[q][3], bh.z, bh.w);
+          ah[q][0] = p1h[base[q] + o0];
+          ah[q][1] = p1h[base[q] + 8 + o0];
+          ah[q][2] = p1h[base[q] + o1];
+          ah[q][3] = p1h[base[q] + 8 + o1];
+          if (TERMS == 3) {
+            al[q][0] = p1l[base[q] + o0];
+            al[q][1] = p1l[base[q] + 8 + o0];
+            al[q][2] = p1l[base[q] + o1];
+            al[q][3] = p1l[base[q] + 8 + o1];
           }
         }
+        // the three terms of one accumulator are dependent: issue the 6 independent accumulators between them
+        if (TERMS == 3) {
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          if (q < nq) {
-            mma_f16(acc[q][0], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bl.x, bl.y);
-            mma_f16(acc[q][1], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bl.z, bl.w);
+          for (int q = 0; q < 3; ++q) {
+            if (q < nq) {
+              mma_f16(acc[q][0], al[q][0], al[q][1], al[q][2], al[q][3], bh.x, bh.y);
+              mma_f16(acc[q][1], al[q][0], al[q][1], al[q][2], al[q][3], bh.z, bh.w);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            if (q < nq) {
+              mma_f16(acc[q][0], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bl.x, bl.y);
+              mma_f16(acc[q][1], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bl.z, bl.w);
+            }
           }
         }
 #pragma unroll
@@ -660,13 +680,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
             const float v2 = prelu(fmaf(acc[q][1][2 * h], inv, bias2), al2);
             const float v3 = prelu(fmaf(acc[q][1][2 * h + 1], inv, bias3), al3);
             range_bad |= fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3))) > ACT_MAX;
-            uint32_t h0, l0, h1, l1;
-            split_h2(v0 * SA, v1 * SA, h0, l0);
-            split_h2(v2 * SA, v3 * SA, h1, l1);
-            c2_s[0 * C2PLANE + n * 4 + t] = h0;      // hi, channels 0-7   (a warp writes 32 consecutive words)
-            c2_s[1 * C2PLANE + n * 4 + t] = h1;      // hi, channels 8-15
-            c2_s[2 * C2PLANE + n * 4 + t] = l0;
-            c2_s[3 * C2PLANE + n * 4 + t] = l1;
+            if (TERMS == 3) {
+              uint32_t h0, l0, h1, l1;
+              split_h2(v0 * SA, v1 * SA, h0, l0);
+              split_h2(v2 * SA, v3 * SA, h1, l1);
+              c2_s[0 * C2PLANE + n * 4 + t] = h0;      // hi, channels 0-7   (a warp writes 32 consecutive words)
+              c2_s[1 * C2PLANE + n * 4 + t] = h1;      // hi, channels 8-15
+              c2_s[2 * C2PLANE + n * 4 + t] = l0;
+              c2_s[3 * C2PLANE + n * 4 + t] = l1;
+            } else {
+              const __half2 h0 = __floats2half2_rn(v0 * SA, v1 * SA), h1 = __floats2half2_rn(v2 * SA, v3 * SA);
+              c2_s[0 * C2PLANE + n * 4 + t] = *reinterpret_cast<const uint32_t*>(&h0);
+              c2_s[1 * C2PLANE + n * 4 + t] = *reinterpret_cast<const uint32_t*>(&h1);
+            }
           }
         }
       }
@@ -838,7 +864,8 @@ int pnet_pack_weights(trl_ctx* c, const float* h, size_t len) {
   pk[SC + 0] = 1.f / (SA * s2);
   TRL_CUDA(c, cudaMalloc(&c->d_pnet_packed, WTOTAL * sizeof(float)));
   TRL_CUDA(c, cudaMemcpy(c->d_pnet_packed, pk.data(), WTOTAL * sizeof(float), cudaMemcpyHostToDevice));
-  TRL_CUDA(c, cudaFuncSetAttribute(pnet::pnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  TRL_CUDA(c, cudaFuncSetAttribute(pnet::pnet_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  TRL_CUDA(c, cudaFuncSetAttribute(pnet::pnet_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   return TRL_OK;
 }
 
@@ -884,7 +911,8 @@ int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float
   }
   p.thr = 2.f; p.cap = 0; p.capflag = c->d_cap;
   if (B == 0) return TRL_OK;
-  pnet_kernel<<<grid_for(c, L.tiles, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
+  if (c->cfg.pnet_precision == 1) pnet_kernel<1><<<grid_for(c, L.tiles, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
+  else pnet_kernel<3><<<grid_for(c, L.tiles, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
@@ -921,7 +949,8 @@ int launch_pnet_candidates(trl_ctx* c, const float* d_pyr, int B, const PyramidG
     if (rc != TRL_OK) return rc;
   }
   if (blocks == 0 || B == 0) return TRL_OK;
-  pnet_kernel<<<grid_for(c, blocks, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
+  if (c->cfg.pnet_precision == 1) pnet_kernel<1><<<grid_for(c, blocks, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
+  else pnet_kernel<3><<<grid_for(c, blocks, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }

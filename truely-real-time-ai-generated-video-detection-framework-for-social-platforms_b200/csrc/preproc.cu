@@ -325,11 +325,15 @@ int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, con
   if (smem > 200 * 1024) TRL_FAIL(c, TRL_E_INVALID, "frame width %d too large for the pyramid kernel", W);
   const size_t total = (size_t)B * H * W * 3;
   const bool aligned = (3 * W) % 4 == 0;
-  if (smem > c->pyr_smem_set) {
-    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    c->pyr_smem_set = smem;
+  if (!c->pyr_smem_set) {
+    // The opt-in is a property of the kernel function, shared by every context of the process: always raise it to the
+    // kernel's ceiling (a per-context "largest size so far" let a second context with smaller frames lower it under the
+    // first one's feet -> invalid-argument launches).  The launch itself still asks only for what this shape needs.
+    const int cap = 200 * 1024;
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    c->pyr_smem_set = cap;
   }
   dim3 grid(blocks, B);
   const bool rows16 = (3 * W) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 15) == 0;

@@ -52,7 +52,8 @@ class Analyzer:
     (the reference rebuilds both models on every call, server/model.py:18-19; behaviourally invisible)."""
 
     def __init__(self, device: int = 0, facenet_impl: int | None = None, crop_size: int = CROP_SIZE,
-                 cand_cap_scale: int | None = None, cand_cap_frame: int | None = None, box_cap_frame: int | None = None):
+                 cand_cap_scale: int | None = None, cand_cap_frame: int | None = None, box_cap_frame: int | None = None,
+                 pnet_precision: int | None = None):
         import torch
         self.torch = torch
         self.lib = L.load()
@@ -66,6 +67,9 @@ class Analyzer:
         if facenet_impl is None:
             facenet_impl = int(os.environ.get("TRUELY_FACENET_IMPL", "0"))
         cfg.facenet_impl = facenet_impl
+        if pnet_precision is None:
+            pnet_precision = int(os.environ.get("TRUELY_PNET_PRECISION", "0"))
+        cfg.pnet_precision = pnet_precision
         if cand_cap_scale:
             cfg.cand_cap_scale = cand_cap_scale
         if cand_cap_frame:
@@ -129,6 +133,11 @@ class Analyzer:
         saved = (self.cfg.cand_cap_scale, self.cfg.cand_cap_frame, self.cfg.box_cap_frame)
         B, H, Wd, _ = d_frames.shape
         self.stream.synchronize()
+        try:
+            self.check_capacity()          # drop a flag left by work that was still in flight (the caller redoes all of it)
+        except L.TrlError as e:
+            if e.code != L.TRL_E_CAPACITY:
+                raise
         self.set_capacity(*self.BIG_CAPS)
         try:
             with self.torch.cuda.stream(self.stream):
