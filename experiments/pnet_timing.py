@@ -4,6 +4,7 @@ The timing .so is built next to this script and never replaces the product libra
 import ctypes as C
 import glob
 import os
+os.environ.setdefault("TRUELY_ALLOW_SYNTHETIC", "1")
 import subprocess
 import sys
 

@@ -69,6 +69,11 @@ typedef struct {
   int pnet_precision;     /* P-Net conv2/conv3 tensor-core operands: 0 = 3-term fp16 split (maps within 2e-5 of the fp32
                              reference); 1 = single-pass fp16 (a third of the tensor work; maps within ~2e-3, parity judged at
                              cascade level: same face count, IoU >= 0.95) */
+  int mode;               /* 0 = the reference's crop path (server/model.py:49-58): truncated + clamped box, cv2.resize
+                             INTER_LINEAR to crop_size, F.to_tensor (/255).  1 = "mode B", upstream facenet_pytorch's own
+                             face crop as the north star words it: extract_face (margin-adjusted box, cv2.resize INTER_AREA
+                             to crop_size, normally 160) + fixed_image_standardization ((x - 127.5) / 128) */
+  int margin;             /* mode B: extract_face margin in pixels of the crop_size image (upstream default 0) */
 } trl_config_t;
 
 void trl_default_config(trl_config_t* cfg);
@@ -127,6 +132,25 @@ int trl_crop_align(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W,
 /* K11: F.to_tensor (/255) + InceptionResnetV1.forward (server/model.py:58-59).
  * d_crops uint8 [N,S,S,3] BGR -> d_emb float32 [N,512], unit norm. */
 int trl_facenet(trl_ctx_t* ctx, const uint8_t* d_crops, int n, int S, float* d_emb, void* stream);
+
+/* Mode B building blocks (upstream facenet_pytorch models/utils/detect_face.py, SURVEY.md Appendix A "Mode-B extras").
+ * trl_extract_face: extract_face(img, boxes[0], image_size, margin) per frame -- box arithmetic in fp32, int() truncation,
+ *   crop, cv2.resize(.., (image_size, image_size), interpolation=cv2.INTER_AREA) on uint8, bit exact with OpenCV
+ *   (integer-ratio, general-area and enlarging code paths).  Same argument meaning as trl_crop_align.
+ * trl_extract_faces_all: keep_all -- every box of every frame (d_boxes float32 [B, box_stride], rows of 5 floats per box,
+ *   at most box_cap boxes per frame).  Faces are numbered frame by frame: d_face_off int32 [B+1] receives the prefix
+ *   (face i of frame b is face d_face_off[b] + i of the batch, d_face_off[B] = total), d_face_frame int32 [max_faces]
+ *   (optional) the frame of each face; d_box_int [max_faces,4], d_valid [max_faces], d_crops [max_faces,S,S,3].  More than
+ *   max_faces faces is reported through trl_check_capacity (stage 6), never silently dropped.
+ * trl_facenet_norm: trl_facenet with the input normalisation chosen per call: 0 = F.to_tensor (x / 255, the reference),
+ *   1 = fixed_image_standardization ((x - 127.5) / 128, what MTCNN.forward applies with post_process=True). */
+int trl_extract_face(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
+                     const int* d_nfaces, int image_size, int margin, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops,
+                     void* stream);
+int trl_extract_faces_all(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
+                          int box_cap, const int* d_nfaces, int image_size, int margin, int max_faces, int* d_face_off,
+                          int* d_face_frame, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops, void* stream);
+int trl_facenet_norm(trl_ctx_t* ctx, const uint8_t* d_crops, int n, int S, int norm, float* d_emb, void* stream);
 
 /* K12: cosine similarity against the previous face-bearing frame and the 0.99 test (server/model.py:60-62).
  * d_emb [B,512], d_valid [B]; d_halo_emb [512] (or NULL) is the last face-bearing embedding before this

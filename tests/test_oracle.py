@@ -199,3 +199,34 @@ def test_bundled_clip_golden_pins_the_oracle():
             assert np.allclose(f.emb, g["emb"][k], atol=2e-5)
             if f.sim is not None:
                 assert abs(f.sim - float(g["sim"][k])) < 1e-5
+
+
+def test_inter_area_restatement_is_bit_exact_with_opencv():
+    """oracle.mode_b.resize_area_u8 (what crop_area_kernel mirrors) against the installed cv2.resize(INTER_AREA): the
+    integer-ratio fast path (incl. the 2x2 rounding special case), the general float area path, and the bilinear path with
+    area coefficients for enlarged / mixed crops."""
+    from oracle.mode_b import resize_area_u8
+    rng = np.random.default_rng(0)
+    cases = [(320, 320), (480, 320), (160, 160), (161, 200), (200, 260), (233, 177), (640, 640), (80, 95), (100, 100),
+             (159, 161), (161, 159), (400, 123), (50, 300), (800, 480), (163, 163), (319, 321), (21, 23)]
+    cases += [(int(rng.integers(20, 500)), int(rng.integers(20, 500))) for _ in range(12)]
+    for h, w in cases:
+        src = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for S in (160, 80):
+            assert np.array_equal(resize_area_u8(src, S, S), cv2.resize(src, (S, S), interpolation=cv2.INTER_AREA)), (h, w, S)
+
+
+def test_mode_b_extract_face_semantics():
+    """upstream extract_face: margin-adjusted truncated box, INTER_AREA resize, standardisation (x - 127.5) / 128."""
+    from oracle.mode_b import extract_box, extract_face, fixed_image_standardization
+    assert extract_box([10.7, 20.2, 110.9, 150.5], 160, 0, 640, 360) == [10, 20, 110, 150]
+    assert extract_box([-5.0, -3.0, 700.0, 400.0], 160, 0, 640, 360) == [0, 0, 640, 360]
+    b = extract_box([100.0, 100.0, 200.0, 260.0], 160, 32, 640, 360)          # margin 32: 25 px wider, 40 px taller
+    assert b == [87, 80, 212, 280]
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (360, 640, 3), dtype=np.uint8)
+    face, bb = extract_face(img, [100.3, 50.2, 300.9, 310.1], 160, 0)
+    assert face.shape == (160, 160, 3) and bb == [100, 50, 300, 310]
+    t = fixed_image_standardization(face)
+    assert t.shape == (3, 160, 160) and float(t.min()) >= -127.5 / 128 and float(t.max()) <= 127.5 / 128
+    assert extract_face(img, [700.0, 10.0, 800.0, 90.0], 160, 0)[0] is None       # box outside the frame: empty crop

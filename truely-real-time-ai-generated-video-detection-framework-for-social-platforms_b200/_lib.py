@@ -29,7 +29,8 @@ class Weights(C.Structure):
 class Config(C.Structure):
     _fields_ = [("min_face_size", C.c_int), ("thresholds", C.c_float * 3), ("factor", C.c_double),
                 ("crop_size", C.c_int), ("cand_cap_scale", C.c_int), ("cand_cap_frame", C.c_int),
-                ("box_cap_frame", C.c_int), ("facenet_impl", C.c_int), ("pnet_precision", C.c_int)]
+                ("box_cap_frame", C.c_int), ("facenet_impl", C.c_int), ("pnet_precision", C.c_int),
+                ("mode", C.c_int), ("margin", C.c_int)]
 
 
 _P = C.c_void_p
@@ -51,6 +52,10 @@ SIGNATURES = {
     "trl_detect": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "trl_crop_align": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
     "trl_facenet": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "trl_facenet_norm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "trl_extract_face": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "trl_extract_faces_all": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int,
+                                        _P, _P, _P, _P, _P, _P]),
     "trl_consistency": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P]),
     "trl_consistency_clips": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P]),
     "trl_shard_record_bytes": (C.c_size_t, [C.c_int]),

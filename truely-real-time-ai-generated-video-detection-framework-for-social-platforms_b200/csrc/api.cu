@@ -48,6 +48,8 @@ void trl_default_config(trl_config_t* cfg) {
   cfg->box_cap_frame = 128;
   cfg->facenet_impl = 0;
   cfg->pnet_precision = 0;
+  cfg->mode = 0;
+  cfg->margin = 0;
 }
 
 const char* trl_last_error(const trl_ctx_t* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
@@ -123,6 +125,8 @@ int trl_create(int device, const trl_weights_t* w, const trl_config_t* cfg, trl_
              std::to_string(nms_max_n()) + "]";
     return fail(TRL_E_INVALID);
   }
+  if (c->cfg.mode != 0 && c->cfg.mode != 1) { c->err = "trl_create: mode must be 0 (reference) or 1 (mode B)"; return fail(TRL_E_INVALID); }
+  if (c->cfg.margin < 0 || c->cfg.margin >= c->cfg.crop_size) { c->err = "trl_create: margin must be in [0, crop_size)"; return fail(TRL_E_INVALID); }
   if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(TRL_E_CUDA); }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { c->err = "cudaGetDeviceProperties failed"; return fail(TRL_E_CUDA); }
@@ -346,8 +350,38 @@ int trl_facenet(trl_ctx_t* c, const uint8_t* d_crops, int n, int S, float* d_emb
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
   if ((rc = join_tail(c, s)) != TRL_OK) return rc;
-  TIMED(11, facenet_forward(c, d_crops, n, S, d_emb, s));
+  TIMED(11, facenet_forward(c, d_crops, n, S, c->cfg.mode == 1 ? 1 : 0, d_emb, s));
   return TRL_OK;
+}
+
+int trl_facenet_norm(trl_ctx_t* c, const uint8_t* d_crops, int n, int S, int norm, float* d_emb, void* stream) {
+  if (!c || !d_crops || !d_emb || n < 0 || (norm != 0 && norm != 1)) return TRL_E_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if ((rc = join_tail(c, s)) != TRL_OK) return rc;
+  TIMED(11, facenet_forward(c, d_crops, n, S, norm, d_emb, s));
+  return TRL_OK;
+}
+
+int trl_extract_face(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
+                     const int* d_nfaces, int image_size, int margin, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops,
+                     void* stream) {
+  if (!c || !d_frames || !d_boxes || !d_nfaces || !d_box_int || !d_valid || !d_crops) return TRL_E_INVALID;
+  int rc = join_tail(c, (cudaStream_t)stream);
+  if (rc != TRL_OK) return rc;
+  return launch_extract_face(c, d_frames, B, H, W, d_boxes, box_stride, d_nfaces, image_size, margin, d_box_int, d_valid, d_crops,
+                             (cudaStream_t)stream);
+}
+
+int trl_extract_faces_all(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
+                          int box_cap, const int* d_nfaces, int image_size, int margin, int max_faces, int* d_face_off,
+                          int* d_face_frame, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops, void* stream) {
+  if (!c || !d_frames || !d_boxes || !d_nfaces || !d_face_off || !d_box_int || !d_valid || !d_crops || box_stride < 5 * box_cap)
+    return TRL_E_INVALID;
+  int rc = join_tail(c, (cudaStream_t)stream);
+  if (rc != TRL_OK) return rc;
+  return launch_extract_faces_all(c, d_frames, B, H, W, d_boxes, box_stride, box_cap, d_nfaces, image_size, margin, max_faces,
+                                  d_face_off, d_face_frame, d_box_int, d_valid, d_crops, (cudaStream_t)stream);
 }
 
 int trl_consistency(trl_ctx_t* c, const float* d_emb, const uint8_t* d_valid, int B, const float* d_halo_emb,
@@ -394,6 +428,16 @@ int trl_shard_resolve(trl_ctx_t* c, void* d_all_records, int world, int rank, in
                               (cudaStream_t)stream);
 }
 
+// crop of the largest face of every frame: the reference's (server/model.py:49-57) or, in mode B, upstream extract_face
+static int crop_stage(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const int* nf, int* d_box_int, uint8_t* d_valid,
+                      uint8_t* d_crops, cudaStream_t s) {
+  if (c->cfg.mode == 1)
+    return launch_extract_face(c, d_frames, B, H, W, c->d_boxes, c->cfg.box_cap_frame * 5, nf, c->cfg.crop_size, c->cfg.margin,
+                               d_box_int, d_valid, d_crops, s);
+  return launch_crop_align(c, d_frames, B, H, W, c->d_boxes, c->cfg.box_cap_frame * 5, nf, c->cfg.crop_size, d_box_int, d_valid,
+                           d_crops, s);
+}
+
 int trl_detect_align(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, int* d_box_int, uint8_t* d_valid,
                      int* d_nfaces, uint8_t* d_crops, void* stream) {
   if (!c || !d_frames || !d_box_int || !d_valid || !d_crops || B <= 0) return TRL_E_INVALID;
@@ -403,8 +447,7 @@ int trl_detect_align(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W,
   if ((rc = ensure_workspace(c, B, H, W)) != TRL_OK) return rc;
   int* nf = d_nfaces ? d_nfaces : c->d_nfaces;
   if ((rc = detect_impl(c, d_frames, B, H, W, nf, c->d_boxes, nullptr, s)) != TRL_OK) return rc;
-  TIMED(10, launch_crop_align(c, d_frames, B, H, W, c->d_boxes, c->cfg.box_cap_frame * 5, nf, c->cfg.crop_size, d_box_int,
-                              d_valid, d_crops, s));
+  TIMED(10, crop_stage(c, d_frames, B, H, W, nf, d_box_int, d_valid, d_crops, s));
   return TRL_OK;
 }
 
@@ -429,8 +472,7 @@ int trl_detect_align_async(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, 
   cudaStream_t ts = c->tail_stream;
   TRL_CUDA(c, cudaStreamWaitEvent(ts, c->ev_head, 0));
   if ((rc = detect_tail(c, d_frames, B, H, W, nf, c->d_boxes, nullptr, ts)) != TRL_OK) return rc;
-  if ((rc = launch_crop_align(c, d_frames, B, H, W, c->d_boxes, c->cfg.box_cap_frame * 5, nf, c->cfg.crop_size, d_box_int,
-                              d_valid, d_crops, ts)) != TRL_OK) return rc;
+  if ((rc = crop_stage(c, d_frames, B, H, W, nf, d_box_int, d_valid, d_crops, ts)) != TRL_OK) return rc;
   TRL_CUDA(c, cudaEventRecord(c->ev_tail, ts));
   c->tail_pending = true;
   return TRL_OK;
@@ -463,7 +505,7 @@ int trl_process(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, cons
   if ((rc = trl_detect_align(c, d_frames, B, H, W, d_box_int, d_valid, d_nfaces, c->d_crops, stream)) != TRL_OK) return rc;
   // FaceNet runs on all B crops (faceless frames carry a zero crop; their embeddings are never compared):
   // this keeps the whole batch free of host synchronisation.
-  TIMED(11, facenet_forward(c, c->d_crops, B, c->cfg.crop_size, d_emb, s));
+  TIMED(11, facenet_forward(c, c->d_crops, B, c->cfg.crop_size, c->cfg.mode == 1 ? 1 : 0, d_emb, s));
   TIMED(12, launch_consistency(c, d_emb, d_valid, B, nullptr, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
                                d_last_valid, s));
   return TRL_OK;

@@ -230,6 +230,13 @@ int launch_crop_resample(trl_ctx* c, const uint8_t* d_frames, int B, int H, int 
 int launch_crop_align(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
                       const int* d_nfaces, int S, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops, cudaStream_t s);
 
+int launch_extract_face(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
+                        const int* d_nfaces, int S, int margin, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops,
+                        cudaStream_t s);
+int launch_extract_faces_all(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
+                             int box_cap, const int* d_nfaces, int S, int margin, int max_faces, int* d_face_off,
+                             int* d_face_frame, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops, cudaStream_t s);
+
 int pnet_pack_weights(trl_ctx* c, const float* h_pnet, size_t len);
 // maps mode: d_prob/d_reg non-null, one level.  candidate mode: all levels, thresholded append.
 int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float* d_prob, float* d_reg, cudaStream_t s);
@@ -242,7 +249,8 @@ int launch_onet(trl_ctx* c, const float* d_in, int n_max, const int* d_count, fl
 
 int facenet_create(trl_ctx* c, const float* h_blob, size_t len);
 void facenet_destroy(trl_ctx* c);
-int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, float* d_emb, cudaStream_t s);
+// norm: 0 = F.to_tensor (x / 255, the reference, server/model.py:58); 1 = fixed_image_standardization ((x - 127.5) / 128)
+int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, int norm, float* d_emb, cudaStream_t s);
 
 int nms_init(trl_ctx* c);
 int nms_max_n();

@@ -42,8 +42,10 @@ struct FaceNetEngine {
   std::vector<LayerSpec> layers;
   bf16* d_w = nullptr;
   float* d_bias = nullptr;
-  float* d_stem_w = nullptr;   // [27][32]  (already divided by 255)
+  float* d_stem_w = nullptr;   // [27][32]  (already divided by 255: F.to_tensor folded in)
   float* d_stem_b = nullptr;
+  float* d_stem_w_std = nullptr;   // mode B: fixed_image_standardization folded in: w / 128, bias - (127.5 / 128) sum(w)
+  float* d_stem_b_std = nullptr;
   float* d_head_w = nullptr;   // [1792][512]
   float* d_head_b = nullptr;
   int buf_stem = -1, buf_final = -1;
@@ -183,6 +185,18 @@ int facenet_create(trl_ctx* c, const float* blob, size_t len) {
     TRL_CUDA(c, cudaMemcpy(e->d_stem_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
     TRL_CUDA(c, cudaMalloc(&e->d_stem_b, 32 * 4));
     TRL_CUDA(c, cudaMemcpy(e->d_stem_b, t.b.data(), 32 * 4, cudaMemcpyHostToDevice));
+    // mode B input (x - 127.5) / 128: conv(w, (x - 127.5) / 128) = conv(w / 128, x) - (127.5 / 128) * sum(w); the conv has no
+    // padding, so the shift is the same for every output pixel.  w / 128 is exact.
+    std::vector<float> ws(27 * 32), bs(32);
+    for (int co = 0; co < 32; ++co) {
+      double sum = 0.0;
+      for (int k = 0; k < 27; ++k) { ws[k * 32 + co] = t.w[co * 27 + k] * 0.0078125f; sum += (double)t.w[co * 27 + k]; }
+      bs[co] = (float)((double)t.b[co] - 127.5 / 128.0 * sum);
+    }
+    TRL_CUDA(c, cudaMalloc(&e->d_stem_w_std, ws.size() * 4));
+    TRL_CUDA(c, cudaMemcpy(e->d_stem_w_std, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice));
+    TRL_CUDA(c, cudaMalloc(&e->d_stem_b_std, 32 * 4));
+    TRL_CUDA(c, cudaMemcpy(e->d_stem_b_std, bs.data(), 32 * 4, cudaMemcpyHostToDevice));
   }
   // ---- buffers
   const int a1 = B.add_buf(L1, 32), a2 = B.add_buf(L2, 32), a3 = B.add_buf(L2, 64), a4 = B.add_buf(L4, 64);
@@ -299,7 +313,7 @@ void facenet_destroy(trl_ctx* c) {
   FaceNetEngine* e = c->facenet;
   if (!e) return;
   for (bf16* p : e->d_act) cudaFree(p);
-  cudaFree(e->d_w); cudaFree(e->d_bias); cudaFree(e->d_stem_w); cudaFree(e->d_stem_b); cudaFree(e->d_head_w); cudaFree(e->d_head_b);
+  cudaFree(e->d_w); cudaFree(e->d_bias); cudaFree(e->d_stem_w); cudaFree(e->d_stem_b); cudaFree(e->d_stem_w_std); cudaFree(e->d_stem_b_std); cudaFree(e->d_head_w); cudaFree(e->d_head_b);
   delete e;
   c->facenet = nullptr;
 }
@@ -367,7 +381,7 @@ static int facenet_prepare(trl_ctx* c, int S, int cap) {
   return TRL_OK;
 }
 
-int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, float* d_emb, cudaStream_t s) {
+int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, int norm, float* d_emb, cudaStream_t s) {
   FaceNetEngine* e = c->facenet;
   if (!e) TRL_FAIL(c, TRL_E_STATE, "facenet weights not loaded");
   if (n <= 0) return TRL_OK;
@@ -377,7 +391,8 @@ int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, float* d_e
     int rc = facenet_prepare(c, S, cap);
     if (rc != TRL_OK) return rc;
   }
-  int rc = launch_stem_conv(c, d_crops, n, S, e->d_stem_w, e->d_stem_b, e->d_act[e->buf_stem], e->sz[L1], s);
+  int rc = launch_stem_conv(c, d_crops, n, S, norm ? e->d_stem_w_std : e->d_stem_w, norm ? e->d_stem_b_std : e->d_stem_b,
+                            e->d_act[e->buf_stem], e->sz[L1], s);
   if (rc != TRL_OK) return rc;
   for (const FaceNetEngine::Step& st : e->steps) {
     if (st.kind == 1) rc = launch_maxpool(c, st.pool, n, s);
@@ -395,7 +410,7 @@ extern "C" int trl_debug_facenet_step_times(trl_ctx* c, const uint8_t* d_crops, 
   FaceNetEngine* e = c->facenet;
   if (!e || !info || !ms) return TRL_E_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = facenet_forward(c, d_crops, n, S, d_emb, s);      // sizes the engine, warms up
+  int rc = facenet_forward(c, d_crops, n, S, 0, d_emb, s);      // sizes the engine, warms up
   if (rc != TRL_OK) return rc;
   const int ns = (int)e->steps.size();
   if (ns > max_steps) return TRL_E_INVALID;

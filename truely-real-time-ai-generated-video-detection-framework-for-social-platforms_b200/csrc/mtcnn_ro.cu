@@ -9,6 +9,13 @@
 
 #include "common.cuh"
 
+// RO_FFMA2 = 1: packed fma.rn.f32x2 in the conv rows; 0: scalar FFMA.  Same IEEE results either way.  Measured on B200
+// (experiments/fma_rate_probe.cu): FFMA issues one warp instruction per cycle and sub-partition, FFMA2 one per three
+// cycles -- two FMAs in 3 cycles with two issue slots left for other pipes, against two FMAs in 2 cycles with none.
+#ifndef RO_FFMA2
+#define RO_FFMA2 1
+#endif
+
 namespace ro {
 
 __device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : v * a; }
@@ -42,7 +49,11 @@ __device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* _
   for (int base = 0; base < items; base += MAXI * (int)blockDim.x) {
     int cg[MAXI], row[MAXI], x0[MAXI];
     bool live[MAXI];
+#if RO_FFMA2
     unsigned long long acc2[MAXI][4][2];
+#else
+    float accs[MAXI][4][4];
+#endif
 #pragma unroll
     for (int i = 0; i < MAXI; ++i) {
       const int item = base + (int)threadIdx.x + i * (int)blockDim.x;
@@ -53,7 +64,13 @@ __device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* _
       row[i] = rem / PXG;
       x0[i] = (rem - row[i] * PXG) * 4;
 #pragma unroll
+#if RO_FFMA2
       for (int px = 0; px < 4; ++px) acc2[i][px][0] = acc2[i][px][1] = 0ull;
+#else
+      for (int px = 0; px < 4; ++px)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) accs[i][px][j] = 0.f;
+#endif
     }
     stage(0);
 #pragma unroll 1
@@ -81,6 +98,7 @@ __device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* _
 #pragma unroll
             for (int kx = 0; kx < K; ++kx) {
               const float4 wv = *reinterpret_cast<const float4*>(ws + ((cl * K + ky) * K + kx) * COUT + cg[i] * 4);
+#if RO_FFMA2
               const unsigned long long w01 = pack_f32x2(wv.x, wv.y), w23 = pack_f32x2(wv.z, wv.w);
 #pragma unroll
               for (int px = 0; px < 4; ++px) {
@@ -88,6 +106,16 @@ __device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* _
                 ffma2(acc2[i][px][0], vv, w01);
                 ffma2(acc2[i][px][1], vv, w23);
               }
+#else
+#pragma unroll
+              for (int px = 0; px < 4; ++px) {
+                const float vv = v[px + kx];
+                accs[i][px][0] = fmaf(vv, wv.x, accs[i][px][0]);
+                accs[i][px][1] = fmaf(vv, wv.y, accs[i][px][1]);
+                accs[i][px][2] = fmaf(vv, wv.z, accs[i][px][2]);
+                accs[i][px][3] = fmaf(vv, wv.w, accs[i][px][3]);
+              }
+#endif
             }
           }
         }
@@ -100,8 +128,13 @@ __device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* _
       float acc[4][4];
 #pragma unroll
       for (int px = 0; px < 4; ++px) {
+#if RO_FFMA2
         unpack_f32x2(acc2[i][px][0], acc[px][0], acc[px][1]);
         unpack_f32x2(acc2[i][px][1], acc[px][2], acc[px][3]);
+#else
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[px][j] = accs[i][px][j];
+#endif
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {

@@ -36,6 +36,9 @@ namespace pnet {
 #define PNET_TOY 20
 #define PNET_TOX 28
 #endif
+#ifndef PNET_C1_FFMA2
+#define PNET_C1_FFMA2 1
+#endif
 constexpr int TOY = PNET_TOY, TOX = PNET_TOX;   // output cells per CTA
 constexpr int P1H = TOY + 4, P1W = TOX + 4;  // pooled conv1 tile (20 x 36), flat pixel index n = row * P1W + col
 constexpr int C2TILES_ = ((TOY + 2) * P1W + 15) / 16;
@@ -376,7 +379,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
           const float2 v1 = *reinterpret_cast<const float2*>(&in_s[(ci * INH + 2 * py + r) * INP + 2 * px + 2]);
           patch[ci][r][0] = v0.x; patch[ci][r][1] = v0.y; patch[ci][r][2] = v1.x; patch[ci][r][3] = v1.y;
         }
-      // packed fp32 pairs: FFMA2 (fma.rn.f32x2) does two channels per issued instruction, same rounding as FFMA
+      float accf[4][10];
+#if PNET_C1_FFMA2
+      // packed fp32 pairs: FFMA2 (fma.rn.f32x2) does two channels per issued instruction, same rounding as FFMA.  On B200
+      // an FFMA2 holds the FMA pipe for 3 cycles (experiments/fma_rate_probe.cu: two FMAs per 3 cycles, against one FFMA
+      // per cycle) but leaves two issue slots to the other pipes and to group B, which is what this kernel is short of.
       unsigned long long acc[4][5];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
@@ -402,12 +409,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
               for (int cp = 0; cp < 5; ++cp) ffma2(acc[q][cp], vv, w[cp]);
             }
           }
-      const int gy = 2 * (oy0 + py), gx = 2 * (ox0 + px);
-      float accf[4][10];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int cp = 0; cp < 5; ++cp) unpack_f32x2(acc[q][cp], accf[q][2 * cp], accf[q][2 * cp + 1]);
+#else
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int co = 0; co < 10; ++co) accf[q][co] = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float* wr = &w_s[W1 + ((ci * 3 + ky) * 3 + kx) * 12];
+            const float4 wa = *reinterpret_cast<const float4*>(wr);
+            const float4 wb = *reinterpret_cast<const float4*>(wr + 4);
+            const float2 wc = *reinterpret_cast<const float2*>(wr + 8);
+            const float w[10] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float v = patch[ci][(q >> 1) + ky][(q & 1) + kx];
+#pragma unroll
+              for (int co = 0; co < 10; ++co) accf[q][co] = fmaf(v, w[co], accf[q][co]);
+            }
+          }
+#endif
+      const int gy = 2 * (oy0 + py), gx = 2 * (ox0 + px);
       float m[10];
       if (p.conv1_monotone && gy + 1 < c1h && gx + 1 < c1w) {
         // interior pixel and every PReLU slope >= 0: bias add and PReLU are non-decreasing (rounding included), so

@@ -519,6 +519,242 @@ int launch_crop_align(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, 
   return TRL_OK;
 }
 
+// ----------------------------------------------------------------------------- K10, mode B: extract_face (INTER_AREA)
+// Upstream facenet_pytorch extract_face (SURVEY.md Appendix A "Mode-B extras"; oracle/mode_b.py): margin-adjusted box in
+// fp32, truncated and clamped, crop, cv2.resize(..., (S, S), interpolation=cv2.INTER_AREA) on uint8 -- bit exact with
+// OpenCV's three code paths (oracle.mode_b.resize_area_u8 is the numpy restatement this mirrors, pinned against cv2):
+//   both axes shrink by integers : block sums, (s + 2) >> 2 for 2x2, else saturate(rint(s * (1.f / area)))
+//   both axes shrink             : separable fp32 weights from computeResizeAreaTab (double -> float), accumulated in table
+//                                  order with separate multiplies and adds, saturate(rint(sum))
+//   an axis is enlarged          : the 11-bit fixed-point bilinear resize with area-mode coefficients
+// One CTA per face.  keep_all: face i of the batch = box j of frame b through the prefix `face_off` (faces_prefix_kernel).
+constexpr int AREA_MAX_S = 256;
+
+struct AreaTab {      // one destination index: up to three weights over source indices [s_first .. s_last]
+  int s_mid0, s_mid1; // full cells [s_mid0, s_mid1)
+  float a_first, a_mid, a_last;   // a_first applies to s_mid0 - 1 (if has_first), a_last to s_mid1 (if has_last)
+  int has_first, has_last;
+};
+
+__device__ __forceinline__ AreaTab area_tab(int d, int ssize, double scale) {
+  AreaTab t;
+  const double fsx1 = (double)d * scale, fsx2 = fsx1 + scale;
+  const double cell = fmin(scale, (double)ssize - fsx1);
+  int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+  sx2 = min(sx2, ssize - 1);
+  sx1 = min(sx1, sx2);
+  t.s_mid0 = sx1; t.s_mid1 = sx2;
+  t.has_first = ((double)sx1 - fsx1 > 1e-3) ? 1 : 0;
+  t.has_last = (fsx2 - (double)sx2 > 1e-3) ? 1 : 0;
+  t.a_first = (float)(((double)sx1 - fsx1) / cell);
+  t.a_mid = (float)(1.0 / cell);
+  t.a_last = (float)(fmin(fmin(fsx2 - (double)sx2, 1.0), cell) / cell);
+  return t;
+}
+
+// bilinear coefficients in area mode (cv::resize with INTER_AREA when an axis is enlarged)
+__device__ __forceinline__ ResizeCoef resize_coef_area(int d, int ssize, double scale, double inv_scale) {
+  int sidx = (int)floor((double)d * scale);
+  float f = (float)((double)(d + 1) - (double)(sidx + 1) * inv_scale);
+  f = f <= 0.f ? 0.f : __fsub_rn(f, floorf(f));
+  if (sidx < 0) { f = 0.f; sidx = 0; }
+  if (sidx >= ssize - 1) { f = 0.f; sidx = ssize - 1; }
+  ResizeCoef r;
+  r.idx = sidx;
+  r.c1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  r.c0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  return r;
+}
+
+// face_off[b] = number of faces of frames < b (each clipped to cap); face_off[B] = total.  One CTA.
+__global__ void __launch_bounds__(256) faces_prefix_kernel(const int* __restrict__ nfaces, int B, int cap, int max_faces,
+                                                          int* __restrict__ face_off, CapFlag* capflag) {
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += 256) {
+    const int i = base + threadIdx.x;
+    int v = i < B ? min(max(nfaces[i], 0), cap) : 0;
+    // inclusive scan over the 256 threads (warp scans + warp totals)
+    __shared__ int wsum[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += u; }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    int add = carry;
+    for (int q = 0; q < w; ++q) add += wsum[q];
+    if (i < B) face_off[i] = add + x - v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry = add + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    face_off[B] = carry;
+    if (carry > max_faces && capflag) { capflag->overflow = 1; capflag->stage = 6; capflag->frame = 0; capflag->count = carry; capflag->capacity = max_faces; }
+  }
+}
+
+__global__ void __launch_bounds__(256) crop_area_kernel(const uint8_t* __restrict__ frames, int B, int H, int W,
+                                                       const float* __restrict__ boxes, int box_stride,
+                                                       const int* __restrict__ nfaces, const int* __restrict__ face_off,
+                                                       int max_faces, int S, int margin, int* __restrict__ box_int,
+                                                       uint8_t* __restrict__ valid, int* __restrict__ face_frame,
+                                                       uint8_t* __restrict__ crops) {
+  __shared__ int sb[6];          // x1, y1, x2, y2, ok, frame
+  __shared__ AreaTab xt[AREA_MAX_S], yt[AREA_MAX_S];
+  __shared__ ResizeCoef xc[AREA_MAX_S], yc[AREA_MAX_S];
+  const int i = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int b = i, j = 0, present = 0;
+    if (face_off) {                                  // keep_all: face i -> (frame, box) by binary search in the prefix
+      const int total = min(face_off[B], max_faces);
+      if (i < total) {
+        int lo = 0, hi = B;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (face_off[mid] <= i) lo = mid; else hi = mid; }
+        b = lo; j = i - face_off[lo]; present = 1;
+      } else {
+        b = -1;
+      }
+    } else {
+      present = nfaces[b] > 0 ? 1 : 0;
+    }
+    int x1 = 0, y1 = 0, x2 = 0, y2 = 0, ok = 0;
+    if (present) {
+      const float* bx = boxes + (size_t)b * box_stride + (size_t)j * 5;
+      // margin = [margin * (x2 - x1) / (S - margin), margin * (y2 - y1) / (S - margin)], float32 scalars upstream
+      const float mx = __fdiv_rn(__fmul_rn((float)margin, __fsub_rn(bx[2], bx[0])), (float)(S - margin));
+      const float my = __fdiv_rn(__fmul_rn((float)margin, __fsub_rn(bx[3], bx[1])), (float)(S - margin));
+      x1 = (int)fmaxf(__fsub_rn(bx[0], __fmul_rn(mx, 0.5f)), 0.f);
+      y1 = (int)fmaxf(__fsub_rn(bx[1], __fmul_rn(my, 0.5f)), 0.f);
+      x2 = (int)fminf(__fadd_rn(bx[2], __fmul_rn(mx, 0.5f)), (float)W);
+      y2 = (int)fminf(__fadd_rn(bx[3], __fmul_rn(my, 0.5f)), (float)H);
+      ok = (x2 > x1 && y2 > y1) ? 1 : 0;
+    }
+    sb[0] = x1; sb[1] = y1; sb[2] = x2; sb[3] = y2; sb[4] = ok; sb[5] = b;
+    if (b >= 0) {
+      box_int[i * 4 + 0] = x1; box_int[i * 4 + 1] = y1; box_int[i * 4 + 2] = x2; box_int[i * 4 + 3] = y2;
+      valid[i] = (uint8_t)ok;
+      if (face_frame) face_frame[i] = b;
+    }
+  }
+  __syncthreads();
+  if (sb[5] < 0) return;                              // beyond the number of faces of this batch
+  uint8_t* o = crops + (size_t)i * S * S * 3;
+  if (!sb[4]) {
+    for (int k = threadIdx.x; k < S * S * 3; k += blockDim.x) o[k] = 0;
+    return;
+  }
+  const int b = sb[5], x1 = sb[0], y1 = sb[1], sw = sb[2] - sb[0], sh = sb[3] - sb[1];
+  const uint8_t* src = frames + ((size_t)b * H * W + (size_t)y1 * W + x1) * 3;
+  const size_t rowb = (size_t)W * 3;
+  const double inv_x = (double)S / (double)sw, inv_y = (double)S / (double)sh;
+  const double scale_x = 1.0 / inv_x, scale_y = 1.0 / inv_y;
+  if (scale_x >= 1.0 && scale_y >= 1.0) {
+    const int isx = (int)rint(scale_x), isy = (int)rint(scale_y);
+    const double eps = 2.220446049250313e-16;
+    if (fabs(scale_x - (double)isx) < eps && fabs(scale_y - (double)isy) < eps) {
+      // integer ratios (resizeAreaFast_)
+      const float fscale = __fdiv_rn(1.f, (float)(isx * isy));
+      const bool two = isx == 2 && isy == 2;
+      for (int pix = threadIdx.x; pix < S * S; pix += blockDim.x) {
+        const int dy = pix / S, dx = pix - dy * S;
+        int s0 = 0, s1 = 0, s2 = 0;
+        for (int ky = 0; ky < isy; ++ky) {
+          const uint8_t* r = src + (size_t)(dy * isy + ky) * rowb + (size_t)dx * isx * 3;
+          for (int kx = 0; kx < isx; ++kx, r += 3) { s0 += r[0]; s1 += r[1]; s2 += r[2]; }
+        }
+        int v0, v1, v2;
+        if (two) { v0 = (s0 + 2) >> 2; v1 = (s1 + 2) >> 2; v2 = (s2 + 2) >> 2; }
+        else {
+          v0 = __float2int_rn(__fmul_rn((float)s0, fscale));
+          v1 = __float2int_rn(__fmul_rn((float)s1, fscale));
+          v2 = __float2int_rn(__fmul_rn((float)s2, fscale));
+        }
+        o[pix * 3 + 0] = (uint8_t)min(max(v0, 0), 255);
+        o[pix * 3 + 1] = (uint8_t)min(max(v1, 0), 255);
+        o[pix * 3 + 2] = (uint8_t)min(max(v2, 0), 255);
+      }
+      return;
+    }
+    // general area path (resizeArea_<uchar, float>)
+    for (int d = threadIdx.x; d < S; d += blockDim.x) { xt[d] = area_tab(d, sw, scale_x); yt[d] = area_tab(d, sh, scale_y); }
+    __syncthreads();
+    for (int pix = threadIdx.x; pix < S * S; pix += blockDim.x) {
+      const int dy = pix / S, dx = pix - dy * S;
+      const AreaTab tx = xt[dx], ty = yt[dy];
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
+      const int ya = ty.s_mid0 - ty.has_first, yb = ty.s_mid1 + ty.has_last;      // source rows [ya, yb)
+      for (int sy = ya; sy < yb; ++sy) {
+        const float beta = (sy < ty.s_mid0) ? ty.a_first : (sy < ty.s_mid1 ? ty.a_mid : ty.a_last);
+        const uint8_t* r = src + (size_t)sy * rowb;
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        const int xa = tx.s_mid0 - tx.has_first, xb = tx.s_mid1 + tx.has_last;
+        for (int sx = xa; sx < xb; ++sx) {
+          const float alpha = (sx < tx.s_mid0) ? tx.a_first : (sx < tx.s_mid1 ? tx.a_mid : tx.a_last);
+          const uint8_t* q = r + (size_t)sx * 3;
+          b0 = __fadd_rn(b0, __fmul_rn((float)q[0], alpha));
+          b1 = __fadd_rn(b1, __fmul_rn((float)q[1], alpha));
+          b2 = __fadd_rn(b2, __fmul_rn((float)q[2], alpha));
+        }
+        sum0 = __fadd_rn(sum0, __fmul_rn(beta, b0));
+        sum1 = __fadd_rn(sum1, __fmul_rn(beta, b1));
+        sum2 = __fadd_rn(sum2, __fmul_rn(beta, b2));
+      }
+      o[pix * 3 + 0] = (uint8_t)min(max(__float2int_rn(sum0), 0), 255);
+      o[pix * 3 + 1] = (uint8_t)min(max(__float2int_rn(sum1), 0), 255);
+      o[pix * 3 + 2] = (uint8_t)min(max(__float2int_rn(sum2), 0), 255);
+    }
+    return;
+  }
+  // an axis is enlarged: bilinear fixed point with area-mode coefficients
+  for (int d = threadIdx.x; d < S; d += blockDim.x) {
+    xc[d] = resize_coef_area(d, sw, scale_x, inv_x);
+    yc[d] = resize_coef_area(d, sh, scale_y, inv_y);
+  }
+  __syncthreads();
+  for (int pix = threadIdx.x; pix < S * S; pix += blockDim.x) {
+    const int dy = pix / S, dx = pix - dy * S;
+    const ResizeCoef cx = xc[dx], cy = yc[dy];
+    const int xa = cx.idx, xb = min(cx.idx + 1, sw - 1);
+    const int ya = cy.idx, yb = min(cy.idx + 1, sh - 1);
+    const uint8_t* ra = src + (size_t)ya * rowb;
+    const uint8_t* rb = src + (size_t)yb * rowb;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const int h0 = ra[xa * 3 + ch] * cx.c0 + ra[xb * 3 + ch] * cx.c1;
+      const int h1 = rb[xa * 3 + ch] * cx.c0 + rb[xb * 3 + ch] * cx.c1;
+      int v = (((cy.c0 * (h0 >> 4)) >> 16) + ((cy.c1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      o[pix * 3 + ch] = (uint8_t)min(max(v, 0), 255);
+    }
+  }
+}
+
+int launch_extract_face(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
+                        const int* d_nfaces, int S, int margin, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops,
+                        cudaStream_t s) {
+  if (B <= 0) return TRL_OK;
+  if (S < 1 || S > AREA_MAX_S || margin < 0 || margin >= S) TRL_FAIL(c, TRL_E_INVALID, "extract_face: image size %d / margin %d unsupported", S, margin);
+  crop_area_kernel<<<B, 256, 0, s>>>(d_frames, B, H, W, d_boxes, box_stride, d_nfaces, nullptr, B, S, margin, d_box_int, d_valid,
+                                     nullptr, d_crops);
+  TRL_LAUNCH_CHECK(c);
+  return TRL_OK;
+}
+
+int launch_extract_faces_all(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const float* d_boxes, int box_stride,
+                             int box_cap, const int* d_nfaces, int S, int margin, int max_faces, int* d_face_off,
+                             int* d_face_frame, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops, cudaStream_t s) {
+  if (B <= 0 || max_faces <= 0) return TRL_OK;
+  if (S < 1 || S > AREA_MAX_S || margin < 0 || margin >= S) TRL_FAIL(c, TRL_E_INVALID, "extract_face: image size %d / margin %d unsupported", S, margin);
+  faces_prefix_kernel<<<1, 256, 0, s>>>(d_nfaces, B, box_cap, max_faces, d_face_off, c->d_cap);
+  TRL_LAUNCH_CHECK(c);
+  crop_area_kernel<<<max_faces, 256, 0, s>>>(d_frames, B, H, W, d_boxes, box_stride, d_nfaces, d_face_off, max_faces, S, margin,
+                                             d_box_int, d_valid, d_face_frame, d_crops);
+  TRL_LAUNCH_CHECK(c);
+  return TRL_OK;
+}
+
 // ----------------------------------------------------------------------------- pyramid geometry (host)
 
 // upstream detect_face: m = 12/minsize; scales m*factor^k while min(h,w)*m*factor^k >= 12, all in doubles;

@@ -51,9 +51,16 @@ class Analyzer:
     """Process-global GPU context: weights resident on the device, reusable across ``run`` calls
     (the reference rebuilds both models on every call, server/model.py:18-19; behaviourally invisible)."""
 
-    def __init__(self, device: int = 0, facenet_impl: int | None = None, crop_size: int = CROP_SIZE,
+    def __init__(self, device: int = 0, facenet_impl: int | None = None, crop_size: int | None = None,
                  cand_cap_scale: int | None = None, cand_cap_frame: int | None = None, box_cap_frame: int | None = None,
-                 pnet_precision: int | None = None):
+                 pnet_precision: int | None = None, mode: str = "reference", margin: int = 0):
+        """``mode``: "reference" = the crop path of server/model.py:49-58 (80x80, INTER_LINEAR, /255: what ``run`` uses);
+        "b" = upstream facenet_pytorch's own crop as the north star words it (extract_face: INTER_AREA to 160x160 with
+        ``margin``, fixed_image_standardization), SURVEY.md section 0 / Appendix A "Mode-B extras"."""
+        if mode not in ("reference", "b"):
+            raise ValueError("mode must be 'reference' or 'b'")
+        if crop_size is None:
+            crop_size = CROP_SIZE if mode == "reference" else 160
         import torch
         self.torch = torch
         self.lib = L.load()
@@ -70,6 +77,9 @@ class Analyzer:
         if pnet_precision is None:
             pnet_precision = int(os.environ.get("TRUELY_PNET_PRECISION", "0"))
         cfg.pnet_precision = pnet_precision
+        cfg.mode = 0 if mode == "reference" else 1
+        cfg.margin = margin
+        self.mode, self.margin = mode, margin
         if cand_cap_scale:
             cfg.cand_cap_scale = cand_cap_scale
         if cand_cap_frame:
@@ -233,6 +243,43 @@ class Analyzer:
             res.counts = counts.cpu().numpy()
         return res
 
+
+    def embed_all_faces(self, frames: np.ndarray, max_faces: int | None = None):
+        """keep_all (mode B, BASELINE.json configs[3]: 4-8 faces per frame): MTCNN.detect on every frame, then EVERY
+        detected box is cropped (extract_face: INTER_AREA to crop_size, margin) and embedded with
+        fixed_image_standardization, batched over all faces of the batch.  Synchronous convenience wrapper.
+        -> list over frames of [(int box [4], float32 embedding [512] or None for an empty crop), ...], largest box first."""
+        t = self.torch
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        B, H, Wd, _ = frames.shape
+        dev = f"cuda:{self.device}"
+        S = self.crop_size
+        cap = self.box_cap
+        if max_faces is None:
+            max_faces = B * min(cap, 16)
+        with t.cuda.stream(self.stream):
+            d_frames = t.from_numpy(frames).pin_memory().to(dev, non_blocking=True)
+            nfaces = t.empty(B, dtype=t.int32, device=dev)
+            boxes = t.zeros((B, cap, 5), dtype=t.float32, device=dev)
+            self._check(self.lib.trl_detect(self.ctx, _vp(d_frames), B, H, Wd, _vp(nfaces), _vp(boxes), None, self._sptr()))
+            face_off = t.empty(B + 1, dtype=t.int32, device=dev)
+            face_frame = t.full((max_faces,), -1, dtype=t.int32, device=dev)
+            box_int = t.zeros((max_faces, 4), dtype=t.int32, device=dev)
+            valid = t.zeros(max_faces, dtype=t.uint8, device=dev)
+            crops = t.zeros((max_faces, S, S, 3), dtype=t.uint8, device=dev)
+            emb = t.zeros((max_faces, L.EMB_DIM), dtype=t.float32, device=dev)
+            self._check(self.lib.trl_extract_faces_all(
+                self.ctx, _vp(d_frames), B, H, Wd, _vp(boxes), cap * 5, cap, _vp(nfaces), S, self.margin, max_faces,
+                _vp(face_off), _vp(face_frame), _vp(box_int), _vp(valid), _vp(crops), self._sptr()))
+            self._check(self.lib.trl_facenet_norm(self.ctx, _vp(crops), max_faces, S, 1, _vp(emb), self._sptr()))
+        self.stream.synchronize()
+        self.check_capacity()
+        off = face_off.cpu().numpy()
+        bi, va, em = box_int.cpu().numpy(), valid.cpu().numpy(), emb.cpu().numpy()
+        out = []
+        for b in range(B):
+            out.append([(bi[i].copy(), em[i].copy() if va[i] else None) for i in range(off[b], off[b + 1])])
+        return out
 
     # ------------------------------------------------------------------ clip-level API on staged frames
     def analyze_resident(self, frames, chunk: int = 90, host_out=None, halo=None, h2d: bool = False, dev_frames=None,
