@@ -152,6 +152,12 @@ int trl_extract_faces_all(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H,
                           int* d_face_frame, int* d_box_int, uint8_t* d_valid, uint8_t* d_crops, void* stream);
 int trl_facenet_norm(trl_ctx_t* ctx, const uint8_t* d_crops, int n, int S, int norm, float* d_emb, void* stream);
 
+/* trl_facenet restricted to the face-bearing crops: the reference never embeds a frame without a face
+ * (server/model.py:48 `continue`s first).  Crops with d_valid[i] != 0 are packed on the device, embedded as one batch
+ * whose size never travels to the host (every kernel of the pass reads it from device memory), and scattered back;
+ * rows of d_emb that belong to frames without a face are set to zero.  Normalisation follows trl_config_t.mode. */
+int trl_facenet_valid(trl_ctx_t* ctx, const uint8_t* d_crops, const uint8_t* d_valid, int n, int S, float* d_emb, void* stream);
+
 /* K12: cosine similarity against the previous face-bearing frame and the 0.99 test (server/model.py:60-62).
  * d_emb [B,512], d_valid [B]; d_halo_emb [512] (or NULL) is the last face-bearing embedding before this
  * range (previous batch or previous rank), d_halo_valid uint8[1] (or NULL = valid) says on the device whether

@@ -371,3 +371,37 @@ def test_consistency_matches_numpy(analyzer):
                     assert below[i] == (ref < 0.99)
             prev = emb[i]
         assert d_lv.item() == 1 and np.array_equal(d_le.cpu().numpy(), prev)
+
+
+def test_facenet_valid_only_equals_full_batch_on_the_valid_rows(analyzer):
+    """trl_facenet_valid packs the face-bearing crops on the device (batch size read from device memory by every kernel of
+    the pass) -- same bits as embedding everything, zeros for the frames without a face, any pattern of holes."""
+    import ctypes as C
+    from truely_b200.model import _vp
+    an = analyzer
+    rng = np.random.default_rng(3)
+    for n, S, pattern in ((37, 80, "random"), (64, 80, "none"), (9, 160, "all"), (130, 80, "first_last"), (5, 80, "empty")):
+        crops = torch.from_numpy(rng.integers(0, 256, (n, S, S, 3), dtype=np.uint8)).cuda()
+        if pattern == "random":
+            v = (rng.random(n) > 0.4).astype(np.uint8)
+        elif pattern == "none":
+            v = np.ones(n, np.uint8)
+        elif pattern == "all":
+            v = np.ones(n, np.uint8); v[3] = 0
+        elif pattern == "first_last":
+            v = np.zeros(n, np.uint8); v[0] = v[-1] = 1
+        else:
+            v = np.zeros(n, np.uint8)
+        valid = torch.from_numpy(v).cuda()
+        full = torch.empty((n, 512), dtype=torch.float32, device="cuda")
+        part = torch.full((n, 512), 7.0, dtype=torch.float32, device="cuda")
+        with torch.cuda.stream(an.stream):
+            an._check(an.lib.trl_facenet(an.ctx, _vp(crops), n, S, _vp(full), an._sptr()))
+            an._check(an.lib.trl_facenet_valid(an.ctx, _vp(crops), _vp(valid), n, S, _vp(part), an._sptr()))
+        an.stream.synchronize()
+        full, part = full.cpu().numpy(), part.cpu().numpy()
+        for i in range(n):
+            if v[i]:
+                assert np.array_equal(part[i], full[i]), f"{pattern}: row {i}"
+            else:
+                assert not part[i].any(), f"{pattern}: row {i} must be zero"

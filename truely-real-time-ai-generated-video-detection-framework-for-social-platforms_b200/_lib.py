@@ -52,6 +52,7 @@ SIGNATURES = {
     "trl_detect": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "trl_crop_align": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
     "trl_facenet": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "trl_facenet_valid": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "trl_facenet_norm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "trl_extract_face": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "trl_extract_faces_all": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int,

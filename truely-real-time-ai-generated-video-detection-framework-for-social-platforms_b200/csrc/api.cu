@@ -354,6 +354,15 @@ int trl_facenet(trl_ctx_t* c, const uint8_t* d_crops, int n, int S, float* d_emb
   return TRL_OK;
 }
 
+int trl_facenet_valid(trl_ctx_t* c, const uint8_t* d_crops, const uint8_t* d_valid, int n, int S, float* d_emb, void* stream) {
+  if (!c || !d_crops || !d_valid || !d_emb || n < 0) return TRL_E_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if ((rc = join_tail(c, s)) != TRL_OK) return rc;
+  TIMED(11, facenet_forward_valid(c, d_crops, d_valid, n, S, c->cfg.mode == 1 ? 1 : 0, d_emb, s));
+  return TRL_OK;
+}
+
 int trl_facenet_norm(trl_ctx_t* c, const uint8_t* d_crops, int n, int S, int norm, float* d_emb, void* stream) {
   if (!c || !d_crops || !d_emb || n < 0 || (norm != 0 && norm != 1)) return TRL_E_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
@@ -503,9 +512,9 @@ int trl_process(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, cons
   int rc = ensure_workspace(c, B, H, W);       // before c->d_crops is read: the workspace may be (re)allocated here
   if (rc != TRL_OK) return rc;
   if ((rc = trl_detect_align(c, d_frames, B, H, W, d_box_int, d_valid, d_nfaces, c->d_crops, stream)) != TRL_OK) return rc;
-  // FaceNet runs on all B crops (faceless frames carry a zero crop; their embeddings are never compared):
-  // this keeps the whole batch free of host synchronisation.
-  TIMED(11, facenet_forward(c, c->d_crops, B, c->cfg.crop_size, c->cfg.mode == 1 ? 1 : 0, d_emb, s));
+  // only face-bearing frames are embedded (server/model.py:48 skips the others): the crops are packed on the device and
+  // the live batch size stays there, so the batch remains free of host synchronisation
+  TIMED(11, facenet_forward_valid(c, c->d_crops, d_valid, B, c->cfg.crop_size, c->cfg.mode == 1 ? 1 : 0, d_emb, s));
   TIMED(12, launch_consistency(c, d_emb, d_valid, B, nullptr, d_halo_emb, d_halo_valid, thr, d_sim, d_below, d_has_sim, d_last_emb,
                                d_last_valid, s));
   return TRL_OK;

@@ -250,7 +250,11 @@ int launch_onet(trl_ctx* c, const float* d_in, int n_max, const int* d_count, fl
 int facenet_create(trl_ctx* c, const float* h_blob, size_t len);
 void facenet_destroy(trl_ctx* c);
 // norm: 0 = F.to_tensor (x / 255, the reference, server/model.py:58); 1 = fixed_image_standardization ((x - 127.5) / 128)
-int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, int norm, float* d_emb, cudaStream_t s);
+int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, int norm, float* d_emb, cudaStream_t s,
+                    const int* d_n = nullptr);
+// only the crops with d_valid[i] != 0 are embedded (packed on the device, no host synchronisation); other rows of d_emb = 0
+int facenet_forward_valid(trl_ctx* c, const uint8_t* d_crops, const uint8_t* d_valid, int n, int S, int norm, float* d_emb,
+                          cudaStream_t s);
 
 int nms_init(trl_ctx* c);
 int nms_max_n();

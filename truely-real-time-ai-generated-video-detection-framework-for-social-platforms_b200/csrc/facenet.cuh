@@ -50,11 +50,13 @@ struct PoolOp {       // MaxPool2d(3, stride 2), NHWC
   bf16* out; int Hout, Wout, out_ctot, out_coff;
 };
 
-int launch_conv_simt(trl_ctx* c, const ConvOp& op, int n, cudaStream_t s);
-int launch_conv_umma(trl_ctx* c, const ConvOp& op, int n, cudaStream_t s);
+// d_n (may be NULL): device-side live batch size <= n (face-bearing crops after compaction); n sizes the launch
+int launch_conv_simt(trl_ctx* c, const ConvOp& op, int n, cudaStream_t s, const int* d_n = nullptr);
+int launch_conv_umma(trl_ctx* c, const ConvOp& op, int n, cudaStream_t s, const int* d_n = nullptr);
 int umma_init(trl_ctx* c);
 int umma_encode_maps(trl_ctx* c, ConvOp& op, int n_cap);
 int launch_stem_conv(trl_ctx* c, const uint8_t* d_crops, int n, int S, const float* w, const float* bias, bf16* out,
-                     int Ho, cudaStream_t s);
-int launch_maxpool(trl_ctx* c, const PoolOp& op, int n, cudaStream_t s);
-int launch_head(trl_ctx* c, const bf16* feat, int n, int hw, const float* w_t, const float* bias, float* emb, cudaStream_t s);
+                     int Ho, cudaStream_t s, const int* d_n = nullptr);
+int launch_maxpool(trl_ctx* c, const PoolOp& op, int n, cudaStream_t s, const int* d_n = nullptr);
+int launch_head(trl_ctx* c, const bf16* feat, int n, int hw, const float* w_t, const float* bias, float* emb, cudaStream_t s,
+                const int* d_n = nullptr);

@@ -44,6 +44,8 @@ struct FaceNetEngine {
   float* d_bias = nullptr;
   float* d_stem_w = nullptr;   // [27][32]  (already divided by 255: F.to_tensor folded in)
   float* d_stem_b = nullptr;
+  // compaction scratch of facenet_forward_valid
+  uint8_t* d_cmp_crops = nullptr; float* d_cmp_emb = nullptr; int* d_cmp_rank = nullptr; int cmp_cap = 0, cmp_S = 0;
   float* d_stem_w_std = nullptr;   // mode B: fixed_image_standardization folded in: w / 128, bias - (127.5 / 128) sum(w)
   float* d_stem_b_std = nullptr;
   float* d_head_w = nullptr;   // [1792][512]
@@ -313,7 +315,8 @@ void facenet_destroy(trl_ctx* c) {
   FaceNetEngine* e = c->facenet;
   if (!e) return;
   for (bf16* p : e->d_act) cudaFree(p);
-  cudaFree(e->d_w); cudaFree(e->d_bias); cudaFree(e->d_stem_w); cudaFree(e->d_stem_b); cudaFree(e->d_stem_w_std); cudaFree(e->d_stem_b_std); cudaFree(e->d_head_w); cudaFree(e->d_head_b);
+  cudaFree(e->d_w); cudaFree(e->d_bias); cudaFree(e->d_stem_w); cudaFree(e->d_stem_b); cudaFree(e->d_stem_w_std); cudaFree(e->d_stem_b_std);
+  cudaFree(e->d_cmp_crops); cudaFree(e->d_cmp_emb); cudaFree(e->d_cmp_rank); cudaFree(e->d_head_w); cudaFree(e->d_head_b);
   delete e;
   c->facenet = nullptr;
 }
@@ -381,7 +384,7 @@ static int facenet_prepare(trl_ctx* c, int S, int cap) {
   return TRL_OK;
 }
 
-int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, int norm, float* d_emb, cudaStream_t s) {
+int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, int norm, float* d_emb, cudaStream_t s, const int* d_n) {
   FaceNetEngine* e = c->facenet;
   if (!e) TRL_FAIL(c, TRL_E_STATE, "facenet weights not loaded");
   if (n <= 0) return TRL_OK;
@@ -392,14 +395,92 @@ int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, int norm, 
     if (rc != TRL_OK) return rc;
   }
   int rc = launch_stem_conv(c, d_crops, n, S, norm ? e->d_stem_w_std : e->d_stem_w, norm ? e->d_stem_b_std : e->d_stem_b,
-                            e->d_act[e->buf_stem], e->sz[L1], s);
+                            e->d_act[e->buf_stem], e->sz[L1], s, d_n);
   if (rc != TRL_OK) return rc;
   for (const FaceNetEngine::Step& st : e->steps) {
-    if (st.kind == 1) rc = launch_maxpool(c, st.pool, n, s);
-    else rc = (c->cfg.facenet_impl == 0) ? launch_conv_umma(c, st.conv, n, s) : launch_conv_simt(c, st.conv, n, s);
+    if (st.kind == 1) rc = launch_maxpool(c, st.pool, n, s, d_n);
+    else rc = (c->cfg.facenet_impl == 0) ? launch_conv_umma(c, st.conv, n, s, d_n) : launch_conv_simt(c, st.conv, n, s, d_n);
     if (rc != TRL_OK) return rc;
   }
-  return launch_head(c, e->d_act[e->buf_final], n, e->sz[L9] * e->sz[L9], e->d_head_w, e->d_head_b, d_emb, s);
+  return launch_head(c, e->d_act[e->buf_final], n, e->sz[L9] * e->sz[L9], e->d_head_w, e->d_head_b, d_emb, s, d_n);
+}
+
+// ---- face-bearing crops only (server/model.py:48 skips frames without a face before anything is embedded)
+// rank[i] = position of crop i among the valid ones (exclusive prefix of valid), *count = number of valid crops.  One CTA.
+__global__ void __launch_bounds__(1024) valid_prefix_kernel(const uint8_t* __restrict__ valid, int n, int* __restrict__ rank,
+                                                           int* __restrict__ count) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = (i < n && valid[i]) ? 1 : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += u; }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    int add = carry;
+    for (int q = 0; q < w; ++q) add += wsum[q];
+    if (i < n) rank[i] = add + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = add + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = carry;
+}
+
+// crops of the valid frames, packed front to back (16-byte copies; a crop is S*S*3 bytes, a multiple of 16 for even S)
+__global__ void __launch_bounds__(256) gather_crops_kernel(const uint8_t* __restrict__ crops, const uint8_t* __restrict__ valid,
+                                                          const int* __restrict__ rank, int bytes, uint8_t* __restrict__ out) {
+  const int i = blockIdx.x;
+  if (!valid[i]) return;
+  const uint8_t* src = crops + (size_t)i * bytes;
+  uint8_t* dst = out + (size_t)rank[i] * bytes;
+  if ((bytes & 15) == 0) {
+    for (int k = threadIdx.x; k < bytes / 16; k += blockDim.x)
+      reinterpret_cast<uint4*>(dst)[k] = reinterpret_cast<const uint4*>(src)[k];
+  } else {
+    for (int k = threadIdx.x; k < bytes; k += blockDim.x) dst[k] = src[k];
+  }
+}
+
+// emb[i] = packed embedding of frame i, zeros for a frame without a face
+__global__ void __launch_bounds__(128) scatter_emb_kernel(const float* __restrict__ packed, const uint8_t* __restrict__ valid,
+                                                         const int* __restrict__ rank, float* __restrict__ emb) {
+  const int i = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(packed + (size_t)(valid[i] ? rank[i] : 0) * TRL_EMB_DIM);
+  float4* dst = reinterpret_cast<float4*>(emb + (size_t)i * TRL_EMB_DIM);
+  dst[threadIdx.x] = valid[i] ? src[threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+int facenet_forward_valid(trl_ctx* c, const uint8_t* d_crops, const uint8_t* d_valid, int n, int S, int norm, float* d_emb,
+                          cudaStream_t s) {
+  FaceNetEngine* e = c->facenet;
+  if (!e) TRL_FAIL(c, TRL_E_STATE, "facenet weights not loaded");
+  if (n <= 0) return TRL_OK;
+  const size_t bytes = (size_t)S * S * 3;
+  if (e->cmp_cap < n || e->cmp_S != S) {
+    cudaFree(e->d_cmp_crops); cudaFree(e->d_cmp_emb); cudaFree(e->d_cmp_rank);
+    e->d_cmp_crops = nullptr; e->d_cmp_emb = nullptr; e->d_cmp_rank = nullptr; e->cmp_cap = 0;
+    const int cap = ((n + 63) / 64) * 64;
+    TRL_CUDA(c, cudaMalloc(&e->d_cmp_crops, (size_t)cap * bytes + 256));
+    TRL_CUDA(c, cudaMalloc(&e->d_cmp_emb, (size_t)cap * TRL_EMB_DIM * sizeof(float)));
+    TRL_CUDA(c, cudaMalloc(&e->d_cmp_rank, ((size_t)cap + 4) * sizeof(int)));
+    e->cmp_cap = cap; e->cmp_S = S;
+  }
+  int* d_count = e->d_cmp_rank + e->cmp_cap;
+  valid_prefix_kernel<<<1, 1024, 0, s>>>(d_valid, n, e->d_cmp_rank, d_count);
+  TRL_LAUNCH_CHECK(c);
+  gather_crops_kernel<<<n, 256, 0, s>>>(d_crops, d_valid, e->d_cmp_rank, (int)bytes, e->d_cmp_crops);
+  TRL_LAUNCH_CHECK(c);
+  int rc = facenet_forward(c, e->d_cmp_crops, n, S, norm, e->d_cmp_emb, s, d_count);
+  if (rc != TRL_OK) return rc;
+  scatter_emb_kernel<<<n, TRL_EMB_DIM / 4, 0, s>>>(e->d_cmp_emb, d_valid, e->d_cmp_rank, d_emb);
+  TRL_LAUNCH_CHECK(c);
+  return TRL_OK;
 }
 
 

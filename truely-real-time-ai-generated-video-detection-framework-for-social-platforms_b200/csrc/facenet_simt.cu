@@ -9,9 +9,12 @@
 
 // ----------------------------------------------------------------------------- stem
 // thread = one output pixel x 32 channels; weights [27][32] fp32 in shared memory
+// `d_n` (optional, every kernel of the forward pass): the live batch size on the device -- the number of face-bearing
+// crops after compaction (facenet_forward_valid), known only there; the launch is sized for the host-side bound `n`.
 __global__ void __launch_bounds__(128) stem_conv_kernel(const uint8_t* __restrict__ crops, int n, int S, int Ho,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
-                                                       bf16* __restrict__ out) {
+                                                       bf16* __restrict__ out, const int* __restrict__ d_n) {
+  if (d_n) n = min(n, *d_n);
   __shared__ __align__(16) float w_s[27 * 32];
   __shared__ float b_s[32];
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) w_s[i] = w[i];
@@ -59,16 +62,17 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const uint8_t* __restric
 }
 
 int launch_stem_conv(trl_ctx* c, const uint8_t* d_crops, int n, int S, const float* w, const float* bias, bf16* out,
-                     int Ho, cudaStream_t s) {
+                     int Ho, cudaStream_t s, const int* d_n) {
   const long long total = (long long)n * Ho * Ho;
   if (total == 0) return TRL_OK;
-  stem_conv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_crops, n, S, Ho, w, bias, out);
+  stem_conv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_crops, n, S, Ho, w, bias, out, d_n);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
 
 // ----------------------------------------------------------------------------- maxpool 3x3 s2 (NHWC, 8 channels / thread)
-__global__ void __launch_bounds__(256) maxpool_kernel(PoolOp op, int n) {
+__global__ void __launch_bounds__(256) maxpool_kernel(PoolOp op, int n, const int* __restrict__ d_n) {
+  if (d_n) n = min(n, *d_n);
   const int cg = op.C / 8;
   const long long total = (long long)n * op.Hout * op.Wout * cg;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,10 +106,10 @@ __global__ void __launch_bounds__(256) maxpool_kernel(PoolOp op, int n) {
   *reinterpret_cast<uint4*>(op.out + (((size_t)img * op.Hout + oy) * op.Wout + ox) * op.out_ctot + op.out_coff + g * 8) = o;
 }
 
-int launch_maxpool(trl_ctx* c, const PoolOp& op, int n, cudaStream_t s) {
+int launch_maxpool(trl_ctx* c, const PoolOp& op, int n, cudaStream_t s, const int* d_n) {
   const long long total = (long long)n * op.Hout * op.Wout * (op.C / 8);
   if (total == 0) return TRL_OK;
-  maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(op, n);
+  maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(op, n, d_n);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
@@ -114,7 +118,10 @@ int launch_maxpool(trl_ctx* c, const PoolOp& op, int n, cudaStream_t s) {
 // HEAD_G crops per CTA, 512 threads = 512 embedding dims.  w_t: [1792][512] fp32 (last_linear * last_bn scale, transposed).
 constexpr int HEAD_G = 2;
 __global__ void __launch_bounds__(512) head_kernel(const bf16* __restrict__ feat, int n, int hw, const float* __restrict__ w_t,
-                                                  const float* __restrict__ bias, float* __restrict__ emb) {
+                                                  const float* __restrict__ bias, float* __restrict__ emb,
+                                                  const int* __restrict__ d_n) {
+  if (d_n) n = min(n, *d_n);
+  if ((int)blockIdx.x * HEAD_G >= n) return;     // whole CTA beyond the live batch
   extern __shared__ __align__(16) float x_s[];   // [HEAD_G][1792]
   __shared__ float red[HEAD_G][16];
   const int n0 = blockIdx.x * HEAD_G;
@@ -159,21 +166,23 @@ __global__ void __launch_bounds__(512) head_kernel(const bf16* __restrict__ feat
   }
 }
 
-int launch_head(trl_ctx* c, const bf16* feat, int n, int hw, const float* w_t, const float* bias, float* emb, cudaStream_t s) {
+int launch_head(trl_ctx* c, const bf16* feat, int n, int hw, const float* w_t, const float* bias, float* emb, cudaStream_t s,
+                const int* d_n) {
   if (n <= 0) return TRL_OK;
   static bool attr = false;
   if (!attr) {
     TRL_CUDA(c, cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_G * 1792 * 4));
     attr = true;
   }
-  head_kernel<<<ceil_div(n, HEAD_G), 512, HEAD_G * 1792 * 4, s>>>(feat, n, hw, w_t, bias, emb);
+  head_kernel<<<ceil_div(n, HEAD_G), 512, HEAD_G * 1792 * 4, s>>>(feat, n, hw, w_t, bias, emb, d_n);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
 
 // ----------------------------------------------------------------------------- direct conv (validation path)
 // thread = one output pixel x one output channel, 8-wide bf16 vector loads along Cin.
-__global__ void __launch_bounds__(256) conv_simt_kernel(ConvOp op, int n) {
+__global__ void __launch_bounds__(256) conv_simt_kernel(ConvOp op, int n, const int* __restrict__ d_n) {
+  if (d_n) n = min(n, *d_n);
   const long long total = (long long)n * op.Hout * op.Wout * op.Cout;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -220,10 +229,10 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvOp op, int n) {
   }
 }
 
-int launch_conv_simt(trl_ctx* c, const ConvOp& op, int n, cudaStream_t s) {
+int launch_conv_simt(trl_ctx* c, const ConvOp& op, int n, cudaStream_t s, const int* d_n) {
   const long long total = (long long)n * op.Hout * op.Wout * op.Cout;
   if (total == 0) return TRL_OK;
-  conv_simt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(op, n);
+  conv_simt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(op, n, d_n);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }

@@ -140,7 +140,7 @@ __device__ unsigned long long g_umma_phase[8];
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_constant__ ConvOp op, int n_img, int tiles_w,
                                                                    int tiles_h, int n_ntiles, int total_tiles, int stages,
-                                                                   uint32_t acc_cols) {
+                                                                   uint32_t acc_cols, const int* __restrict__ d_n) {
   // shared memory: [stages x A][stages x B][barriers, tmem slot, row table][output tile][residual tile]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -184,6 +184,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
   // layer) may run while the previous kernel of the stream is still finishing; the activations may not.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (d_n) {
+    // live batch size known only on the device (face-bearing crops after compaction): shrink the tile list to it.
+    // The launch (grid, tensor maps) is sized for the host-side bound; rows beyond the live batch are never computed.
+    const int ne = min(n_img, *reinterpret_cast<const volatile int*>(d_n));
+    n_img = ne;
+    int tiles_n = 1;
+    if (op.flat) tiles_w = (int)(((long long)ne * op.Hout * op.Wout + 127) / 128);
+    else tiles_n = (ne + op.box_n - 1) / op.box_n;
+    total_tiles = tiles_w * tiles_h * tiles_n * n_ntiles;
+  }
 
   const int cin_blocks = op.Cin / BK;
   const int k_iters = op.kh * op.kw * cin_blocks;
@@ -512,7 +522,7 @@ int umma_encode_maps(trl_ctx* c, ConvOp& op, int n_cap) {
   return TRL_OK;
 }
 
-int launch_conv_umma(trl_ctx* c, const ConvOp& op, int n, cudaStream_t s) {
+int launch_conv_umma(trl_ctx* c, const ConvOp& op, int n, cudaStream_t s, const int* d_n) {
   using namespace umma;
   if (n <= 0) return TRL_OK;
   int tiles_w, tiles_h, tiles_n;
@@ -549,7 +559,7 @@ int launch_conv_umma(trl_ctx* c, const ConvOp& op, int n, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TRL_CUDA(c, cudaLaunchKernelEx(&cfg, conv_umma_kernel, op, n, tiles_w, tiles_h, n_ntiles, (int)total, stages, acc_cols));
+  TRL_CUDA(c, cudaLaunchKernelEx(&cfg, conv_umma_kernel, op, n, tiles_w, tiles_h, n_ntiles, (int)total, stages, acc_cols, d_n));
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }

@@ -226,7 +226,8 @@ class Analyzer:
                 self._check(self.lib.trl_crop_align(self.ctx, _vp(d_frames), B, H, Wd, _vp(boxes), self.box_cap * 5,
                                                     _vp(out["nfaces"]), _vp(out["box"]), _vp(out["valid"]), _vp(crops),
                                                     self._sptr()))
-                self._check(self.lib.trl_facenet(self.ctx, _vp(crops), B, self.crop_size, _vp(out["emb"]), self._sptr()))
+                self._check(self.lib.trl_facenet_valid(self.ctx, _vp(crops), _vp(out["valid"]), B, self.crop_size, _vp(out["emb"]),
+                                                       self._sptr()))
                 self._check(self.lib.trl_consistency(self.ctx, _vp(out["emb"]), _vp(out["valid"]), B, _vp(he), _vp(hv), thr,
                                                      _vp(out["sim"]), _vp(out["below"]), _vp(out["has_sim"]),
                                                      _vp(out["last_emb"]), _vp(out["last_valid"]), self._sptr()))
@@ -347,7 +348,8 @@ class Analyzer:
         with t.cuda.stream(self.stream):
             # one FaceNet batch for the whole range: per-chunk calls (tried, to hide FaceNet under the next copy) make the
             # step launch bound on the host (~110 launches per call) and were 8 ms slower end to end
-            self._check(self.lib.trl_facenet(self.ctx, _vp(out["crops"]), N, S, _vp(out["emb"]), self._sptr()))
+            self._check(self.lib.trl_facenet_valid(self.ctx, _vp(out["crops"]), _vp(out["valid"]), N, S, _vp(out["emb"]),
+                                                   self._sptr()))
             self._check(self.lib.trl_consistency_clips(
                 self.ctx, _vp(out["emb"]), _vp(out["valid"]), N, _vp(clip_start), _vp(he), _vp(hv), thr, _vp(out["sim"]),
                 _vp(out["below"]), _vp(out["has_sim"]), _vp(out["last_emb"]), _vp(out["last_valid"]), self._sptr()))
@@ -623,7 +625,7 @@ def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, a
         an.detect_align_uncapped(o["frames"][:n], o["box"][:n], o["valid"][:n], o["nfaces"][:n], o["crops"][:n])
         he, hv = halo_in if halo_in is not None else (None, None)
         with t.cuda.stream(an.stream):
-            an._check(an.lib.trl_facenet(an.ctx, _vp(o["crops"]), n, S, _vp(o["emb"]), an._sptr()))
+            an._check(an.lib.trl_facenet_valid(an.ctx, _vp(o["crops"]), _vp(o["valid"]), n, S, _vp(o["emb"]), an._sptr()))
             an._check(an.lib.trl_consistency(
                 an.ctx, _vp(o["emb"]), _vp(o["valid"]), n, _vp(he), _vp(hv), THRESHOLD_FACE_SIMILARITY, _vp(o["sim"]),
                 _vp(o["below"]), _vp(o["has_sim"]), _vp(o["last_emb"]), _vp(o["last_valid"]), an._sptr()))
