@@ -3,9 +3,13 @@
 
   python profiles/summarize_ncu.py launches gpurun_out/launches.csv > profiles/rNN_launches.md
   python profiles/summarize_ncu.py full gpurun_out/prof_x.ncu-rep   > profiles/rNN_x_full.md
+  python profiles/summarize_ncu.py traffic profiles/rNN_traffic.json WORKLOAD FRAMES_PER_LAUNCH rep1.ncu-rep [rep2 ...]
 
 `launches` takes the CSV written by  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ...
 `full` takes a report written by      ncu --set full --clock-control none --import-source on -o ...
+`traffic` reads dram__bytes_read.sum + dram__bytes_write.sum of the first launch in each report and writes the JSON that
+bench.py turns into `roofline.traffic` (so that number always comes from a capture, keyed by kernel, workload and frames
+per launch -- never from a literal in the bench).
 """
 import collections
 import csv
@@ -85,5 +89,33 @@ def full(path):
         print()
 
 
+def _to_bytes(value, unit):
+    v = float(value.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1)
+
+
+def traffic(out_path, workload, frames_per_launch, *reports):
+    import json
+    import os
+    recs = []
+    for path in reports:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        hdr, units, r = rows[0], rows[1], rows[2]
+        rd, wr, du = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+        full_name = r[hdr.index("Kernel Name")]
+        m = re.search(r"(\w+)\s*(<|\(|$)", re.sub(r"^void\s+", "", full_name).split("::")[-1])
+        name = m.group(1) if m else full_name
+        recs.append({"kernel": name, "workload": workload, "frames_per_launch": float(frames_per_launch),
+                     "dram_bytes_read": _to_bytes(r[rd], units[rd]), "dram_bytes_write": _to_bytes(r[wr], units[wr]),
+                     "dram_bytes_per_launch": _to_bytes(r[rd], units[rd]) + _to_bytes(r[wr], units[wr]),
+                     "duration": f"{r[du]} {units[du]} (under ncu)", "source": os.path.basename(path)})
+    json.dump(recs, open(out_path, "w"), indent=1)
+    print(json.dumps(recs, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
