@@ -39,6 +39,9 @@ namespace pnet {
 #ifndef PNET_C1_FFMA2
 #define PNET_C1_FFMA2 1
 #endif
+#ifndef PNET_C2_PIPE
+#define PNET_C2_PIPE 0
+#endif
 constexpr int TOY = PNET_TOY, TOX = PNET_TOX;   // output cells per CTA
 constexpr int P1H = TOY + 4, P1W = TOX + 4;  // pooled conv1 tile (20 x 36), flat pixel index n = row * P1W + col
 constexpr int C2TILES_ = ((TOY + 2) * P1W + 15) / 16;
@@ -648,49 +651,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
         for (int j = 0; j < 2; ++j)
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[q][j][e] = 0.f;
-#pragma unroll
-      for (int s = 0; s < 6; ++s) {
+      // Software pipelined over the six k-steps: the A fragments (and weights) of step s + 1 are requested before the MMAs
+      // of step s are issued, so the shared-memory latency of a step hides under the previous step's tensor work
+      // (PNET_C2_PIPE = 0 keeps the straight load-then-multiply order).
+      uint32_t ah[2][3][4], al[2][3][4];
+      uint4 bhv[2], blv[2];
+      auto load_step = [&](int s, int buf) {
         const int o0 = tab[8 * s + t], o1 = tab[8 * s + t + 4];
-        const uint4 bh = *reinterpret_cast<const uint4*>(&wu[W2 + ((2 * s + 0) * 32 + lane) * 4]);
-        uint4 bl = make_uint4(0u, 0u, 0u, 0u);
-        if (TERMS == 3) bl = *reinterpret_cast<const uint4*>(&wu[W2 + ((2 * s + 1) * 32 + lane) * 4]);
-        uint32_t ah[3][4], al[3][4];
+        bhv[buf] = *reinterpret_cast<const uint4*>(&wu[W2 + ((2 * s + 0) * 32 + lane) * 4]);
+        blv[buf] = make_uint4(0u, 0u, 0u, 0u);
+        if (TERMS == 3) blv[buf] = *reinterpret_cast<const uint4*>(&wu[W2 + ((2 * s + 1) * 32 + lane) * 4]);
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
           if (q >= nq) continue;               // warp uniform
-          ah[q][0] = p1h[base[q] + o0];
-          ah[q][1] = p1h[base[q] + 8 + o0];
-          ah[q][2] = p1h[base[q] + o1];
-          ah[q][3] = p1h[base[q] + 8 + o1];
+          ah[buf][q][0] = p1h[base[q] + o0];
+          ah[buf][q][1] = p1h[base[q] + 8 + o0];
+          ah[buf][q][2] = p1h[base[q] + o1];
+          ah[buf][q][3] = p1h[base[q] + 8 + o1];
           if (TERMS == 3) {
-            al[q][0] = p1l[base[q] + o0];
-            al[q][1] = p1l[base[q] + 8 + o0];
-            al[q][2] = p1l[base[q] + o1];
-            al[q][3] = p1l[base[q] + 8 + o1];
+            al[buf][q][0] = p1l[base[q] + o0];
+            al[buf][q][1] = p1l[base[q] + 8 + o0];
+            al[buf][q][2] = p1l[base[q] + o1];
+            al[buf][q][3] = p1l[base[q] + 8 + o1];
           }
         }
+      };
+      if (PNET_C2_PIPE) load_step(0, 0);
+#pragma unroll
+      for (int s = 0; s < 6; ++s) {
+        const int cb = PNET_C2_PIPE ? (s & 1) : 0;
+        if (PNET_C2_PIPE) { if (s + 1 < 6) load_step(s + 1, cb ^ 1); }
+        else load_step(s, 0);
+        const uint4 bh = bhv[cb], bl = blv[cb];
         // the three terms of one accumulator are dependent: issue the 6 independent accumulators between them
         if (TERMS == 3) {
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             if (q < nq) {
-              mma_f16(acc[q][0], al[q][0], al[q][1], al[q][2], al[q][3], bh.x, bh.y);
-              mma_f16(acc[q][1], al[q][0], al[q][1], al[q][2], al[q][3], bh.z, bh.w);
+              mma_f16(acc[q][0], al[cb][q][0], al[cb][q][1], al[cb][q][2], al[cb][q][3], bh.x, bh.y);
+              mma_f16(acc[q][1], al[cb][q][0], al[cb][q][1], al[cb][q][2], al[cb][q][3], bh.z, bh.w);
             }
           }
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             if (q < nq) {
-              mma_f16(acc[q][0], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bl.x, bl.y);
-              mma_f16(acc[q][1], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bl.z, bl.w);
+              mma_f16(acc[q][0], ah[cb][q][0], ah[cb][q][1], ah[cb][q][2], ah[cb][q][3], bl.x, bl.y);
+              mma_f16(acc[q][1], ah[cb][q][0], ah[cb][q][1], ah[cb][q][2], ah[cb][q][3], bl.z, bl.w);
             }
           }
         }
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
           if (q < nq) {
-            mma_f16(acc[q][0], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bh.x, bh.y);
-            mma_f16(acc[q][1], ah[q][0], ah[q][1], ah[q][2], ah[q][3], bh.z, bh.w);
+            mma_f16(acc[q][0], ah[cb][q][0], ah[cb][q][1], ah[cb][q][2], ah[cb][q][3], bh.x, bh.y);
+            mma_f16(acc[q][1], ah[cb][q][0], ah[cb][q][1], ah[cb][q][2], ah[cb][q][3], bh.z, bh.w);
           }
         }
       }
