@@ -6,7 +6,7 @@ in :mod:`model` keeps the reference's signature and return structure and drives
 PyTorch is used for device memory, streams and ``torch.distributed`` only.
 There is no CPU fallback: every compute entry point raises if the CUDA library is absent.
 """
-from . import synth, weights, _lib, model  # noqa: F401
+from . import synth, weights, _lib, model, service  # noqa: F401
 from .model import run, run_trace, Analyzer  # noqa: F401
 
 __version__ = "0.1.0"
