@@ -259,3 +259,23 @@ def test_flag_comparison_helper_only_frees_in_band_decisions():
     if abs(ref_sim[5] - 0.99) >= 1e-3:
         with pytest.raises(AssertionError):
             Hh.assert_flags_match_outside_band(valid, far, fl3, sc3, n * 4, 4, 30, valid, ref_sim, fl, sc)
+
+
+def test_vectorised_score_equals_the_frame_by_frame_machine():
+    """model.score_from_flags (numpy) against RunLength.step fed frame by frame and the oracle's final_score, random flags."""
+    rng = np.random.default_rng(21)
+    for trial in range(200):
+        n = int(rng.integers(0, 400))
+        valid = (rng.random(n) > rng.uniform(0, 0.5)).astype(np.uint8)
+        has = valid & (rng.random(n) > 0.1).astype(np.uint8)
+        below = (rng.random(n) > rng.uniform(0.02, 0.6)).astype(np.uint8)
+        stride = int(rng.integers(1, 9))
+        frame_count = n * stride - int(rng.integers(0, stride)) if n else 0
+        fps = int(rng.choice([7, 24, 30, 60]))
+        rl, flagged = M.RunLength(), []
+        for v, h, b in zip(valid, has, below):
+            flagged.append(rl.step(bool(b)) if (v and h) else False)
+        want = R.final_score(rl.deep_fake_frame_count, rl.deepfake_count, max(frame_count, 0), fps, stride)
+        score, fl, got = M.score_from_flags(valid, has, below, max(frame_count, 0), fps, stride)
+        assert fl == flagged and score == want
+        assert (got.deepfake_count, got.deep_fake_frame_count) == (rl.deepfake_count, rl.deep_fake_frame_count)

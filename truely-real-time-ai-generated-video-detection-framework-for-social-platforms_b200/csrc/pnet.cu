@@ -4,21 +4,33 @@
 //
 // upstream: models/mtcnn.py PNet.forward, models/utils/detect_face.py generateBoundingBox.
 //
-// conv1 (15 % of the MACs) runs on the FP32 FMA pipe with register-blocked thread tiles.  conv2 and conv3 (85 %) run
-// on the tensor pipe as implicit GEMMs with mma.sync.m16n8k16 and a 3-term fp16 split that keeps fp32-level
-// accuracy: every operand x is scaled by a power of two S and stored as hi = fp16(S x), lo = fp16(S x - hi);
+// Persistent and warp specialised: ONE 544-thread CTA per SM walks the list of tiles of every level and frame.
+//   group A (warps 0-7)  : stages the fp32 input tile (one 3-D TMA box, zero filled out of bounds, double buffered; cp.async when
+//                          the rows are not 16-byte aligned) and runs conv1 + PReLU + 2x2 max-pool on the FMA pipe (packed FFMA2),
+//                          writing the pooled tile as scaled fp16 hi / lo planes (double buffered towards group B);
+//   group B (warps 8-15) : conv2 as an implicit GEMM on the legacy tensor path (mma.sync.m16n8k16 -> HMMA.16816.F32), its
+//                          bias / PReLU / split epilogue into the UMMA operand planes, and the conv3 + heads epilogue
+//                          (tcgen05.ld -> bias, PReLU, conv4_1 / conv4_2, softmax, generateBoundingBox, candidate append);
+//   warp 16              : issues conv3 as tcgen05.mma implicit GEMMs (A = the conv2 tile in shared memory read through
+//                          shifted no-swizzle K-major descriptors, one per filter tap; fp32 accumulators in TMEM).
+// conv1 is 15 % of the MACs, conv2 + conv3 85 %.  The tensor-pipe layers keep fp32-level accuracy with a 3-term fp16 split:
+// every operand x is scaled by a power of two S and stored as hi = fp16(S x), lo = fp16(S x - hi);
 //     S_a S_w sum(a w) ~= sum(a_hi w_hi) + sum(a_lo w_hi) + sum(a_hi w_lo)          (fp32 accumulate)
 // drops only a_lo w_lo (2^-22 relative) and lo's own rounding (2^-22 relative; the scale keeps lo out of fp16's
 // subnormal range for |x| >= 2^-9, below that the absolute error is < 1e-9).  The result is unscaled exactly in the
 // epilogue.  Against the fp32 oracle the maps agree to ~1e-6 (tests/test_gpu_stages.py bar: 2e-5), so the cascade
-// sees the same candidates.  k16 fp16 MMAs need half the tensor-pipe cycles of the 3xTF32 (k8) form of the same
-// product, and the operands are split once where they are produced (weights on the host, activations in the
+// sees the same candidates.  The operands are split once where they are produced (weights on the host, activations in the
 // producing layer's epilogue), not in the MMA loop.  Activations beyond +-1000 would overflow the scaled fp16 hi part:
 // the kernel raises the capacity flag (stage 5) instead of continuing silently.
-// tcgen05 was measured and rejected for these layers: with N = 16/32 output channels an SS-mode UMMA is bound by
-// re-reading the A tile from shared memory (~73 cycles per M128 x N32 x K8 step, experiments/umma_probe.cu).
-// The two CTAs of an SM overlap one CTA's FMA-pipe stage with the other's tensor-pipe stages.
-// FLOP roof, not HBM, binds this kernel.
+// A single-pass variant (TERMS = 1: hi parts only, trl_config_t.pnet_precision = 1) exists as a measured experiment: 15 %
+// faster, maps within ~1e-4, but the cascade is chaotic in the last bits (integer truncation of boxes) -- face counts, boxes
+// and embeddings left the north-star tolerances on the bundled and the 1080p clips, so it is not the default
+// (profiles/PROFILE_NOTES.md r02).
+// Roofs (profiles/r02_pnet_full.md, experiments/fma_rate_probe.cu, hmma_rate_probe.cu): per tile the FMA pipe is busy
+// ~9 k of 18.5 k cycles (conv1's FFMA2 stream + the two epilogues), the tensor pipe ~9 k (1476 HMMA at one per 2.7 cycles
+// next to an FFMA2 stream + 90 UTCHMMA at ~60 cycles), the issue slots 65 %: no single pipe is saturated, the two groups are
+// latency bound at 4.25 warps per scheduler (216 KB of shared memory pin the kernel to one CTA per SM).  HBM is not the
+// roof: the kernel reads the pyramid exactly once.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -43,20 +55,20 @@ namespace pnet {
 #define PNET_C2_PIPE 0
 #endif
 constexpr int TOY = PNET_TOY, TOX = PNET_TOX;   // output cells per CTA
-constexpr int P1H = TOY + 4, P1W = TOX + 4;  // pooled conv1 tile (20 x 36), flat pixel index n = row * P1W + col
+constexpr int P1H = TOY + 4, P1W = TOX + 4;  // pooled conv1 tile (24 x 32 for the 20 x 28 tile), flat pixel index n = row * P1W + col
 constexpr int C2TILES_ = ((TOY + 2) * P1W + 15) / 16;
-// pixels per p1 plane: the tile + slack read by conv2's last (partial) M tile, rounded up to 8 mod 32 (744 for 16 x 32)
+// pixels per p1 plane: the tile + slack read by conv2's last (partial) M tile, rounded up to 8 mod 32 (776 for 20 x 28)
 constexpr int P1PL = ((C2TILES_ * 16 + 2 * P1W + 2 - 8 + 31) / 32) * 32 + 8;
 static_assert(P1PL >= P1H * P1W && P1PL >= C2TILES_ * 16 + 2 * P1W + 2, "p1 plane covers the tile and conv2's slack reads");
                                              // spreads the four channel-pair planes a warp reads at once over the banks
 constexpr int P1WORDS = 5;                   // 10 channels = 5 half2 planes [pair][pixel] (hi set, lo set)
-constexpr int C2H = TOY + 2, C2P = P1W;      // conv2 tile: 18 rows at the same pitch as its input (flat indexing)
-constexpr int C2PX = C2H * C2P;              // 648 pixels (columns 34, 35 of a row are never read)
-constexpr int C2TILES = (C2PX + 15) / 16;    // 41 M tiles of two 8-pixel segments
+constexpr int C2H = TOY + 2, C2P = P1W;      // conv2 tile: 22 rows at the same pitch as its input (flat indexing)
+constexpr int C2PX = C2H * C2P;              // 704 pixels (columns 30, 31 of a row are computed but never read)
+constexpr int C2TILES = (C2PX + 15) / 16;    // 44 M tiles of two 8-pixel segments
 // conv2 output = conv3's UMMA A operand: four planes [hi k0, hi k1, lo k0, lo k1] of [pixel][8 channels = 16 B]
 // (no-swizzle K-major core matrices: 8 consecutive pixels x 16 B; k-half stride = plane, 8-pixel stride = 128 B)
-constexpr int C3TILES = (TOY * C2P + 127) / 128;   // conv3 M tiles of 128 flat pixels (16 rows x pitch 36 = 576 = 4.5 tiles -> 5)
-constexpr int C2NP = ((C3TILES * 128 + 2 * C2P + 2 + 15) / 16) * 16;   // pixels per plane: computed + slack read by the last (partial) M tile (720 for 16 x 32)
+constexpr int C3TILES = (TOY * C2P + 127) / 128;   // conv3 M tiles of 128 flat pixels (20 rows x pitch 32 = 640 = exactly 5 tiles)
+constexpr int C2NP = ((C3TILES * 128 + 2 * C2P + 2 + 15) / 16) * 16;   // pixels per plane: computed + slack read by the last M tile (720 for 20 x 28)
 static_assert(C2NP >= C2PX, "c2 plane covers the conv2 tile");
 constexpr int C2PLANE = C2NP * 4;            // words per plane
 constexpr int TMEM_COLS = 512;
@@ -76,8 +88,8 @@ constexpr int NB_THREADS = 32 * NB_WARPS;
 constexpr int ISSUE_WARP = NA_WARPS + NB_WARPS;
 constexpr int NTHREADS = 32 * (ISSUE_WARP + 1);   // group A warps: staging + conv1, then group B: conv2 + heads, last warp: conv3 MMA issue
 static_assert(NB_WARPS % 4 == 0 && NA_WARPS % 4 == 0, "group B covers the four TMEM lane groups evenly and starts at a multiple of 4");
-constexpr int INH = 2 * TOY + 10, INW = 2 * TOX + 10;   // 42 x 74 input tile
-constexpr int INP = (INW + 3) / 4 * 4;       // row pitch: 16-byte multiple (76 for 16 x 32)
+constexpr int INH = 2 * TOY + 10, INW = 2 * TOX + 10;   // 50 x 66 input tile
+constexpr int INP = (INW + 3) / 4 * 4;       // row pitch: 16-byte multiple (68 for 20 x 28)
 static_assert(C3TILES * 64 <= 512, "conv3 accumulators fit TMEM");
 
 constexpr float SA = 64.f;                   // activation scale (p1 and c2 tiles)
@@ -96,13 +108,13 @@ constexpr int SC = W3 + 9 * 2 * 64 * 4;   // [4]: 1 / (SA * S_w2)
 constexpr int WTOTAL = SC + 4;
 static_assert(WTOTAL % 4 == 0 && W2 % 4 == 0 && W3 % 4 == 0, "16-byte alignment of the operand arrays");
 
-constexpr int SM_IN = ((3 * INH * INP + 31) / 32) * 32;      // 9576 words, padded to 128 bytes (TMA destination alignment)
+constexpr int SM_IN = ((3 * INH * INP + 31) / 32) * 32;      // 10208 words, padded to 128 bytes (TMA destination alignment)
 constexpr int IN_BYTES = 3 * INH * INP * 4;                  // bytes one TMA box delivers
 constexpr int IN_OFF = ((WTOTAL + 31) / 32) * 32;            // input tiles start 128-byte aligned behind the weights
 constexpr int SM_C2 = 4 * C2PLANE;                   // 11520 words
-constexpr int SM_P1 = 2 * P1WORDS * P1PL;            // 7440 words
+constexpr int SM_P1 = 2 * P1WORDS * P1PL;            // 7760 words
 constexpr int SMEM_WORDS = IN_OFF + 2 * SM_IN + 2 * SM_P1 + SM_C2;    // weights, 2 input tiles, 2 pooled conv1 tiles, conv2 planes
-constexpr int SMEM_BYTES = SMEM_WORDS * 4;           // ~206 KB -> one persistent CTA per SM
+constexpr int SMEM_BYTES = SMEM_WORDS * 4;           // 216 KB -> one persistent CTA per SM
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct Level {
@@ -117,7 +129,7 @@ struct Level {
 };
 
 struct Params {
-  CUtensorMap tmap[TRL_MAX_SCALES];   // per level: fp32 {ws, hs, 3 B} view of the pyramid, box {76, 42, 3}, zero fill out of bounds
+  CUtensorMap tmap[TRL_MAX_SCALES];   // per level: fp32 {ws, hs, 3 B} view of the pyramid, box {INP, INH, 3} = {68, 50, 3}, zero fill out of bounds
   int use_tma;         // 1: every level has a tensor map (16-byte aligned rows); 0: cp.async staging
   int n_levels;
   int blocks;          // tiles per frame (all levels)

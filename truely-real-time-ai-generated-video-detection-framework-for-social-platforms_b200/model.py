@@ -399,12 +399,24 @@ def chunk_schedule(n: int, chunk: int, ramp: bool = False):
 
 
 def score_from_flags(valid, has_sim, below, frame_count: int, fps: int, stride: int):
-    """K13 on the host: run-length machine over the per-frame flags (server/model.py:62-70) + score (83-95)."""
+    """K13 on the host: run-length machine over the per-frame flags (server/model.py:62-70) + score (83-95).
+
+    Vectorised (the flags of a whole clip -- or of all ranks' shards -- arrive at once): among the compared frames
+    (valid and has_sim) the counter after frame i is the length of the run of `below` ending at i, a frame is flagged when
+    that length exceeds 15.  Same integers as feeding RunLength.step frame by frame (tests/test_host.py)."""
+    v = np.asarray(valid).astype(bool) & np.asarray(has_sim).astype(bool)
+    idx = np.flatnonzero(v)
+    flagged = np.zeros(len(v), bool)
     rl = RunLength()
-    flagged = []
-    for v, h, b in zip(valid, has_sim, below):
-        flagged.append(rl.step(bool(b)) if (v and h) else False)
-    return final_score(rl.deep_fake_frame_count, rl.deepfake_count, frame_count, fps, stride), flagged, rl
+    if len(idx):
+        b = np.asarray(below)[idx].astype(np.int64)
+        c = np.cumsum(b)
+        run = c - np.maximum.accumulate(np.where(b == 0, c, 0))     # consecutive `below` frames ending here
+        f = run > THRESHOLD_FRAMES_FOR_DEEPFAKE
+        flagged[idx] = f
+        rl.deepfake_count = int(run[-1])
+        rl.deep_fake_frame_count = int(f.sum())
+    return final_score(rl.deep_fake_frame_count, rl.deepfake_count, frame_count, fps, stride), flagged.tolist(), rl
 
 
 def score_clips(valid, has_sim, below, clips, fps: int, stride: int):
@@ -469,7 +481,7 @@ def final_score(deep_fake_frame_count: int, deepfake_count: int, frame_count: in
     """server/model.py:83-95."""
     if frame_count == 0:
         return 0
-    total_processed_frames = sum(1 for i in range(frame_count) if i % stride == 0)
+    total_processed_frames = (frame_count + stride - 1) // stride      # == sum(1 for i in range(frame_count) if i % stride == 0)
     if total_processed_frames == 0:
         return 0
     deepfake_percentage = (deep_fake_frame_count / total_processed_frames) * 100
