@@ -52,6 +52,8 @@ struct PyrParams {
   int rows[TRL_MAX_SCALES];            // output rows per CTA (pyramid kernel)
   int fastdiv[TRL_MAX_SCALES];         // 1: the verified 3-instruction division may be used for this level
   int tab_off[TRL_MAX_SCALES];         // offset of level k's window tables
+  int kwmin[TRL_MAX_SCALES];           // narrowest horizontal window of level k; > 0: every window is kwmin or kwmin + 1 columns
+                                       // wide and kwmin <= 5 (branch-free pass 2), 0: general loop
 };
 
 
@@ -157,6 +159,7 @@ struct trl_ctx {
   int pyr_tab_H = 0, pyr_tab_W = 0;
   int pyr_tab_off[TRL_MAX_SCALES] = {0};
   int pyr_fastdiv[TRL_MAX_SCALES] = {0};
+  int pyr_kwmin[TRL_MAX_SCALES] = {0};
   Cand* d_cand1 = nullptr;       // [B][n_scales][cand_cap_scale]   P-Net candidates
   int* d_cnt1 = nullptr;         // [B][n_scales]
   Cand* d_cand2 = nullptr;       // [B][cand_cap_frame]             after per-scale NMS

@@ -97,6 +97,42 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t* __restrict__ frames
   return v;
 }
 
+// Pass 2 of one output row when every window of the level is KMIN or KMIN + 1 columns wide: the KMIN certain columns are
+// summed unconditionally, the possible extra one under a predicate -- no per-pixel loop, no divergence between neighbouring
+// pixels whose windows differ by one column (the general loop spent ~60 of its ~140 warp instructions per 32 pixels on the
+// branch ladder of its unrolled variable-trip loop).  Same integer sums, same two divisions: bit identical.
+template <int KMIN>
+__device__ __forceinline__ void hpass_fixed(const uint16_t* __restrict__ vr, const int2* __restrict__ tw, int ws, int tid,
+                                            float fkh, float rkh, bool fast, float* __restrict__ o0, int plane) {
+  float* o1 = o0 + plane;
+  float* o2 = o1 + plane;
+  for (int i = tid; i < ws; i += 256, o0 += 256, o1 += 256, o2 += 256, tw += 256) {
+    const int2 e = __ldg(tw);
+    const int xw = e.x;
+    const float rkw = __int_as_float(e.y);
+    const int kw = xw >> 16;
+    const uint16_t* vp = vr + 3 * (xw & 0xFFFF);
+    int s0 = vp[0], s1 = vp[1], s2 = vp[2];
+#pragma unroll
+    for (int x = 1; x < KMIN; ++x) { s0 += vp[3 * x]; s1 += vp[3 * x + 1]; s2 += vp[3 * x + 2]; }
+    if (kw > KMIN) { s0 += vp[3 * KMIN]; s1 += vp[3 * KMIN + 1]; s2 += vp[3 * KMIN + 2]; }
+    const float fkw = (float)kw;
+    float a0, a1, a2;
+    if (fast) {
+      a0 = div_small(div_small((float)s0, fkh, rkh), fkw, rkw);
+      a1 = div_small(div_small((float)s1, fkh, rkh), fkw, rkw);
+      a2 = div_small(div_small((float)s2, fkh, rkh), fkw, rkw);
+    } else {
+      a0 = __fdiv_rn(__fdiv_rn((float)s0, fkh), fkw);
+      a1 = __fdiv_rn(__fdiv_rn((float)s1, fkh), fkw);
+      a2 = __fdiv_rn(__fdiv_rn((float)s2, fkh), fkw);
+    }
+    *o0 = __fmul_rn(__fsub_rn(a0, 127.5f), 0.0078125f);
+    *o1 = __fmul_rn(__fsub_rn(a1, 127.5f), 0.0078125f);
+    *o2 = __fmul_rn(__fsub_rn(a2, 127.5f), 0.0078125f);
+  }
+}
+
 template <int MODE>     // 0: byte-aligned rows, 1: 4-byte aligned rows, 2: 16-byte aligned rows (one 128-bit load per thread and row)
 __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restrict__ frames, int H, int W, size_t total_bytes,
                                                          const __grid_constant__ PyrParams p, const int* __restrict__ tab,
@@ -192,6 +228,18 @@ __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restr
     const int kh = __ldg(ty1 + jj) - __ldg(ty0 + jj);
     const float fkh = (float)kh, rkh = __frcp_rn(fkh);
     const uint16_t* vr = v16 + jj * (4 * nw);
+    if (p.kwmin[lvl] > 0) {
+      const int2* twf = reinterpret_cast<const int2*>(t) + tid;
+      float* of = obase + jj * pitch + tid;
+      switch (p.kwmin[lvl]) {
+        case 1: hpass_fixed<1>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
+        case 2: hpass_fixed<2>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
+        case 3: hpass_fixed<3>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
+        case 4: hpass_fixed<4>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
+        default: hpass_fixed<5>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
+      }
+      continue;
+    }
     // per-thread running pointers: one 64-bit add per plane and step instead of rebuilding three addresses per pixel
     float* o0 = obase + jj * pitch + tid;
     float* o1 = o0 + plane;
@@ -260,6 +308,8 @@ static int build_pyramid_tables(trl_ctx* c, int H, int W, const PyramidGeom& g, 
     for (int i = 0; i < g.ws[k]; ++i) kws.push_back(x1[i] - x0[i]);
     std::sort(khs.begin(), khs.end()); khs.erase(std::unique(khs.begin(), khs.end()), khs.end());
     std::sort(kws.begin(), kws.end()); kws.erase(std::unique(kws.begin(), kws.end()), kws.end());
+    // adaptive-pool windows of one level are kwmin or kwmin + 1 wide; the fine levels (87 % of the pixels) have kwmin <= 5
+    c->pyr_kwmin[k] = (kws.back() <= kws.front() + 1 && kws.front() >= 1 && kws.front() <= 5) ? kws.front() : 0;
     for (int a : khs)
       for (int b : kws) { pairs.push_back(make_int2(a, b)); pair_level.push_back(k); }
   }
@@ -311,6 +361,7 @@ int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, con
     off += 3LL * g.hs[k] * g.ws[k];
     p.tab_off[k] = c->pyr_tab_off[k];
     p.fastdiv[k] = c->pyr_fastdiv[k];
+    p.kwmin[k] = c->pyr_kwmin[k];
     // rows per CTA: about 8-12 source rows of work, bounded by 64 KB of column sums
     int R = (int)(8.0 * g.hs[k] / H);
     R = std::max(1, std::min(R, 4));
