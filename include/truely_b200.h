@@ -66,9 +66,14 @@ typedef struct {
   int cand_cap_frame;     /* capacity: R-Net inputs per frame (candidates surviving stage-1 NMS); default 1024, at most 16384 */
   int box_cap_frame;      /* capacity: O-Net inputs / final boxes per frame; default 128, at most 2048 */
   int facenet_impl;       /* 0 = tcgen05 implicit-GEMM path (product); 1 = SIMT direct-conv kernels (validation) */
-  int pnet_precision;     /* P-Net conv2/conv3 tensor-core operands: 0 = 3-term fp16 split (maps within 2e-5 of the fp32
-                             reference); 1 = single-pass fp16 (a third of the tensor work; maps within ~2e-3, parity judged at
-                             cascade level: same face count, IoU >= 0.95) */
+  int pnet_precision;     /* how the cascade evaluates P-Net (the trl_pnet stage entry point always uses 0):
+                             0 = one kernel, 3-term fp16 operand split on the tensor pipe (maps within 2e-5 of the fp32 reference);
+                             1 = one kernel, single-pass fp16 (experiment: maps within ~2e-3, candidates may differ);
+                             2 = hybrid: the single-pass kernel of (1) only screens -- cells with prob >= thresholds[0] - 0.05
+                                 are re-evaluated exactly in fp32 (12x12 receptive field each) and thresholded there, so the
+                                 candidate set and its scores / regressions are those of an fp32 P-Net;
+                             3 = hybrid with the all-tcgen05 screening kernel on fp16 pixel-pair pyramid images (the default
+                                 of the Python host; fastest) */
   int mode;               /* 0 = the reference's crop path (server/model.py:49-58): truncated + clamped box, cv2.resize
                              INTER_LINEAR to crop_size, F.to_tensor (/255).  1 = "mode B", upstream facenet_pytorch's own
                              face crop as the north star words it: extract_face (margin-adjusted box, cv2.resize INTER_AREA
@@ -93,6 +98,17 @@ int trl_pyramid_geometry(const trl_ctx_t* ctx, int H, int W, double* scales, int
 /* K1: imresample(mode="area") + (x-127.5)*0.0078125 for every scale.
  * d_out: concatenation over scales of float32 [B,3,hs,ws]. */
 int trl_pyramid(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, float* d_out, void* stream);
+
+/* K1 in the layout of the all-tensor-pipe P-Net (pnet_precision 3): every level as two images of pixel PAIRS, 16 bytes per pair
+ * = 2 x (B, G, R, 0) fp16; d_hi holds fp16(v), d_lo holds fp16(v - hi) (hi + lo restores v to 2^-23 relative).  Level k of a
+ * batch of B frames starts at pair offset level_off[k] * B and is [B, hs, pitch_pairs[k]] pairs (trl_pyramid_pairs_size, which
+ * returns the number of levels); the pad pixel of an odd-width level is not written. */
+int trl_pyramid_pairs_size(const trl_ctx_t* ctx, int H, int W, long long* pairs_per_frame, long long* level_off, int* pitch_pairs);
+int trl_pyramid_pairs(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, void* d_hi, void* d_lo, void* stream);
+
+/* K2 (screen): the single-pass tcgen05 P-Net on the hi image of trl_pyramid_pairs; d_logit receives, levels concatenated,
+ * float32 [B, oh, ow] = conv4_1 logit of class 1 minus class 0 (sigmoid of it approximates PNet's probability map to ~1e-3). */
+int trl_pnet_screen_maps(trl_ctx_t* ctx, const void* d_hi, int B, int H, int W, float* d_logit, void* stream);
 
 /* K2: PNet.forward on one pyramid level.  d_in float32 [B,3,hs,ws] -> d_prob [B,oh,ow] (softmax class 1),
  * d_reg [B,4,oh,ow]. */

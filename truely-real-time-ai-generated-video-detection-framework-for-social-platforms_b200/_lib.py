@@ -44,6 +44,9 @@ SIGNATURES = {
     "trl_pyramid_geometry": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "trl_pyramid": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "trl_pyramid_pairs_size": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
+    "trl_pyramid_pairs": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "trl_pnet_screen_maps": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "trl_pnet": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "trl_nms": (C.c_int, [_P, _P, _P, C.c_int, C.c_float, C.c_int, _P, _P, _P]),
     "trl_crop_resample": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P]),

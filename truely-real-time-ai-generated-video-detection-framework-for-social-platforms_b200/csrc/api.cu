@@ -47,7 +47,7 @@ void trl_default_config(trl_config_t* cfg) {
   cfg->cand_cap_frame = 1024;
   cfg->box_cap_frame = 128;
   cfg->facenet_impl = 0;
-  cfg->pnet_precision = 0;
+  cfg->pnet_precision = 3;      // hybrid P-Net: all-tcgen05 screen (pnet2.cu) + exact fp32 re-evaluation (pnet_refine.cu)
   cfg->mode = 0;
   cfg->margin = 0;
 }
@@ -77,10 +77,11 @@ static bool capacities_ok(int cap_scale, int cap_frame, int box_cap) {
 }
 
 static void free_workspace(trl_ctx* c) {
-  void* ptrs[] = {c->d_pyr, c->d_cand1, c->d_cnt1, c->d_cand2, c->d_cnt2, c->d_cand3, c->d_cnt3, c->d_pad3, c->d_rin,
+  void* ptrs[] = {c->d_pyr, c->d_pyr_hi, c->d_pyr_lo, c->d_screen, c->d_screen_cnt, c->d_cand1, c->d_cnt1, c->d_cand2, c->d_cnt2, c->d_cand3, c->d_cnt3, c->d_pad3, c->d_rin,
                   c->d_cand4, c->d_cnt4, c->d_pad4, c->d_oin, c->d_rprob, c->d_rreg, c->d_oprob, c->d_oreg,
                   c->d_boxes, c->d_nfaces, c->d_crops, c->d_nms_big};
   for (void* p : ptrs) if (p) cudaFree(p);
+  c->d_pyr_hi = nullptr; c->d_pyr_lo = nullptr; c->d_screen = nullptr; c->d_screen_cnt = nullptr; c->screen_cap = 0;
   c->d_pyr = nullptr; c->d_cand1 = nullptr; c->d_cnt1 = nullptr; c->d_cand2 = nullptr; c->d_cnt2 = nullptr;
   c->d_cand3 = nullptr; c->d_cnt3 = nullptr; c->d_pad3 = nullptr; c->d_rin = nullptr; c->d_cand4 = nullptr;
   c->d_cnt4 = nullptr; c->d_pad4 = nullptr; c->d_oin = nullptr; c->d_rprob = nullptr; c->d_rreg = nullptr;
@@ -98,6 +99,8 @@ void trl_destroy(trl_ctx_t* c) {
   free_workspace(c);
   facenet_destroy(c);
   if (c->d_pnet_packed) cudaFree(c->d_pnet_packed);
+  if (c->d_pnet_refine) cudaFree(c->d_pnet_refine);
+  if (c->d_pnet2_packed) cudaFree(c->d_pnet2_packed);
   if (c->d_rnet) cudaFree(c->d_rnet);
   if (c->d_onet) cudaFree(c->d_onet);
   if (c->d_nms_tmp) cudaFree(c->d_nms_tmp);
@@ -125,6 +128,7 @@ int trl_create(int device, const trl_weights_t* w, const trl_config_t* cfg, trl_
              std::to_string(nms_max_n()) + "]";
     return fail(TRL_E_INVALID);
   }
+  if (c->cfg.pnet_precision < 0 || c->cfg.pnet_precision > 3) { c->err = "trl_create: pnet_precision must be 0..3"; return fail(TRL_E_INVALID); }
   if (c->cfg.mode != 0 && c->cfg.mode != 1) { c->err = "trl_create: mode must be 0 (reference) or 1 (mode B)"; return fail(TRL_E_INVALID); }
   if (c->cfg.margin < 0 || c->cfg.margin >= c->cfg.crop_size) { c->err = "trl_create: margin must be in [0, crop_size)"; return fail(TRL_E_INVALID); }
   if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(TRL_E_CUDA); }
@@ -141,6 +145,8 @@ int trl_create(int device, const trl_weights_t* w, const trl_config_t* cfg, trl_
   int rc;
   if ((rc = nms_init(c)) != TRL_OK) return fail(rc);
   if (w->h_pnet && (rc = pnet_pack_weights(c, w->h_pnet, w->pnet_len)) != TRL_OK) return fail(rc);
+  if (w->h_pnet && (rc = pnet_refine_pack_weights(c, w->h_pnet, w->pnet_len)) != TRL_OK) return fail(rc);
+  if (w->h_pnet && (rc = pnet2_pack_weights(c, w->h_pnet, w->pnet_len)) != TRL_OK) return fail(rc);
   if (w->h_rnet && w->h_onet && (rc = ro_pack_weights(c, w->h_rnet, w->rnet_len, w->h_onet, w->onet_len)) != TRL_OK) return fail(rc);
   if (w->h_facenet && (rc = facenet_create(c, w->h_facenet, w->facenet_len)) != TRL_OK) return fail(rc);
   *out = c;
@@ -168,6 +174,35 @@ int trl_pyramid(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, floa
   int rc = compute_geometry(c->cfg, H, W, &g);
   if (rc != TRL_OK) TRL_FAIL(c, rc, "trl_pyramid: bad geometry %dx%d", H, W);
   return launch_pyramid(c, d_frames, B, H, W, g, d_out, false, (cudaStream_t)stream);
+}
+
+int trl_pyramid_pairs(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, void* d_hi, void* d_lo, void* stream) {
+  if (!c || !d_frames || !d_hi || !d_lo || B < 0) return TRL_E_INVALID;
+  PyramidGeom g;
+  int rc = compute_geometry(c->cfg, H, W, &g);
+  if (rc != TRL_OK) TRL_FAIL(c, rc, "trl_pyramid_pairs: bad geometry %dx%d", H, W);
+  return launch_pyramid_pairs(c, d_frames, B, H, W, g, reinterpret_cast<uint4*>(d_hi), reinterpret_cast<uint4*>(d_lo), (cudaStream_t)stream);
+}
+
+int trl_pyramid_pairs_size(const trl_ctx_t* c, int H, int W, long long* pairs_per_frame, long long* level_off, int* pitch_pairs) {
+  if (!c) return TRL_E_INVALID;
+  PyramidGeom g;
+  int rc = compute_geometry(c->cfg, H, W, &g);
+  if (rc != TRL_OK) return rc;
+  if (pairs_per_frame) *pairs_per_frame = g.pairs_total;
+  for (int k = 0; k < g.n; ++k) {
+    if (level_off) level_off[k] = g.off2[k];
+    if (pitch_pairs) pitch_pairs[k] = g.pitch2[k];
+  }
+  return g.n;
+}
+
+int trl_pnet_screen_maps(trl_ctx_t* c, const void* d_hi, int B, int H, int W, float* d_logit, void* stream) {
+  if (!c || !d_hi || !d_logit || B < 0) return TRL_E_INVALID;
+  PyramidGeom g;
+  int rc = compute_geometry(c->cfg, H, W, &g);
+  if (rc != TRL_OK) TRL_FAIL(c, rc, "trl_pnet_screen_maps: bad geometry %dx%d", H, W);
+  return launch_pnet2(c, reinterpret_cast<const uint4*>(d_hi), B, g, 0.5f, nullptr, nullptr, 0, d_logit, (cudaStream_t)stream);
 }
 
 int trl_pnet(trl_ctx_t* c, const float* d_in, int B, int hs, int ws, float* d_prob, float* d_reg, void* stream) {
@@ -225,7 +260,24 @@ static int ensure_workspace(trl_ctx* c, int B, int H, int W) {
   const PyramidGeom& g = c->geom;
   const size_t c1 = c->cfg.cand_cap_scale, c2 = c->cfg.cand_cap_frame, c4 = c->cfg.box_cap_frame;
   const int S = c->cfg.crop_size;
-  WS_ALLOC(c->d_pyr, (size_t)Bc * g.floats_total * sizeof(float));
+  if (c->cfg.pnet_precision == 3) {
+    // fp16 hi / lo pair images; the pad pixel of an odd-width level's last pair is never written again: zero it once
+    const size_t bytes = (size_t)Bc * g.pairs_total * sizeof(uint4);
+    WS_ALLOC(c->d_pyr_hi, bytes);
+    WS_ALLOC(c->d_pyr_lo, bytes);
+    TRL_CUDA(c, cudaMemset(c->d_pyr_hi, 0, bytes));
+    TRL_CUDA(c, cudaMemset(c->d_pyr_lo, 0, bytes));
+  } else {
+    WS_ALLOC(c->d_pyr, (size_t)Bc * g.floats_total * sizeof(float));
+  }
+  if (c->cfg.pnet_precision >= 2) {
+    long long cells = 0;
+    for (int k = 0; k < g.n; ++k) cells += (long long)(g.oh[k] > 0 ? g.oh[k] : 0) * (g.ow[k] > 0 ? g.ow[k] : 0);
+    const long long per_frame = std::min<long long>((long long)g.n * (long long)c1, cells);
+    c->screen_cap = (int)std::min<long long>((long long)Bc * std::max<long long>(per_frame, 1), 0x7fffffffLL / 16);
+    WS_ALLOC(c->d_screen, (size_t)c->screen_cap * sizeof(ScreenEntry));
+    WS_ALLOC(c->d_screen_cnt, sizeof(int));
+  }
   WS_ALLOC(c->d_cand1, (size_t)Bc * g.n * c1 * sizeof(Cand));
   WS_ALLOC(c->d_cnt1, (size_t)Bc * (g.n + 3) * sizeof(int));     // cnt1 [B][n] then cnt2 [B], cnt3 [B], cnt4 [B]
   c->d_cnt2 = nullptr;
@@ -268,10 +320,27 @@ static int join_tail(trl_ctx* c, cudaStream_t s) {
 static int detect_head(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, cudaStream_t s) {
   const PyramidGeom& g = c->geom;
   int rc;
-  TIMED(0, launch_pyramid(c, d_frames, B, H, W, g, c->d_pyr, true, s));
+  const int prec = c->cfg.pnet_precision;
+  if (prec == 3) { TIMED(0, launch_pyramid_pairs(c, d_frames, B, H, W, g, c->d_pyr_hi, c->d_pyr_lo, s)); }
+  else { TIMED(0, launch_pyramid(c, d_frames, B, H, W, g, c->d_pyr, true, s)); }
   if ((rc = join_tail(c, s)) != TRL_OK) return rc;          // previous tail still reads the candidate workspace
   TRL_CUDA(c, cudaMemsetAsync(c->d_cnt1, 0, (size_t)B * (g.n + 3) * sizeof(int), s));
-  TIMED(1, launch_pnet_candidates(c, c->d_pyr, B, g, c->cfg.thresholds[0], c->d_cand1, c->d_cnt1, c->cfg.cand_cap_scale, s));
+  if (prec < 2) {
+    TIMED(1, launch_pnet_candidates(c, c->d_pyr, B, g, c->cfg.thresholds[0], c->d_cand1, c->d_cnt1, c->cfg.cand_cap_scale, s));
+    return TRL_OK;
+  }
+  // hybrid: single-pass tensor-core screen at thr - margin, then the exact fp32 re-evaluation of the screened cells
+  const float thr = c->cfg.thresholds[0], thr_lo = thr - TRL_SCREEN_MARGIN;
+  TRL_CUDA(c, cudaMemsetAsync(c->d_screen_cnt, 0, sizeof(int), s));
+  {
+    StageScope _sc(c, s, 1);      // one stage record ("pnet") for screen + refine
+    if (prec == 3) rc = launch_pnet2_screen(c, c->d_pyr_hi, B, g, thr_lo, c->d_screen, c->d_screen_cnt, c->screen_cap, s);
+    else rc = launch_pnet_screen_v1(c, c->d_pyr, B, g, thr_lo, c->d_screen, c->d_screen_cnt, c->screen_cap, s);
+    if (rc != TRL_OK) return rc;
+    rc = launch_pnet_refine(c, prec == 3 ? 1 : 0, prec == 3 ? (const void*)c->d_pyr_hi : (const void*)c->d_pyr, c->d_pyr_lo, B, g, thr,
+                            c->d_screen, c->d_screen_cnt, c->screen_cap, c->d_cand1, c->d_cnt1, c->cfg.cand_cap_scale, s);
+    if (rc != TRL_OK) return rc;
+  }
   return TRL_OK;
 }
 

@@ -19,6 +19,12 @@ struct __align__(8) Cand {
   uint32_t key;           // tie-break key: position in the upstream list at this stage
 };
 
+// One P-Net cell kept by the single-pass screen for exact re-evaluation (pnet_refine.cu)
+struct ScreenEntry {
+  int group;   // frame * n_levels + level
+  int cell;    // oy * ow + ox
+};
+
 // capacity overflow record, written by kernels into pinned mapped host memory
 struct CapFlag {
   int overflow;   // 0 = ok
@@ -36,6 +42,9 @@ struct PyramidGeom {
   int pitch[TRL_MAX_SCALES];                    // row pitch (floats) of level k in the cascade's pyramid buffer: ws rounded up to 4
   int oh[TRL_MAX_SCALES], ow[TRL_MAX_SCALES];   // P-Net output map size
   long long off[TRL_MAX_SCALES];                // float offset of level k in the pyramid buffer, per frame count B: off*B
+  int pitch2[TRL_MAX_SCALES];                   // fp16 pair images (pnet2.cu): pixel PAIRS (16 bytes: 2 x BGR0 halves) per row = ceil(ws / 2)
+  long long off2[TRL_MAX_SCALES];               // pair offset of level k in the hi / lo pair images, per frame count B: off2*B
+  long long pairs_total;                        // pairs per frame of one pair image: sum hs*pitch2
   long long px_total;                           // sum hs*ws
   long long floats_total;                       // floats per frame of the padded pyramid buffer: sum 3*hs*pitch
 };
@@ -146,6 +155,9 @@ struct trl_ctx {
   // weights (device)
   float h_pnet_head[32 * 8 + 8 + 1 + 20] = {0};   // P-Net head / conv3 epilogue constants, copied into the kernel parameters
   float* d_pnet_packed = nullptr;   // smem image of P-Net (pnet.cu layout)
+  float h_pnet2_epi[152] = {0};     // pnet2.cu epilogue constants (biases, slopes, conv4_1 logit-difference weights)
+  float* d_pnet_refine = nullptr;   // fp32 weight image of the exact per-cell kernel (pnet_refine.cu)
+  uint32_t* d_pnet2_packed = nullptr;   // smem image of the all-tensor-pipe screening P-Net (pnet2.cu)
   float* d_rnet = nullptr;          // packed R-Net (mtcnn_ro.cu layout)
   float* d_onet = nullptr;
   FaceNetEngine* facenet = nullptr;
@@ -153,7 +165,12 @@ struct trl_ctx {
   // workspace for trl_detect / trl_process, sized for (ws_B, ws_H, ws_W)
   int ws_B = 0, ws_H = 0, ws_W = 0;
   PyramidGeom geom{};
-  float* d_pyr = nullptr;
+  float* d_pyr = nullptr;        // fp32 planar pyramid (pnet_precision 0-2)
+  uint4* d_pyr_hi = nullptr;     // pnet_precision 3: fp16 hi / lo pair images, [level][B][hs][pitch2] x 16 bytes
+  uint4* d_pyr_lo = nullptr;
+  ScreenEntry* d_screen = nullptr;   // cells kept by the single-pass screen (pnet_precision 2, 3)
+  int* d_screen_cnt = nullptr;
+  int screen_cap = 0;
   size_t pyr_smem_set = 0;       // dynamic shared memory the pyramid kernel has been opted in to
   int* d_pyr_tab = nullptr;      // adaptive-average window tables of the current frame shape
   int pyr_tab_H = 0, pyr_tab_W = 0;
@@ -245,6 +262,23 @@ int pnet_pack_weights(trl_ctx* c, const float* h_pnet, size_t len);
 int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float* d_prob, float* d_reg, cudaStream_t s);
 int launch_pnet_candidates(trl_ctx* c, const float* d_pyr, int B, const PyramidGeom& g, float thr, Cand* d_cand,
                            int* d_cnt, int cap, cudaStream_t s);
+
+// hybrid P-Net: single-pass screen (prob >= thr - TRL_SCREEN_MARGIN) + exact fp32 re-evaluation of the screened cells
+#define TRL_SCREEN_MARGIN 0.05f
+int launch_pnet_screen_v1(trl_ctx* c, const float* d_pyr, int B, const PyramidGeom& g, float thr_lo, ScreenEntry* d_screen,
+                          int* d_screen_cnt, int screen_cap, cudaStream_t s);
+int pnet_refine_pack_weights(trl_ctx* c, const float* h_pnet, size_t len);
+int launch_pnet_refine(trl_ctx* c, int fmt, const void* d_pyr, const void* d_pyr_lo, int B, const PyramidGeom& g, float thr,
+                       const ScreenEntry* d_screen, const int* d_screen_cnt, int screen_cap, Cand* d_cand, int* d_cnt, int cap,
+                       cudaStream_t s);
+int pnet2_pack_weights(trl_ctx* c, const float* h_pnet, size_t len);
+int launch_pnet2(trl_ctx* c, const uint4* d_pyr_hi, int B, const PyramidGeom& g, float thr_lo, ScreenEntry* d_screen,
+                 int* d_screen_cnt, int screen_cap, float* d_logit, cudaStream_t s);
+int launch_pnet2_screen(trl_ctx* c, const uint4* d_pyr_hi, int B, const PyramidGeom& g, float thr_lo, ScreenEntry* d_screen,
+                        int* d_screen_cnt, int screen_cap, cudaStream_t s);
+// fp16 hi / lo pair images of every level (the cascade's pyramid when pnet_precision == 3)
+int launch_pyramid_pairs(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const PyramidGeom& g, uint4* d_hi, uint4* d_lo,
+                         cudaStream_t s);
 
 int ro_pack_weights(trl_ctx* c, const float* h_rnet, size_t rlen, const float* h_onet, size_t olen);
 int launch_rnet(trl_ctx* c, const float* d_in, int n_max, const int* d_count, float* d_prob, float* d_reg, cudaStream_t s);

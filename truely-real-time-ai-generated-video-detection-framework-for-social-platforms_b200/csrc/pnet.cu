@@ -144,6 +144,9 @@ struct Params {
   float inv3;          // 1 / (SA * S_w3)
   float conv1_bias[10], conv1_slope[10];
   int conv1_monotone;  // 1: every conv1 PReLU slope is >= 0 (max-pool may run before bias + PReLU, exactly)
+  ScreenEntry* screen; // non-null: screening launch (hybrid P-Net) -- cells with prob >= thr go to this list for pnet_refine.cu
+  int* screen_cnt;
+  int screen_cap;
 };
 
 #ifdef PNET_TIMING
@@ -598,7 +601,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet_kernel(const float* __restri
           float* rg = Lv.reg + (size_t)b * 4 * plane + cell;
           rg[0] = h[2]; rg[plane] = h[3]; rg[2 * plane] = h[4]; rg[3 * plane] = h[5];
         }
-        if (Lv.cand && prob >= p.thr) {
+        if (p.screen) {
+          if (prob >= p.thr) {
+            const int slot = atomicAdd(p.screen_cnt, 1);
+            if (slot < p.screen_cap) {
+              p.screen[slot] = ScreenEntry{b * p.n_levels + lvl, (int)cell};
+            } else if (p.capflag) {
+              p.capflag->overflow = 1; p.capflag->stage = 1; p.capflag->frame = b;
+              p.capflag->count = slot + 1; p.capflag->capacity = p.screen_cap;
+            }
+          }
+        } else if (Lv.cand && prob >= p.thr) {
           // generateBoundingBox: q1 = floor((2*c + 1)/scale), q2 = floor((2*c + 12)/scale)  (fp32, true division)
           const int slotbase = b * p.n_levels + lvl;
           const int slot = atomicAdd(&Lv.cnt[slotbase], 1);
@@ -973,10 +986,26 @@ int launch_pnet_maps(trl_ctx* c, const float* d_in, int B, int hs, int ws, float
   return TRL_OK;
 }
 
+static int launch_pnet_levels(trl_ctx* c, const float* d_pyr, int B, const PyramidGeom& g, float thr, Cand* d_cand,
+                              int* d_cnt, int cap, ScreenEntry* d_screen, int* d_screen_cnt, int screen_cap, cudaStream_t s);
+
 int launch_pnet_candidates(trl_ctx* c, const float* d_pyr, int B, const PyramidGeom& g, float thr, Cand* d_cand,
                            int* d_cnt, int cap, cudaStream_t s) {
+  return launch_pnet_levels(c, d_pyr, B, g, thr, d_cand, d_cnt, cap, nullptr, nullptr, 0, s);
+}
+
+// screening launch of the hybrid P-Net on the fp32 pyramid: the single-pass variant of this kernel appends every cell with
+// prob >= thr_lo to the screen list (pnet_precision = 2; pnet2.cu is the faster screen, pnet_precision = 3)
+int launch_pnet_screen_v1(trl_ctx* c, const float* d_pyr, int B, const PyramidGeom& g, float thr_lo, ScreenEntry* d_screen,
+                          int* d_screen_cnt, int screen_cap, cudaStream_t s) {
+  return launch_pnet_levels(c, d_pyr, B, g, thr_lo, nullptr, nullptr, 0, d_screen, d_screen_cnt, screen_cap, s);
+}
+
+static int launch_pnet_levels(trl_ctx* c, const float* d_pyr, int B, const PyramidGeom& g, float thr, Cand* d_cand,
+                              int* d_cnt, int cap, ScreenEntry* d_screen, int* d_screen_cnt, int screen_cap, cudaStream_t s) {
   using namespace pnet;
   Params p{};
+  p.screen = d_screen; p.screen_cnt = d_screen_cnt; p.screen_cap = screen_cap;
   p.n_levels = g.n;
   int blocks = 0;
   for (int k = 0; k < g.n; ++k) {
@@ -1005,7 +1034,7 @@ int launch_pnet_candidates(trl_ctx* c, const float* d_pyr, int B, const PyramidG
     if (rc != TRL_OK) return rc;
   }
   if (blocks == 0 || B == 0) return TRL_OK;
-  if (c->cfg.pnet_precision == 1) pnet_kernel<1><<<grid_for(c, blocks, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
+  if (c->cfg.pnet_precision == 1 || d_screen) pnet_kernel<1><<<grid_for(c, blocks, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
   else pnet_kernel<3><<<grid_for(c, blocks, B), NTHREADS, SMEM_BYTES, s>>>(c->d_pnet_packed, p);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;

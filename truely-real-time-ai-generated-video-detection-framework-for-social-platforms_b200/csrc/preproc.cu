@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 // ----------------------------------------------------------------------------- shared device helpers
 
@@ -101,12 +102,35 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t* __restrict__ frames
 // summed unconditionally, the possible extra one under a predicate -- no per-pixel loop, no divergence between neighbouring
 // pixels whose windows differ by one column (the general loop spent ~60 of its ~140 warp instructions per 32 pixels on the
 // branch ladder of its unrolled variable-trip loop).  Same integer sums, same two divisions: bit identical.
-template <int KMIN>
+// Output formats of the pyramid kernel.  OUT = 0: planar fp32 [3][hs][pitch] (trl_pyramid, the 3-term P-Net).  OUT = 1: the
+// all-tensor-pipe P-Net's input (pnet2.cu): per pixel 4 halves (B, G, R, 0) = 8 bytes in a "hi" image (fp16(v): the screen's
+// operand) and a "lo" image (fp16(v - hi): with hi it restores v to 2^-23 relative for the exact re-evaluation,
+// pnet_refine.cu); one 8-byte store each instead of three 4-byte planar stores.
+template <int OUT> struct PyrOut;
+template <> struct PyrOut<0> {
+  typedef float T;
+  static __device__ __forceinline__ void store(float* o, long long plane, float v0, float v1, float v2) {
+    o[0] = v0; o[plane] = v1; o[2 * plane] = v2;
+  }
+};
+template <> struct PyrOut<1> {
+  typedef uint2 T;
+  static __device__ __forceinline__ void store(uint2* o, long long lo_off, float v0, float v1, float v2) {
+    const __half2 h01 = __floats2half2_rn(v0, v1);
+    const __half2 h2 = __floats2half2_rn(v2, 0.f);
+    const float2 f01 = __half22float2(h01);
+    const float f2 = __low2float(h2);
+    const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y);
+    const __half2 l2 = __floats2half2_rn(v2 - f2, 0.f);
+    o[0] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h2));
+    o[lo_off] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l2));
+  }
+};
+
+template <int KMIN, int OUT>
 __device__ __forceinline__ void hpass_fixed(const uint16_t* __restrict__ vr, const int2* __restrict__ tw, int ws, int tid,
-                                            float fkh, float rkh, bool fast, float* __restrict__ o0, int plane) {
-  float* o1 = o0 + plane;
-  float* o2 = o1 + plane;
-  for (int i = tid; i < ws; i += 256, o0 += 256, o1 += 256, o2 += 256, tw += 256) {
+                                            float fkh, float rkh, bool fast, typename PyrOut<OUT>::T* __restrict__ o0, long long plane) {
+  for (int i = tid; i < ws; i += 256, o0 += 256, tw += 256) {
     const int2 e = __ldg(tw);
     const int xw = e.x;
     const float rkw = __int_as_float(e.y);
@@ -127,16 +151,15 @@ __device__ __forceinline__ void hpass_fixed(const uint16_t* __restrict__ vr, con
       a1 = __fdiv_rn(__fdiv_rn((float)s1, fkh), fkw);
       a2 = __fdiv_rn(__fdiv_rn((float)s2, fkh), fkw);
     }
-    *o0 = __fmul_rn(__fsub_rn(a0, 127.5f), 0.0078125f);
-    *o1 = __fmul_rn(__fsub_rn(a1, 127.5f), 0.0078125f);
-    *o2 = __fmul_rn(__fsub_rn(a2, 127.5f), 0.0078125f);
+    PyrOut<OUT>::store(o0, plane, __fmul_rn(__fsub_rn(a0, 127.5f), 0.0078125f), __fmul_rn(__fsub_rn(a1, 127.5f), 0.0078125f),
+                       __fmul_rn(__fsub_rn(a2, 127.5f), 0.0078125f));
   }
 }
 
-template <int MODE>     // 0: byte-aligned rows, 1: 4-byte aligned rows, 2: 16-byte aligned rows (one 128-bit load per thread and row)
+template <int MODE, int OUT>     // MODE 0: byte-aligned rows, 1: 4-byte aligned rows, 2: 16-byte aligned rows (one 128-bit load per thread and row)
 __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restrict__ frames, int H, int W, size_t total_bytes,
                                                          const __grid_constant__ PyrParams p, const int* __restrict__ tab,
-                                                         float* __restrict__ out) {
+                                                         typename PyrOut<OUT>::T* __restrict__ out, long long lo_off) {
   extern __shared__ __align__(16) uint32_t vs[];      // [R][nw] x 2 words = u16 column sums [R][4*nw]
   int lvl = 0;
   while (lvl + 1 < p.n && (int)blockIdx.x >= p.blk_start[lvl + 1]) ++lvl;
@@ -220,9 +243,10 @@ __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restr
   __syncthreads();
 
   const uint16_t* v16 = reinterpret_cast<const uint16_t*>(vs);
-  const int pitch = p.pitch[lvl];
-  const int plane = hs * pitch;
-  float* obase = out + p.off[lvl] + (size_t)b * 3 * plane + (size_t)j0 * pitch;
+  typedef typename PyrOut<OUT>::T OT;
+  const int pitch = p.pitch[lvl];                     // OUT 0: floats per row; OUT 1: pixels per row (2 x pair pitch)
+  const long long plane = OUT == 0 ? (long long)hs * pitch : lo_off;
+  OT* obase = out + p.off[lvl] + (size_t)b * (OUT == 0 ? 3 : 1) * hs * pitch + (size_t)j0 * pitch;
   const bool fast = p.fastdiv[lvl] != 0;
   for (int jj = 0; jj < nrows; ++jj) {
     const int kh = __ldg(ty1 + jj) - __ldg(ty0 + jj);
@@ -230,22 +254,20 @@ __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restr
     const uint16_t* vr = v16 + jj * (4 * nw);
     if (p.kwmin[lvl] > 0) {
       const int2* twf = reinterpret_cast<const int2*>(t) + tid;
-      float* of = obase + jj * pitch + tid;
+      OT* of = obase + jj * pitch + tid;
       switch (p.kwmin[lvl]) {
-        case 1: hpass_fixed<1>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
-        case 2: hpass_fixed<2>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
-        case 3: hpass_fixed<3>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
-        case 4: hpass_fixed<4>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
-        default: hpass_fixed<5>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
+        case 1: hpass_fixed<1, OUT>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
+        case 2: hpass_fixed<2, OUT>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
+        case 3: hpass_fixed<3, OUT>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
+        case 4: hpass_fixed<4, OUT>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
+        default: hpass_fixed<5, OUT>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
       }
       continue;
     }
     // per-thread running pointers: one 64-bit add per plane and step instead of rebuilding three addresses per pixel
-    float* o0 = obase + jj * pitch + tid;
-    float* o1 = o0 + plane;
-    float* o2 = o1 + plane;
+    OT* o0 = obase + jj * pitch + tid;
     const int2* tw = reinterpret_cast<const int2*>(t) + tid;      // {x0 | kw << 16, bits of RN(1 / kw)}
-    for (int i = tid; i < ws; i += 256, o0 += 256, o1 += 256, o2 += 256, tw += 256) {
+    for (int i = tid; i < ws; i += 256, o0 += 256, tw += 256) {
       const int2 e = __ldg(tw);
       const int xw = e.x;
       const float rkw = __int_as_float(e.y);
@@ -264,9 +286,8 @@ __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restr
         a1 = __fdiv_rn(__fdiv_rn((float)s1, fkh), fkw);
         a2 = __fdiv_rn(__fdiv_rn((float)s2, fkh), fkw);
       }
-      *o0 = __fmul_rn(__fsub_rn(a0, 127.5f), 0.0078125f);
-      *o1 = __fmul_rn(__fsub_rn(a1, 127.5f), 0.0078125f);
-      *o2 = __fmul_rn(__fsub_rn(a2, 127.5f), 0.0078125f);
+      PyrOut<OUT>::store(o0, plane, __fmul_rn(__fsub_rn(a0, 127.5f), 0.0078125f), __fmul_rn(__fsub_rn(a1, 127.5f), 0.0078125f),
+                         __fmul_rn(__fsub_rn(a2, 127.5f), 0.0078125f));
     }
   }
   // pad columns [ws, pitch) stay untouched: readers clip at ws
@@ -340,9 +361,23 @@ static int build_pyramid_tables(trl_ctx* c, int H, int W, const PyramidGeom& g, 
 
 // `padded`: rows at g.pitch[k] floats and levels at g.off[k]*B (the cascade's internal layout, 16-byte aligned rows
 // for P-Net's cp.async staging); otherwise the compact layout of the trl_pyramid stage entry point.
+static int launch_pyramid_any(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const PyramidGeom& g, float* d_out,
+                              bool padded, uint4* d_hi, uint4* d_lo, cudaStream_t s);
+
 int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const PyramidGeom& g, float* d_out,
                    bool padded, cudaStream_t s) {
+  return launch_pyramid_any(c, d_frames, B, H, W, g, d_out, padded, nullptr, nullptr, s);
+}
+
+int launch_pyramid_pairs(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const PyramidGeom& g, uint4* d_hi, uint4* d_lo,
+                         cudaStream_t s) {
+  return launch_pyramid_any(c, d_frames, B, H, W, g, nullptr, true, d_hi, d_lo, s);
+}
+
+static int launch_pyramid_any(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, const PyramidGeom& g, float* d_out,
+                              bool padded, uint4* d_hi, uint4* d_lo, cudaStream_t s) {
   if (g.n == 0 || B == 0) return TRL_OK;
+  const bool pairs = d_hi != nullptr;
   int rc = build_pyramid_tables(c, H, W, g, s);
   if (rc != TRL_OK) return rc;
   if ((reinterpret_cast<uintptr_t>(d_frames) & 3) != 0) TRL_FAIL(c, TRL_E_INVALID, "frames pointer must be 4-byte aligned");
@@ -356,8 +391,8 @@ int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, con
     if (kh > PYR_MAX_KH) TRL_FAIL(c, TRL_E_INVALID, "pyramid window of %d rows exceeds %d (frame %dx%d)", kh, PYR_MAX_KH, H, W);
     p.hs[k] = g.hs[k];
     p.ws[k] = g.ws[k];
-    p.pitch[k] = padded ? g.pitch[k] : g.ws[k];
-    p.off[k] = padded ? g.off[k] * B : off * B;
+    p.pitch[k] = pairs ? 2 * g.pitch2[k] : padded ? g.pitch[k] : g.ws[k];
+    p.off[k] = pairs ? 2 * g.off2[k] * B : padded ? g.off[k] * B : off * B;
     off += 3LL * g.hs[k] * g.ws[k];
     p.tab_off[k] = c->pyr_tab_off[k];
     p.fastdiv[k] = c->pyr_fastdiv[k];
@@ -381,16 +416,25 @@ int launch_pyramid(trl_ctx* c, const uint8_t* d_frames, int B, int H, int W, con
     // kernel's ceiling (a per-context "largest size so far" let a second context with smaller frames lower it under the
     // first one's feet -> invalid-argument launches).  The launch itself still asks only for what this shape needs.
     const int cap = 200 * 1024;
-    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     c->pyr_smem_set = cap;
   }
   dim3 grid(blocks, B);
   const bool rows16 = (3 * W) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 15) == 0;
-  if (rows16) pyramid_sep_kernel<2><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out);
-  else if (aligned) pyramid_sep_kernel<1><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out);
-  else pyramid_sep_kernel<0><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out);
+  if (pairs) {
+    uint2* hi = reinterpret_cast<uint2*>(d_hi);
+    const long long lo_off = reinterpret_cast<uint2*>(d_lo) - hi;
+    if (rows16) pyramid_sep_kernel<2, 1><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, hi, lo_off);
+    else if (aligned) pyramid_sep_kernel<1, 1><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, hi, lo_off);
+    else pyramid_sep_kernel<0, 1><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, hi, lo_off);
+  } else if (rows16) pyramid_sep_kernel<2, 0><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out, 0);
+  else if (aligned) pyramid_sep_kernel<1, 0><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out, 0);
+  else pyramid_sep_kernel<0, 0><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out, 0);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
@@ -814,11 +858,12 @@ int compute_geometry(const trl_config_t& cfg, int H, int W, PyramidGeom* g) {
   g->n = 0;
   g->px_total = 0;
   g->floats_total = 0;
+  g->pairs_total = 0;
   if (H <= 0 || W <= 0 || cfg.min_face_size <= 0) return TRL_E_INVALID;
   const double m = 12.0 / (double)cfg.min_face_size;
   double minl = (double)(H < W ? H : W) * m;
   double scale_i = m;
-  long long off = 0;
+  long long off = 0, off2 = 0;
   while (minl >= 12.0) {
     if (g->n >= TRL_MAX_SCALES) return TRL_E_INVALID;
     const int k = g->n++;
@@ -831,6 +876,10 @@ int compute_geometry(const trl_config_t& cfg, int H, int W, PyramidGeom* g) {
     g->pitch[k] = (g->ws[k] + 3) & ~3;               // rows padded to 16 bytes (internal cascade layout)
     g->off[k] = off;
     off += 3LL * g->hs[k] * g->pitch[k];
+    g->pitch2[k] = (g->ws[k] + 1) / 2;
+    g->off2[k] = off2;
+    off2 += (long long)g->hs[k] * g->pitch2[k];
+    g->pairs_total = off2;
     g->px_total += (long long)g->hs[k] * g->ws[k];
     g->floats_total = off;
     scale_i = scale_i * cfg.factor;

@@ -75,7 +75,7 @@ class Analyzer:
             facenet_impl = int(os.environ.get("TRUELY_FACENET_IMPL", "0"))
         cfg.facenet_impl = facenet_impl
         if pnet_precision is None:
-            pnet_precision = int(os.environ.get("TRUELY_PNET_PRECISION", "0"))
+            pnet_precision = int(os.environ.get("TRUELY_PNET_PRECISION", "3"))
         cfg.pnet_precision = pnet_precision
         cfg.mode = 0 if mode == "reference" else 1
         cfg.margin = margin
