@@ -586,7 +586,8 @@ int launch_pnet2(trl_ctx* c, const uint4* d_pyr_hi, int B, const PyramidGeom& g,
   p.blk_start[g.n] = blocks;
   p.blocks = blocks; p.n_frames = B;
   if (blocks == 0) return TRL_OK;
-  p.logit_lo = logf(thr_lo / (1.f - thr_lo));
+  // prob >= thr_lo  <=>  logit difference >= log(thr_lo / (1 - thr_lo)); thresholds at or below the margin screen every cell
+  p.logit_lo = thr_lo <= 0.f ? -INFINITY : thr_lo >= 1.f ? INFINITY : logf(thr_lo / (1.f - thr_lo));
   p.screen = d_screen; p.screen_cnt = d_screen_cnt; p.screen_cap = screen_cap; p.capflag = c->d_cap;
   const float* e = c->h_pnet2_epi;
   memcpy(p.b1, e + 0, 40); memcpy(p.a1, e + 10, 40);
