@@ -140,6 +140,15 @@ int main() {
   struct T { uint32_t lbo, sbo; int N; };
   const T ts[] = {{2048, 128, 16}, {2048, 128, 32}, {2048, 128, 64}, {16, 128, 16}, {16, 128, 32}, {16, 1056, 32}, {16, 1056, 64},
                   {16, 2112, 32}, {2048, 128, 128}, {2048, 128, 256}, {3072 - 32, 128, 16}};
+  // dependent accumulation: consecutive MMAs into the SAME accumulator against round-robin over 2 / 4 / 8 accumulators
+  for (int nd = 1; nd <= 8; nd *= 2)
+    for (int N : {16, 32, 64}) {
+      probe<<<1, 128, smem>>>(d_out, d_cyc, 1, 0, 0, 16, 1056, N, 1024, nd);
+      CK(cudaDeviceSynchronize());
+      long long cyc;
+      CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+      printf("chain  M=128 N=%3d K=16 accumulators in rotation %d : %.1f cycles per MMA\n", N, nd, (double)cyc / 1024);
+    }
   for (const T& t : ts) {
     const int n_mma = 1024, ndst = t.N >= 256 ? 2 : 4;
     probe<<<1, 128, smem>>>(d_out, d_cyc, 1, 0, 0, t.lbo, t.sbo, t.N, n_mma, ndst);

@@ -101,6 +101,7 @@ void trl_destroy(trl_ctx_t* c) {
   if (c->d_pnet_packed) cudaFree(c->d_pnet_packed);
   if (c->d_pnet_refine) cudaFree(c->d_pnet_refine);
   if (c->d_pnet2_packed) cudaFree(c->d_pnet2_packed);
+  if (c->d_pnet2_tiles) cudaFree(c->d_pnet2_tiles);
   if (c->d_rnet) cudaFree(c->d_rnet);
   if (c->d_onet) cudaFree(c->d_onet);
   if (c->d_nms_tmp) cudaFree(c->d_nms_tmp);

@@ -157,6 +157,8 @@ struct trl_ctx {
   float* d_pnet_packed = nullptr;   // smem image of P-Net (pnet.cu layout)
   float h_pnet2_epi[152] = {0};     // pnet2.cu epilogue constants (biases, slopes, conv4_1 logit-difference weights)
   float* d_pnet_refine = nullptr;   // fp32 weight image of the exact per-cell kernel (pnet_refine.cu)
+  void* d_pnet2_tiles = nullptr;    // pnet2.cu: tile table of the current frame geometry (int4 per tile of one frame)
+  int pnet2_tiles_n = 0; long long pnet2_tiles_key = 0;
   uint32_t* d_pnet2_packed = nullptr;   // smem image of the all-tensor-pipe screening P-Net (pnet2.cu)
   float* d_rnet = nullptr;          // packed R-Net (mtcnn_ro.cu layout)
   float* d_onet = nullptr;

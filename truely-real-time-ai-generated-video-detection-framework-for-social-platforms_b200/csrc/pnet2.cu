@@ -34,6 +34,7 @@
 // a commit that was issued after the last reader of the plane it overwrites).
 // TMEM (512 columns): conv1 ring 2 x 64, conv2 4 x 32, conv3 4 x 64.
 #include <cuda.h>
+#include <algorithm>
 
 #include "common.cuh"
 #include <cuda_fp16.h>
@@ -65,12 +66,15 @@ constexpr int P1A_OFF = IN_OFF + 2 * IN_STRIDE;
 constexpr int P1B_OFF = P1A_OFF + PL_BYTES;
 constexpr int C0_OFF = P1B_OFF + PL_BYTES;
 constexpr int C1_OFF = C0_OFF + PL_BYTES;
-constexpr int SMEM_BYTES = C1_OFF + PL_BYTES;
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr int TILES_OFF = C1_OFF + PL_BYTES;         // tile table: 16 bytes per tile of a frame
+constexpr int SMEM_BYTES = TILES_OFF;                // + 16 * tiles per frame at launch
+constexpr int SMEM_CAP = 227 * 1024 - 1024;          // dynamic shared memory ceiling (the barriers are static shared memory)
+constexpr int MAX_TILES_PER_FRAME = (SMEM_CAP - SMEM_BYTES) / 16;
+static_assert(SMEM_BYTES <= 200 * 1024, "shared memory budget");
 
 constexpr int TMEM_COLS = 512;
 constexpr int ACC1_COL = 0, ACC2_COL = 128, ACC3_COL = 256;
-constexpr int W_TMA = 0, W_MMA = 1, W_E1 = 4, W_E2 = 8, W_E3 = 12, N_WARPS = 20;
+constexpr int W_TMA = 0, W_MMA = 1, W_E1 = 4, W_E2 = 12, W_E3 = 16, N_WARPS = 20;
 constexpr int NTHREADS = 32 * N_WARPS;
 constexpr float ACT_MAX = 60000.f;          // fp16 operand range guard
 
@@ -85,7 +89,7 @@ struct Params {
   int n_levels;
   int blocks;          // tiles per frame (all levels)
   int n_frames;
-  int blk_start[TRL_MAX_SCALES + 1];
+  const int4* tiles;   // [blocks] tile table of one frame
   Level lv[TRL_MAX_SCALES];
   float logit_lo;      // screen: logit(thr - margin)
   ScreenEntry* screen;
@@ -99,6 +103,14 @@ struct Params {
   int conv1_monotone;
 };
 
+#ifdef PNET_TIMING
+// cycles summed over CTAs: [0] MMA thread total, [1..6] its waits (in_full, p1_ready, acc2_empty, acc1_empty, c2_ready, acc3_empty),
+// [7] tiles, [8] E1 warp 0 wait, [9] E1 busy, [10] E2 wait, [11] E2 busy, [12] E3 wait, [13] E3 busy, [14] TMA wait
+__device__ unsigned long long g_pnet2_phase[24];   // [16] conv2 issue, [17] conv1 issue, [18] conv3 issue (MMA thread, waits excluded)
+#define P2T(...) __VA_ARGS__
+#else
+#define P2T(...)
+#endif
 __device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : v * a; }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ bool elect_one() {
@@ -117,6 +129,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+#ifdef PNET_TIMING
+__device__ long long g_dummy_sink;
+#define umma_commit_t(bar, acc) do { const long long _t = clock64(); umma_commit(bar); acc += clock64() - _t; } while (0)
+#else
+#define umma_commit_t(bar, acc) umma_commit(bar)
+#endif
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -136,6 +154,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();        // ~2 s: a lost arrival must not hang the device
   }
 }
+#ifdef PNET_TIMING
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+#else
+#define mbar_wait_t(bar, parity, acc) mbar_wait(bar, parity)
+#endif
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -160,19 +187,26 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// tile id -> (frame, level, origin, live extent); uniform per call
+// Tiles: the per-frame tile table (level, origin, live extent of every tile of every level; built on the host, copied to shared
+// memory once per CTA) + a cursor (frame, tile-in-frame) that advances by the grid size -- no division or level search per tile
+// (the MMA-issue thread spent 600 cycles per decode on them).
 struct TileRef { int b, lvl, oy0, ox0, rows, cols; };
-__device__ __forceinline__ TileRef decode_tile(const Params& p, int id) {
+struct TileCursor { int b, blk; };
+__device__ __forceinline__ TileCursor cursor_init(int blocks) {
+  TileCursor c;
+  c.b = (int)blockIdx.x / blocks;
+  c.blk = (int)blockIdx.x - c.b * blocks;
+  return c;
+}
+__device__ __forceinline__ void cursor_next(TileCursor& c, int blocks) {
+  c.blk += (int)gridDim.x;
+  while (c.blk >= blocks) { c.blk -= blocks; ++c.b; }
+}
+__device__ __forceinline__ TileRef tile_at(const int4* tile_s, const TileCursor& c) {
+  const int4 rec = tile_s[c.blk];            // x = level | rows << 8 | cols << 16, y = oy0, z = ox0
   TileRef r;
-  r.b = id / p.blocks;
-  const int blk = id - r.b * p.blocks;
-  int lvl = 0;
-  while (lvl + 1 < p.n_levels && blk >= p.blk_start[lvl + 1]) ++lvl;
-  const int tile = blk - p.blk_start[lvl];
-  const int ty = tile / p.lv[lvl].tiles_x;
-  r.lvl = lvl; r.oy0 = ty * T; r.ox0 = (tile - ty * p.lv[lvl].tiles_x) * T;
-  r.rows = min(T, p.lv[lvl].oh - r.oy0);
-  r.cols = min(T, p.lv[lvl].ow - r.ox0);
+  r.b = c.b; r.lvl = rec.x & 0xFF; r.rows = (rec.x >> 8) & 0xFF; r.cols = (rec.x >> 16) & 0xFF;
+  r.oy0 = rec.y; r.ox0 = rec.z;
   return r;
 }
 // live 8-column groups of the three layers and conv1 row blocks (pooled rows in blocks of 16) of a tile
@@ -190,11 +224,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   float act_max = 0.f;
+  P2T(long long tcm = 0; long long tdec = 0; long long ti2 = 0; long long ti1 = 0; long long ti3 = 0; long long tq = 0; long long tw0 = 0; long long tw1 = 0; long long tw2 = 0; long long tw3 = 0; long long tw4 = 0; long long tw5 = 0; long long tstart = clock64();)
 
   // zero the operand planes once (slack rows / pad halves are read by dead accumulator rows and must stay finite), load weights
-  for (int i = tid; i < (SMEM_BYTES - IN_OFF) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + IN_OFF)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < (TILES_OFF - IN_OFF) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + IN_OFF)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < W_BYTES / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wpacked) + i);
+  const int4* tile_s = reinterpret_cast<const int4*>(smem + TILES_OFF);
+  for (int i = tid; i < p.blocks; i += NTHREADS) reinterpret_cast<int4*>(smem + TILES_OFF)[i] = __ldg(p.tiles + i);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -204,7 +241,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
         mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 128);
       }
       for (int i = 0; i < 4; ++i) { mbar_init(&acc2_full[i], 1); mbar_init(&acc3_full[i], 1); }
-      mbar_init(&p1_ready, 128); mbar_init(&acc2_empty, 128); mbar_init(&c2_ready, 128); mbar_init(&acc3_empty, 256);
+      mbar_init(&p1_ready, 256); mbar_init(&acc2_empty, 128); mbar_init(&c2_ready, 128); mbar_init(&acc3_empty, 128);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -219,10 +256,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
   if (warp == W_TMA) {
     // =================================================================== TMA producer
     if (elect_one()) {
-      for (int i = 0; i < n_my; ++i) {
-        const TileRef tr = decode_tile(p, blockIdx.x + i * gridDim.x);
+      TileCursor cur = cursor_init(p.blocks);
+      for (int i = 0; i < n_my; ++i, cursor_next(cur, p.blocks)) {
+        const TileRef tr = tile_at(tile_s, cur);
         const int buf = i & 1;
-        if (i >= 2) mbar_wait(&in_empty[buf], ((i >> 1) - 1) & 1);
+        if (i >= 2) mbar_wait_t(&in_empty[buf], ((i >> 1) - 1) & 1, tw0);
         const uint32_t bar = smem_u32(&in_full[buf]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)IN_BYTES) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -233,8 +271,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
     __syncwarp();
   } else if (warp == W_MMA) {
     // =================================================================== MMA issue (one elected thread)
-    const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
-    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    // This thread is the kernel's critical path: ~105 MMAs, 17 commits and a dozen barrier waits per tile from ONE thread.  The
+    // first version spent 1300 instructions per tile here (descriptors rebuilt in vector registers and moved to uniform ones
+    // with R2UR for every group; 600-cycle tile decodes) and took 9.5 k cycles per tile for 4.5 k cycles of tensor work.  Now
+    // everything an MMA needs is a compile-time offset from a descriptor template that the compiler can keep in the uniform
+    // datapath: the shared-memory window base is uniform by construction, the TMEM base is 0 because the CTA owns all 512
+    // columns (checked once), and the group loops are fully unrolled.
+    const uint32_t sbase = smem_u32(smem);
+    constexpr uint32_t tm = 0u;
+    if (tmem != 0u) __trap();
     constexpr uint32_t ID16 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);      // f32 accumulate, f16 x f16, K-major, M = 128
     constexpr uint32_t ID32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t ID64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
@@ -250,18 +295,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
       const uint64_t b2b_t = umma_desc(sbase + W2_OFF + 2u * W2_ROWS * 16u, W2_ROWS * 16u, 128u);
       const uint64_t b3_t = umma_desc(sbase + W3_OFF, W3_ROWS * 16u, 128u);
       uint32_t u1 = 0;                                   // conv1 accumulator ring use count
+      TileCursor cur = cursor_init(p.blocks);
+      int g_cur = 0, g_prev = 0;                         // live groups of tile i / i - 1: nq1 | nrb << 4 | nq2 << 8 | nq3 << 12
 #pragma unroll 1
       for (int i = 0; i <= n_my; ++i) {
+        g_prev = g_cur;
+        if (i < n_my) {
+          const TileRef t = tile_at(tile_s, cur);
+          cursor_next(cur, p.blocks);
+          g_cur = ncg1(t) | (nrb1(t) << 4) | (ncg2(t) << 8) | (ncg3(t) << 12);
+        }
+        const bool do1 = i < n_my, do3 = i >= 1;
         // ---- conv2 of tile i - 1: per 8-column group one M tile of 16 row pairs; row taps t = 1, 0, 2, 3, two MMAs each.
         // B rows are blocks dy2 | dy1 | dy0; tap t multiplies [dy = t | dy = t - 1] (taps 0 and 3: one block, half N, one half of D)
-        if (i >= 1) {
+        if (do3) {
           const int k = i - 1;
-          const TileRef tr = decode_tile(p, blockIdx.x + k * gridDim.x);
-          mbar_wait(&p1_ready, k & 1);
-          if (k >= 1) mbar_wait(&acc2_empty, (k - 1) & 1);
+          mbar_wait_t(&p1_ready, k & 1, tw1);
+          if (k >= 1) mbar_wait_t(&acc2_empty, (k - 1) & 1, tw2);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int nq = ncg2(tr);
-#pragma unroll 1
+          const int nq = (g_prev >> 8) & 15;
+          P2T(tq = clock64();)
+#pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (q < nq) {
               const uint32_t d = tm + ACC2_COL + 32u * q;
@@ -278,41 +332,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
             }
             umma_commit(smem_u32(&acc2_full[q]));          // dead groups too: keeps the barrier phases aligned with k
           }
+          P2T(ti2 += clock64() - tq;)
         }
-        // ---- conv1 of tile i: M tile = 8 pooled columns x 16 pooled rows; input-row taps t = 1, 0, 2, 3
-        if (i < n_my) {
-          const TileRef tr = decode_tile(p, blockIdx.x + i * gridDim.x);
-          const int buf = i & 1;
-          mbar_wait(&in_full[buf], (i >> 1) & 1);
-          const int nq = ncg1(tr), nrb = nrb1(tr);
-#pragma unroll 1
-          for (int rb = 0; rb < nrb; ++rb)
-#pragma unroll 1
-            for (int q = 0; q < nq; ++q, ++u1) {
-              const uint32_t slot = u1 & 1u;
-              if (u1 >= 2) mbar_wait(&acc1_empty[slot], ((u1 >> 1) - 1) & 1);
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t d = tm + ACC1_COL + 64u * slot;
-              const uint64_t a = a1_t + (uint64_t)(buf * (IN_STRIDE / 16) + 32 * rb * (IN_ROWB / 16) + 8 * q);
-              umma_f16(d, a + 1 * (IN_ROWB / 16), b1_t + 32, ID64, 0u);
-              umma_f16(d, a, b1_t + 64, ID32, 1u);
-              umma_f16(d, a + 2 * (IN_ROWB / 16), b1_t, ID64, 1u);
-              umma_f16(d + 32u, a + 3 * (IN_ROWB / 16), b1_t, ID32, 1u);
-              umma_commit(smem_u32(&acc1_full[slot]));
-            }
-          umma_commit(smem_u32(&in_empty[buf]));           // every MMA that reads this input buffer has completed
-        }
-        // ---- conv3 of tile i - 1: per 8-column group one M tile of 16 row pairs; row taps x 3 kx taps
-        if (i >= 1) {
-          const int k = i - 1;
-          const TileRef tr = decode_tile(p, blockIdx.x + k * gridDim.x);
-          mbar_wait(&c2_ready, k & 1);
-          if (k >= 1) mbar_wait(&acc3_empty, (k - 1) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int nq = ncg3(tr);
-#pragma unroll 1
-          for (int q = 0; q < 4; ++q) {
-            if (q < nq) {
+        // ---- conv1 of tile i (M tile = 8 pooled columns x 16 pooled rows; input-row taps t = 1, 0, 2, 3) interleaved with
+        // conv3 of tile i - 1 (per 8-column group one M tile of 16 row pairs; 4 row taps x 3 kx taps).  conv1 advances only as
+        // fast as its epilogue frees the two accumulator slots; the conv3 groups between its M tiles keep the tensor pipe busy
+        // meanwhile and give the conv2 epilogue of tile i - 1 time to finish before its output is needed.
+        const int buf = i & 1;
+        const int nq1 = do1 ? (g_cur & 15) : 0, nrb = (g_cur >> 4) & 15, n3 = (g_prev >> 12) & 15;
+        const uint64_t a1_b = a1_t + (uint64_t)(buf * (IN_STRIDE / 16));
+        if (do1) mbar_wait_t(&in_full[buf], (i >> 1) & 1, tw0);
+        auto conv1_tile = [&](int rb, int q) {             // called with literals: the operand offsets fold to constants
+          if (rb < nrb && q < nq1) {
+            const uint32_t slot = u1 & 1u;
+            if (u1 >= 2) mbar_wait_t(&acc1_empty[slot], ((u1 >> 1) - 1) & 1, tw3);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            P2T(tq = clock64();)
+            const uint32_t d = tm + ACC1_COL + 64u * slot;
+            const uint64_t a = a1_b + (uint64_t)(32 * rb * (IN_ROWB / 16) + 8 * q);
+            umma_f16(d, a + 1 * (IN_ROWB / 16), b1_t + 32, ID64, 0u);
+            umma_f16(d, a, b1_t + 64, ID32, 1u);
+            umma_f16(d, a + 2 * (IN_ROWB / 16), b1_t, ID64, 1u);
+            umma_f16(d + 32u, a + 3 * (IN_ROWB / 16), b1_t, ID32, 1u);
+            umma_commit(smem_u32(&acc1_full[slot]));
+            ++u1;
+            P2T(ti1 += clock64() - tq;)
+          }
+        };
+        auto conv3_group = [&](int q) {
+          if (do3) {
+            if (q < n3) {
+              P2T(tq = clock64();)
               const uint32_t d = tm + ACC3_COL + 64u * q;
               const uint64_t aq = a3_t + (uint64_t)(8 * q);
 #pragma unroll
@@ -327,27 +377,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
                 umma_f16(d, aq + (2 * PL_PITCH + kx), bk, ID64, 1u);
                 umma_f16(d + 32u, aq + (3 * PL_PITCH + kx), bk, ID32, 1u);
               }
+              P2T(ti3 += clock64() - tq;)
             }
-            umma_commit(smem_u32(&acc3_full[q]));
+            umma_commit(smem_u32(&acc3_full[q]));          // dead groups too: keeps the barrier phases aligned with the tile count
           }
+        };
+        conv1_tile(0, 0); conv1_tile(0, 1); conv1_tile(0, 2); conv1_tile(0, 3);
+        if (do3) {
+          mbar_wait_t(&c2_ready, (i - 1) & 1, tw4);
+          if (i >= 2) mbar_wait_t(&acc3_empty, (i - 2) & 1, tw5);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
+        conv3_group(0);
+        conv1_tile(1, 0); conv1_tile(1, 1);
+        conv3_group(1);
+        conv1_tile(1, 2); conv1_tile(1, 3);
+        conv3_group(2);
+        conv3_group(3);
+        if (do1) umma_commit(smem_u32(&in_empty[buf]));     // every MMA that reads this input buffer has completed
       }
+      P2T(atomicAdd(&g_pnet2_phase[0], (unsigned long long)(clock64() - tstart)); atomicAdd(&g_pnet2_phase[1], (unsigned long long)tw0);
+          atomicAdd(&g_pnet2_phase[2], (unsigned long long)tw1); atomicAdd(&g_pnet2_phase[3], (unsigned long long)tw2);
+          atomicAdd(&g_pnet2_phase[4], (unsigned long long)tw3); atomicAdd(&g_pnet2_phase[5], (unsigned long long)tw4);
+          atomicAdd(&g_pnet2_phase[6], (unsigned long long)tw5); atomicAdd(&g_pnet2_phase[7], (unsigned long long)n_my);
+          atomicAdd(&g_pnet2_phase[16], (unsigned long long)ti2); atomicAdd(&g_pnet2_phase[17], (unsigned long long)ti1); atomicAdd(&g_pnet2_phase[18], (unsigned long long)ti3);
+          atomicAdd(&g_pnet2_phase[19], (unsigned long long)tcm); atomicAdd(&g_pnet2_phase[20], (unsigned long long)tdec);)
     }
     __syncwarp();
   } else if (warp >= W_E1 && warp < W_E2) {
     // =================================================================== conv1 epilogue: pool, bias, PReLU -> p1 planes
-    const int lg = warp & 3;
+    // two sets of four warps; set s serves accumulator slot s (every second M tile), so two M tiles are in flight
+    const int lg = warp & 3, set = (warp - W_E1) >> 2;
     const int g = 4 * lg + (lane >> 3), ci = lane & 7;       // accumulator row = 8 g + ci: pooled row g of the block, column ci of the group
     uint32_t u1 = 0;
-    for (int k = 0; k < n_my; ++k) {
-      const TileRef tr = decode_tile(p, blockIdx.x + k * gridDim.x);
+    TileCursor cur = cursor_init(p.blocks);
+    for (int k = 0; k < n_my; ++k, cursor_next(cur, p.blocks)) {
+      const TileRef tr = tile_at(tile_s, cur);
       const Level& Lv = p.lv[tr.lvl];
       const int c1h = Lv.hs - 2, c1w = Lv.ws - 2;
       const int nq = ncg1(tr), nrb = nrb1(tr);
       for (int rb = 0; rb < nrb; ++rb)
         for (int q = 0; q < nq; ++q, ++u1) {
           const uint32_t slot = u1 & 1u;
-          mbar_wait(&acc1_full[slot], (u1 >> 1) & 1);
+          if ((int)slot != set) continue;
+          mbar_wait_t(&acc1_full[slot], (u1 >> 1) & 1, tw0);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + ACC1_COL + 64u * slot;
           float v[4][10];                     // [2 * (conv row parity) + (conv x parity)][channel]
@@ -388,6 +461,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
           if (c >= 1) side[-4 + 1] = w89;
           if (c >= 2) side[-8 + 2] = w89;
         }
+      // The other set may own the tile's last M tile: wait for that one too before arriving, so that no warp can arrive for
+      // the next tile before every warp has arrived for this one (conv1 of the next tile is issued behind conv2 of this one,
+      // which waits for p1_ready).
+      mbar_wait_t(&acc1_full[(u1 - 1) & 1u], ((u1 - 1) >> 1) & 1, tw0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // p1 planes -> visible to the UMMA proxy
       mbar_arrive(&p1_ready);
     }
@@ -395,11 +472,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
     // =================================================================== conv2 epilogue: bias, PReLU -> c2 planes
     const int lg = warp & 3;
     const int g = 4 * lg + (lane >> 3), ci = lane & 7;       // accumulator row: row pair g (rows 2g, 2g + 1), column ci of the group
-    for (int k = 0; k < n_my; ++k) {
-      const TileRef tr = decode_tile(p, blockIdx.x + k * gridDim.x);
+    TileCursor cur = cursor_init(p.blocks);
+    for (int k = 0; k < n_my; ++k, cursor_next(cur, p.blocks)) {
+      const TileRef tr = tile_at(tile_s, cur);
       const int nq = ncg2(tr);
       for (int q = 0; q < nq; ++q) {
-        mbar_wait(&acc2_full[q], k & 1);
+        mbar_wait_t(&acc2_full[q], k & 1, tw0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + ACC2_COL + 32u * q;
         float v[2][16];
@@ -427,30 +505,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
     }
   } else if (warp >= W_E3) {
     // =================================================================== conv3 epilogue: bias, PReLU, conv4_1 logit difference -> screen
-    const int lg = warp & 3, half = (warp - W_E3) >> 2;
+    const int lg = warp & 3;
     const int g = 4 * lg + (lane >> 3), ci = lane & 7;
-    for (int k = 0; k < n_my; ++k) {
-      const TileRef tr = decode_tile(p, blockIdx.x + k * gridDim.x);
+    TileCursor cur = cursor_init(p.blocks);
+    for (int k = 0; k < n_my; ++k, cursor_next(cur, p.blocks)) {
+      const TileRef tr = tile_at(tile_s, cur);
       const Level& Lv = p.lv[tr.lvl];
       const int nq = ncg3(tr);
-      for (int q = half; q < 4; q += 2) {
+      for (int q = 0; q < 4; ++q) {
         // dead groups are waited for as well (their barrier is committed empty): a warp without work must not run ahead and
         // arrive on acc3_empty for the next tile before the others have arrived for this one
-        mbar_wait(&acc3_full[q], k & 1);
+        mbar_wait_t(&acc3_full[q], k & 1, tw0);
         if (q >= nq) continue;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + ACC3_COL + 64u * q;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           float dsum = p.db;
+          float v[2][16];
+          tmem_ld16(taddr + 32 * r, v[0]); tmem_ld16(taddr + 32 * r + 16, v[1]);
+          tmem_ld_wait();
 #pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + 32 * r + c0, v);
-            tmem_ld_wait();
+          for (int c0 = 0; c0 < 32; c0 += 16)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dsum = fmaf(prelu(v[j] + p.b3[c0 + j], p.a3[c0 + j]), p.dw[c0 + j], dsum);
-          }
+            for (int j = 0; j < 16; ++j) dsum = fmaf(prelu(v[c0 >> 4][j] + p.b3[c0 + j], p.a3[c0 + j]), p.dw[c0 + j], dsum);
           const int row = 2 * g + r, col = 8 * q + ci;
           const int oy = tr.oy0 + row, ox = tr.ox0 + col;
           const bool live = row < tr.rows && col < tr.cols;
@@ -477,6 +555,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
       mbar_arrive(&acc3_empty);
     }
   }
+  P2T(if (lane == 0 && warp != W_MMA) {
+        const unsigned long long tot = (unsigned long long)(clock64() - tstart), w = (unsigned long long)tw0;
+        const int slot = warp == W_E1 ? 8 : warp == W_E2 ? 10 : warp == W_E3 ? 12 : warp == W_TMA ? 14 : -1;
+        if (slot >= 0) { atomicAdd(&g_pnet2_phase[slot], w); if (slot != 14) atomicAdd(&g_pnet2_phase[slot + 1], tot - w); }
+      })
   if (!(act_max <= ACT_MAX) && p.capflag) {      // also catches NaN
     p.capflag->overflow = 1; p.capflag->stage = 5; p.capflag->frame = 0;
     p.capflag->count = 0; p.capflag->capacity = (int)ACT_MAX;
@@ -487,6 +570,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
 }
 
 }  // namespace pnet2
+#ifdef PNET_TIMING
+extern "C" void trl_debug_pnet2_timing(unsigned long long* out) {
+  cudaMemcpyFromSymbol(out, pnet2::g_pnet2_phase, sizeof(unsigned long long) * 24);
+  unsigned long long z[24] = {0};
+  cudaMemcpyToSymbol(pnet2::g_pnet2_phase, z, sizeof(z));
+}
+#endif
 
 // ---- host side
 
@@ -553,7 +643,7 @@ int pnet2_pack_weights(trl_ctx* c, const float* h, size_t len) {
   memcpy(e + 52, b3, 128); memcpy(e + 84, a3, 128);
   for (int ci = 0; ci < 32; ++ci) e[116 + ci] = w41[32 + ci] - w41[ci];
   e[148] = b41[1] - b41[0];
-  TRL_CUDA(c, cudaFuncSetAttribute(pnet2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  TRL_CUDA(c, cudaFuncSetAttribute(pnet2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
   return TRL_OK;
 }
 
@@ -568,6 +658,7 @@ int launch_pnet2(trl_ctx* c, const uint4* d_pyr_hi, int B, const PyramidGeom& g,
   p.n_levels = g.n;
   int blocks = 0;
   long long logit_off = 0;
+  std::vector<int4> table;
   for (int k = 0; k < g.n; ++k) {
     Level& L = p.lv[k];
     L.hs = g.hs[k]; L.ws = g.ws[k]; L.oh = g.oh[k]; L.ow = g.ow[k];
@@ -575,7 +666,11 @@ int launch_pnet2(trl_ctx* c, const uint4* d_pyr_hi, int B, const PyramidGeom& g,
     L.tiles = (L.oh > 0 && L.ow > 0) ? L.tiles_x * ceil_div(L.oh, T) : 0;
     L.logit = d_logit ? d_logit + logit_off : nullptr;
     if (L.oh > 0 && L.ow > 0) logit_off += (long long)B * L.oh * L.ow;
-    p.blk_start[k] = blocks;
+    for (int t = 0; t < L.tiles; ++t) {
+      const int ty = t / L.tiles_x, tx = t - ty * L.tiles_x;
+      const int rows = std::min(T, L.oh - ty * T), cols = std::min(T, L.ow - tx * T);
+      table.push_back(make_int4(k | (rows << 8) | (cols << 16), ty * T, tx * T, 0));
+    }
     blocks += L.tiles;
     const unsigned long long dims[3] = {2ull * L.ws, (unsigned long long)L.hs, (unsigned long long)B};
     const unsigned long long strides[2] = {(unsigned long long)g.pitch2[k] * 16, (unsigned long long)L.hs * g.pitch2[k] * 16};
@@ -583,9 +678,18 @@ int launch_pnet2(trl_ctx* c, const uint4* d_pyr_hi, int B, const PyramidGeom& g,
     int rc = tma_encode_tiled_f32(c, &p.tmap[k], d_pyr_hi + g.off2[k] * B, 3, dims, strides, box);
     if (rc != TRL_OK) return rc;
   }
-  p.blk_start[g.n] = blocks;
   p.blocks = blocks; p.n_frames = B;
   if (blocks == 0) return TRL_OK;
+  if (blocks > MAX_TILES_PER_FRAME) TRL_FAIL(c, TRL_E_INVALID, "frame has %d P-Net tiles, the tile table holds %d", blocks, MAX_TILES_PER_FRAME);
+  // the tile table of this frame geometry lives in the context; it is rebuilt (stream ordered) only when the geometry changes
+  if (c->pnet2_tiles_n != blocks || c->pnet2_tiles_key != ((long long)g.hs[0] << 32 | (unsigned)g.ws[0]) || !c->d_pnet2_tiles) {
+    if (c->d_pnet2_tiles) { TRL_CUDA(c, cudaStreamSynchronize(s)); TRL_CUDA(c, cudaFree(c->d_pnet2_tiles)); c->d_pnet2_tiles = nullptr; }
+    TRL_CUDA(c, cudaMalloc(&c->d_pnet2_tiles, table.size() * sizeof(int4)));
+    TRL_CUDA(c, cudaMemcpy(c->d_pnet2_tiles, table.data(), table.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    c->pnet2_tiles_n = blocks;
+    c->pnet2_tiles_key = ((long long)g.hs[0] << 32 | (unsigned)g.ws[0]);
+  }
+  p.tiles = reinterpret_cast<const int4*>(c->d_pnet2_tiles);
   // prob >= thr_lo  <=>  logit difference >= log(thr_lo / (1 - thr_lo)); thresholds at or below the margin screen every cell
   p.logit_lo = thr_lo <= 0.f ? -INFINITY : thr_lo >= 1.f ? INFINITY : logf(thr_lo / (1.f - thr_lo));
   p.screen = d_screen; p.screen_cnt = d_screen_cnt; p.screen_cap = screen_cap; p.capflag = c->d_cap;
@@ -599,7 +703,7 @@ int launch_pnet2(trl_ctx* c, const uint4* d_pyr_hi, int B, const PyramidGeom& g,
   for (int co = 0; co < 10; ++co) if (!(p.a1[co] >= 0.f)) p.conv1_monotone = 0;
   const long long total = (long long)blocks * B;
   const int grid = (int)(total < c->num_sms ? total : c->num_sms);
-  pnet2_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(c->d_pnet2_packed, p);
+  pnet2_kernel<<<grid, NTHREADS, SMEM_BYTES + blocks * 16, s>>>(c->d_pnet2_packed, p);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
