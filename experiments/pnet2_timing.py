@@ -30,4 +30,4 @@ if __name__ == "__main__":
         print(f"iter {it}: {b[7]} tiles; MMA thread {b[0] / n:.0f} cycles per tile, waiting: in_full {b[1] / n:.0f}, p1_ready {b[2] / n:.0f}, "
               f"acc2_empty {b[3] / n:.0f}, acc1_empty {b[4] / n:.0f}, c2_ready {b[5] / n:.0f}, acc3_empty {b[6] / n:.0f} | "
               f"E1 wait {b[8] / n:.0f} busy {b[9] / n:.0f} | E2 wait {b[10] / n:.0f} busy {b[11] / n:.0f} | "
-              f"E3 wait {b[12] / n:.0f} busy {b[13] / n:.0f} | TMA wait {b[14] / n:.0f} | issue time conv2 {b[16] / n:.0f} conv1 {b[17] / n:.0f} conv3 {b[18] / n:.0f} | commits {b[19] / n:.0f} one decode_tile {b[20] / n:.0f}")
+              f"E3 wait {b[12] / n:.0f} busy {b[13] / n:.0f} | TMA wait {b[14] / n:.0f} | issue time conv2 {b[16] / n:.0f} conv1 {b[17] / n:.0f} conv3 {b[18] / n:.0f} | conv3 thread total {b[21] / n:.0f} conv1 thread total {b[22] / n:.0f}")

@@ -148,6 +148,8 @@ int trl_create(int device, const trl_weights_t* w, const trl_config_t* cfg, trl_
   if (w->h_pnet && (rc = pnet_pack_weights(c, w->h_pnet, w->pnet_len)) != TRL_OK) return fail(rc);
   if (w->h_pnet && (rc = pnet_refine_pack_weights(c, w->h_pnet, w->pnet_len)) != TRL_OK) return fail(rc);
   if (w->h_pnet && (rc = pnet2_pack_weights(c, w->h_pnet, w->pnet_len)) != TRL_OK) return fail(rc);
+  // the fp16 screen needs activations inside fp16's range (bounded on the host from the weights): otherwise the 3-term kernel
+  if (w->h_pnet && c->cfg.pnet_precision >= 2 && !c->pnet2_range_ok) c->cfg.pnet_precision = 0;
   if (w->h_rnet && w->h_onet && (rc = ro_pack_weights(c, w->h_rnet, w->rnet_len, w->h_onet, w->onet_len)) != TRL_OK) return fail(rc);
   if (w->h_facenet && (rc = facenet_create(c, w->h_facenet, w->facenet_len)) != TRL_OK) return fail(rc);
   *out = c;

@@ -79,6 +79,9 @@ __device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& a, flo
 __device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
 }
+__device__ __forceinline__ void fadd2(unsigned long long& d, unsigned long long a) {
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(d) : "l"(a));
+}
 #endif
 
 int tma_encode_tiled_f32(trl_ctx* c, void* map, const void* base, int rank, const unsigned long long* dims,
@@ -155,6 +158,7 @@ struct trl_ctx {
   // weights (device)
   float h_pnet_head[32 * 8 + 8 + 1 + 20] = {0};   // P-Net head / conv3 epilogue constants, copied into the kernel parameters
   float* d_pnet_packed = nullptr;   // smem image of P-Net (pnet.cu layout)
+  int pnet2_range_ok = 0;           // host-side bound of the P-Net activations fits fp16 (pnet2.cu)
   float h_pnet2_epi[152] = {0};     // pnet2.cu epilogue constants (biases, slopes, conv4_1 logit-difference weights)
   float* d_pnet_refine = nullptr;   // fp32 weight image of the exact per-cell kernel (pnet_refine.cu)
   void* d_pnet2_tiles = nullptr;    // pnet2.cu: tile table of the current frame geometry (int4 per tile of one frame)

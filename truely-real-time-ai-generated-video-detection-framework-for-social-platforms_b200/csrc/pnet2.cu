@@ -64,7 +64,8 @@ constexpr int W_BYTES = W3_OFF + 3 * 2 * W3_ROWS * 16;   // 15360
 constexpr int IN_OFF = ((W_BYTES + 127) / 128) * 128;
 constexpr int P1A_OFF = IN_OFF + 2 * IN_STRIDE;
 constexpr int P1B_OFF = P1A_OFF + PL_BYTES;
-constexpr int C0_OFF = P1B_OFF + PL_BYTES;
+constexpr int P1_STRIDE = 2 * PL_BYTES;              // the p1 planes are double buffered (tile k uses buffer k & 1)
+constexpr int C0_OFF = P1A_OFF + 2 * P1_STRIDE;
 constexpr int C1_OFF = C0_OFF + PL_BYTES;
 constexpr int TILES_OFF = C1_OFF + PL_BYTES;         // tile table: 16 bytes per tile of a frame
 constexpr int SMEM_BYTES = TILES_OFF;                // + 16 * tiles per frame at launch
@@ -72,9 +73,21 @@ constexpr int SMEM_CAP = 227 * 1024 - 1024;          // dynamic shared memory ce
 constexpr int MAX_TILES_PER_FRAME = (SMEM_CAP - SMEM_BYTES) / 16;
 static_assert(SMEM_BYTES <= 200 * 1024, "shared memory budget");
 
+constexpr int MAX_TILES_PARAM = 4096;   // tiles per frame the group table in the kernel parameters holds (8 KB)
 constexpr int TMEM_COLS = 512;
 constexpr int ACC1_COL = 0, ACC2_COL = 128, ACC3_COL = 256;
-constexpr int W_TMA = 0, W_MMA = 1, W_E1 = 4, W_E2 = 12, W_E3 = 16, N_WARPS = 20;
+#ifndef PNET2_E1_SETS
+#define PNET2_E1_SETS 2
+#endif
+constexpr int E1_SETS = PNET2_E1_SETS;       // conv1 epilogue sets of four warps (M tiles are dealt round robin)
+#ifndef PNET2_E3_SETS
+#define PNET2_E3_SETS 1
+#endif
+constexpr int E3_SETS = PNET2_E3_SETS;       // conv3 epilogue sets of four warps (set s takes the column groups q = s, s + E3_SETS, ..)
+#ifndef PNET2_BACKOFF
+#define PNET2_BACKOFF 0                     // ns the epilogue warps sleep between barrier polls (they share issue slots with the MMA threads)
+#endif
+constexpr int W_TMA = 0, W_MMA = 1, W_MMA3 = 2, W_E1 = 4, W_E2 = W_E1 + 4 * E1_SETS, W_E3 = W_E2 + 4, N_WARPS = W_E3 + 4 * E3_SETS;
 constexpr int NTHREADS = 32 * N_WARPS;
 constexpr float ACT_MAX = 60000.f;          // fp16 operand range guard
 
@@ -90,15 +103,21 @@ struct Params {
   int blocks;          // tiles per frame (all levels)
   int n_frames;
   const int4* tiles;   // [blocks] tile table of one frame
+  uint16_t groups[MAX_TILES_PARAM];   // per tile of a frame: live groups nq1 | nrb << 4 | nq2 << 8 | nq3 << 12 -- in the parameter
+                       // (constant) bank so that the MMA-issue thread's control flow and operands stay in uniform registers
   Level lv[TRL_MAX_SCALES];
   float logit_lo;      // screen: logit(thr - margin)
   ScreenEntry* screen;
   int* screen_cnt;
   int screen_cap;
   CapFlag* capflag;
+  // Epilogue constants.  PReLU is evaluated as c1 v + c2 |v| with c1 = (1 + a) / 2, c2 = (1 - a) / 2: two packed instructions
+  // per channel pair instead of compare / multiply / select per channel (this kernel only screens: the extra rounding is
+  // far inside the margin).  conv1 / conv2: packed fp16 pairs (the results are stored as fp16 anyway); conv3: fp32 pairs,
+  // already multiplied by the conv4_1 logit-difference weight dw, so the logit is sum k1 u + k2 |u| with u = acc + b3.
   float b1[10], a1[10];
   float b2[16], a2[16];
-  float b3[32], a3[32], dw[32];       // dw = conv4_1 weight of class 1 minus class 0
+  float b3[32], k1[32], k2[32];
   float db;
   int conv1_monotone;
 };
@@ -151,6 +170,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (ok) break;
+    if (PNET2_BACKOFF > 0 && (threadIdx.x >> 5) >= W_E1) __nanosleep(PNET2_BACKOFF);
     if (clock64() - t0 > 4000000000LL) __trap();        // ~2 s: a lost arrival must not hang the device
   }
 }
@@ -182,6 +202,12 @@ __device__ __forceinline__ void tmem_ld10(uint32_t taddr, float (&v)[10]) {
   for (int i = 0; i < 10; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<const __half2*>(&u); }
+__device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<const uint32_t*>(&h); }
+// PReLU of a packed fp16 pair: c1 v + c2 |v|
+__device__ __forceinline__ __half2 prelu_h2(__half2 v, uint32_t c1, uint32_t c2) {
+  return __hfma2(v, as_h2(c1), __hmul2(__habs2(v), as_h2(c2)));
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -218,12 +244,14 @@ __device__ __forceinline__ int nrb1(const TileRef& t) { return t.rows + 4 > 16 ?
 __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __restrict__ wpacked, const __grid_constant__ Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t in_full[2], in_empty[2];
-  __shared__ __align__(8) uint64_t acc1_full[2], acc1_empty[2];
-  __shared__ __align__(8) uint64_t p1_ready, acc2_full[4], acc2_empty, c2_ready, acc3_full[4], acc3_empty;
+  // conv1 accumulators: two TMEM slots, but EIGHT barrier pairs used round robin -- with more epilogue sets than slots a set's
+  // consecutive uses of one barrier would be two phases apart, which a parity wait cannot tell from zero phases
+  __shared__ __align__(8) uint64_t acc1_full[8], acc1_empty[8];
+  __shared__ __align__(8) uint64_t p1_ready[2], acc2_full[4], acc2_empty, c2_ready, acc3_full[4], acc3_empty;   // p1_ready: one per p1 buffer
+  // (conv1 and its epilogue may finish tile k + 1 before the conv2 issue waits for tile k: one barrier would be two phases ahead)
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  float act_max = 0.f;
   P2T(long long tcm = 0; long long tdec = 0; long long ti2 = 0; long long ti1 = 0; long long ti3 = 0; long long tq = 0; long long tw0 = 0; long long tw1 = 0; long long tw2 = 0; long long tw3 = 0; long long tw4 = 0; long long tw5 = 0; long long tstart = clock64();)
 
   // zero the operand planes once (slack rows / pad halves are read by dead accumulator rows and must stay finite), load weights
@@ -236,12 +264,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1);
-        mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 128);
-      }
+      for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
+      for (int i = 0; i < 8; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 128); }
       for (int i = 0; i < 4; ++i) { mbar_init(&acc2_full[i], 1); mbar_init(&acc3_full[i], 1); }
-      mbar_init(&p1_ready, 256); mbar_init(&acc2_empty, 128); mbar_init(&c2_ready, 128); mbar_init(&acc3_empty, 128);
+      mbar_init(&p1_ready[0], 128 * E1_SETS); mbar_init(&p1_ready[1], 128 * E1_SETS); mbar_init(&acc2_empty, 128); mbar_init(&c2_ready, 128); mbar_init(&acc3_empty, 128 * E3_SETS);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -301,25 +327,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
       for (int i = 0; i <= n_my; ++i) {
         g_prev = g_cur;
         if (i < n_my) {
-          const TileRef t = tile_at(tile_s, cur);
+          g_cur = p.groups[cur.blk];
           cursor_next(cur, p.blocks);
-          g_cur = ncg1(t) | (nrb1(t) << 4) | (ncg2(t) << 8) | (ncg3(t) << 12);
         }
-        const bool do1 = i < n_my, do3 = i >= 1;
-        // ---- conv2 of tile i - 1: per 8-column group one M tile of 16 row pairs; row taps t = 1, 0, 2, 3, two MMAs each.
-        // B rows are blocks dy2 | dy1 | dy0; tap t multiplies [dy = t | dy = t - 1] (taps 0 and 3: one block, half N, one half of D)
-        if (do3) {
+        const bool do1 = i < n_my;
+        // ---- conv1 of tile i: M tile = 8 pooled columns x 16 pooled rows; input-row taps t = 1, 0, 2, 3 (tap 1 first: it writes
+        // all 64 columns).  It advances only as fast as its epilogue sets free the two accumulator slots.  Its epilogue writes
+        // the p1 planes of buffer i & 1; the last MMAs that read that buffer (conv2 of tile i - 2) were issued by this thread
+        // before any conv1 MMA of tile i, so the epilogue cannot start before they have completed.
+        const int buf = i & 1;
+        const int nq1 = do1 ? (g_cur & 15) : 0, nrb = (g_cur >> 4) & 15;
+        const uint64_t a1_b = a1_t + (uint64_t)(buf * (IN_STRIDE / 16));
+        if (do1) mbar_wait_t(&in_full[buf], (i >> 1) & 1, tw0);
+        auto conv1_tile = [&](int rb, int q) {             // called with literals: the operand offsets fold to constants
+          if (rb < nrb && q < nq1) {
+            const uint32_t slot = u1 & 1u;
+            if (u1 >= 2) mbar_wait_t(&acc1_empty[(u1 - 2) & 7u], ((u1 - 2) >> 3) & 1, tw3);   // the slot's previous user has been read out
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            P2T(tq = clock64();)
+            const uint32_t d = tm + ACC1_COL + 64u * slot;
+            const uint64_t a = a1_b + (uint64_t)(32 * rb * (IN_ROWB / 16) + 8 * q);
+            umma_f16(d, a + 1 * (IN_ROWB / 16), b1_t + 32, ID64, 0u);
+            umma_f16(d, a, b1_t + 64, ID32, 1u);
+            umma_f16(d, a + 2 * (IN_ROWB / 16), b1_t, ID64, 1u);
+            umma_f16(d + 32u, a + 3 * (IN_ROWB / 16), b1_t, ID32, 1u);
+            umma_commit(smem_u32(&acc1_full[u1 & 7u]));
+            ++u1;
+            P2T(ti1 += clock64() - tq;)
+          }
+        };
+        conv1_tile(0, 0); conv1_tile(0, 1); conv1_tile(0, 2); conv1_tile(0, 3);
+        conv1_tile(1, 0); conv1_tile(1, 1); conv1_tile(1, 2); conv1_tile(1, 3);
+        if (do1) umma_commit(smem_u32(&in_empty[buf]));     // every MMA that reads this input buffer has completed
+        // ---- conv2 of tile i - 1 (its conv1 epilogue had the whole conv1 phase of tile i to finish): per 8-column group one M
+        // tile of 16 row pairs; row taps t = 1, 0, 2, 3, two MMAs each.  B rows are blocks dy2 | dy1 | dy0; tap t multiplies
+        // [dy = t | dy = t - 1] (taps 0 and 3: one block, half N, one half of D)
+        if (i >= 1) {
           const int k = i - 1;
-          mbar_wait_t(&p1_ready, k & 1, tw1);
+          mbar_wait_t(&p1_ready[k & 1], (k >> 1) & 1, tw1);
           if (k >= 1) mbar_wait_t(&acc2_empty, (k - 1) & 1, tw2);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int nq = (g_prev >> 8) & 15;
+          const uint64_t pb = (uint64_t)((k & 1) * (P1_STRIDE / 16));
           P2T(tq = clock64();)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (q < nq) {
               const uint32_t d = tm + ACC2_COL + 32u * q;
-              const uint64_t aq = (uint64_t)(8 * q);                                  // 8 pixels = 128 bytes
+              const uint64_t aq = pb + (uint64_t)(8 * q);                             // 8 pixels = 128 bytes
               // tap 1 first: it writes all 32 columns (accumulate = 0)
               umma_f16(d, a2a_t + aq + 1 * PL_PITCH, b2a_t + 16, ID32, 0u);
               umma_f16(d, a2b_t + aq + 1 * PL_PITCH, b2b_t + 16, ID32, 1u);
@@ -334,67 +389,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
           }
           P2T(ti2 += clock64() - tq;)
         }
-        // ---- conv1 of tile i (M tile = 8 pooled columns x 16 pooled rows; input-row taps t = 1, 0, 2, 3) interleaved with
-        // conv3 of tile i - 1 (per 8-column group one M tile of 16 row pairs; 4 row taps x 3 kx taps).  conv1 advances only as
-        // fast as its epilogue frees the two accumulator slots; the conv3 groups between its M tiles keep the tensor pipe busy
-        // meanwhile and give the conv2 epilogue of tile i - 1 time to finish before its output is needed.
-        const int buf = i & 1;
-        const int nq1 = do1 ? (g_cur & 15) : 0, nrb = (g_cur >> 4) & 15, n3 = (g_prev >> 12) & 15;
-        const uint64_t a1_b = a1_t + (uint64_t)(buf * (IN_STRIDE / 16));
-        if (do1) mbar_wait_t(&in_full[buf], (i >> 1) & 1, tw0);
-        auto conv1_tile = [&](int rb, int q) {             // called with literals: the operand offsets fold to constants
-          if (rb < nrb && q < nq1) {
-            const uint32_t slot = u1 & 1u;
-            if (u1 >= 2) mbar_wait_t(&acc1_empty[slot], ((u1 >> 1) - 1) & 1, tw3);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            P2T(tq = clock64();)
-            const uint32_t d = tm + ACC1_COL + 64u * slot;
-            const uint64_t a = a1_b + (uint64_t)(32 * rb * (IN_ROWB / 16) + 8 * q);
-            umma_f16(d, a + 1 * (IN_ROWB / 16), b1_t + 32, ID64, 0u);
-            umma_f16(d, a, b1_t + 64, ID32, 1u);
-            umma_f16(d, a + 2 * (IN_ROWB / 16), b1_t, ID64, 1u);
-            umma_f16(d + 32u, a + 3 * (IN_ROWB / 16), b1_t, ID32, 1u);
-            umma_commit(smem_u32(&acc1_full[slot]));
-            ++u1;
-            P2T(ti1 += clock64() - tq;)
-          }
-        };
-        auto conv3_group = [&](int q) {
-          if (do3) {
-            if (q < n3) {
-              P2T(tq = clock64();)
-              const uint32_t d = tm + ACC3_COL + 64u * q;
-              const uint64_t aq = a3_t + (uint64_t)(8 * q);
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                const uint64_t bk = b3_t + (uint64_t)(kx * 2 * W3_ROWS);
-                umma_f16(d, aq + (1 * PL_PITCH + kx), bk + 32, ID64, kx == 0 ? 0u : 1u);
-              }
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                const uint64_t bk = b3_t + (uint64_t)(kx * 2 * W3_ROWS);
-                umma_f16(d, aq + kx, bk + 64, ID32, 1u);
-                umma_f16(d, aq + (2 * PL_PITCH + kx), bk, ID64, 1u);
-                umma_f16(d + 32u, aq + (3 * PL_PITCH + kx), bk, ID32, 1u);
-              }
-              P2T(ti3 += clock64() - tq;)
-            }
-            umma_commit(smem_u32(&acc3_full[q]));          // dead groups too: keeps the barrier phases aligned with the tile count
-          }
-        };
-        conv1_tile(0, 0); conv1_tile(0, 1); conv1_tile(0, 2); conv1_tile(0, 3);
-        if (do3) {
-          mbar_wait_t(&c2_ready, (i - 1) & 1, tw4);
-          if (i >= 2) mbar_wait_t(&acc3_empty, (i - 2) & 1, tw5);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        conv3_group(0);
-        conv1_tile(1, 0); conv1_tile(1, 1);
-        conv3_group(1);
-        conv1_tile(1, 2); conv1_tile(1, 3);
-        conv3_group(2);
-        conv3_group(3);
-        if (do1) umma_commit(smem_u32(&in_empty[buf]));     // every MMA that reads this input buffer has completed
       }
       P2T(atomicAdd(&g_pnet2_phase[0], (unsigned long long)(clock64() - tstart)); atomicAdd(&g_pnet2_phase[1], (unsigned long long)tw0);
           atomicAdd(&g_pnet2_phase[2], (unsigned long long)tw1); atomicAdd(&g_pnet2_phase[3], (unsigned long long)tw2);
@@ -404,10 +398,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
           atomicAdd(&g_pnet2_phase[19], (unsigned long long)tcm); atomicAdd(&g_pnet2_phase[20], (unsigned long long)tdec);)
     }
     __syncwarp();
+  } else if (warp == W_MMA3) {
+    // =================================================================== MMA issue, conv3 (a second elected thread)
+    // conv3 has its own issue thread: one thread cannot issue the ~105 MMAs of a tile as fast as the tensor pipe executes them.
+    // Ordering against the other issuer is by barriers only: c2_ready (conv2 epilogue done) before, acc3_full after -- the
+    // conv2 epilogue of the NEXT tile waits for the last acc3_full of this one before it overwrites the c2 planes.
+    const uint32_t sbase = smem_u32(smem);
+    constexpr uint32_t tm = 0u;
+    constexpr uint32_t ID32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t ID64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    if (elect_one()) {
+      const uint64_t a3_t = umma_desc(sbase + C0_OFF, (uint32_t)(C1_OFF - C0_OFF), 2u * PL_PITCH * 16u);   // conv3 A: [ch 0-7 | ch 8-15]
+      const uint64_t b3_t = umma_desc(sbase + W3_OFF, W3_ROWS * 16u, 128u);
+      TileCursor cur = cursor_init(p.blocks);
+#pragma unroll 1
+      for (int k = 0; k < n_my; ++k) {
+        const int n3 = (p.groups[cur.blk] >> 12) & 15;
+        cursor_next(cur, p.blocks);
+        mbar_wait_t(&c2_ready, k & 1, tw4);
+        if (k >= 1) mbar_wait_t(&acc3_empty, (k - 1) & 1, tw5);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        P2T(tq = clock64();)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q < n3) {
+            const uint32_t d = tm + ACC3_COL + 64u * q;
+            const uint64_t aq = a3_t + (uint64_t)(8 * q);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint64_t bk = b3_t + (uint64_t)(kx * 2 * W3_ROWS);
+              umma_f16(d, aq + (1 * PL_PITCH + kx), bk + 32, ID64, kx == 0 ? 0u : 1u);
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint64_t bk = b3_t + (uint64_t)(kx * 2 * W3_ROWS);
+              umma_f16(d, aq + kx, bk + 64, ID32, 1u);
+              umma_f16(d, aq + (2 * PL_PITCH + kx), bk, ID64, 1u);
+              umma_f16(d + 32u, aq + (3 * PL_PITCH + kx), bk, ID32, 1u);
+            }
+          }
+          umma_commit(smem_u32(&acc3_full[q]));          // dead groups too: keeps the barrier phases aligned with the tile count
+        }
+        P2T(ti3 += clock64() - tq;)
+      }
+      P2T(atomicAdd(&g_pnet2_phase[5], (unsigned long long)tw4); atomicAdd(&g_pnet2_phase[6], (unsigned long long)tw5);
+          atomicAdd(&g_pnet2_phase[18], (unsigned long long)ti3); atomicAdd(&g_pnet2_phase[21], (unsigned long long)(clock64() - tstart));)
+    }
+    __syncwarp();
   } else if (warp >= W_E1 && warp < W_E2) {
     // =================================================================== conv1 epilogue: pool, bias, PReLU -> p1 planes
-    // two sets of four warps; set s serves accumulator slot s (every second M tile), so two M tiles are in flight
+    // E1_SETS sets of four warps take the M tiles round robin, so several are in flight (one set needs ~900 cycles per M
+    // tile, the MMAs of one take 176)
     const int lg = warp & 3, set = (warp - W_E1) >> 2;
+    int turn = 0;                                            // u1 % E1_SETS
     const int g = 4 * lg + (lane >> 3), ci = lane & 7;       // accumulator row = 8 g + ci: pooled row g of the block, column ci of the group
     uint32_t u1 = 0;
     TileCursor cur = cursor_init(p.blocks);
@@ -419,15 +462,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
       for (int rb = 0; rb < nrb; ++rb)
         for (int q = 0; q < nq; ++q, ++u1) {
           const uint32_t slot = u1 & 1u;
-          if ((int)slot != set) continue;
-          mbar_wait_t(&acc1_full[slot], (u1 >> 1) & 1, tw0);
+          const bool mine = turn == set;
+          turn = turn + 1 == E1_SETS ? 0 : turn + 1;
+          if (!mine) continue;
+          mbar_wait_t(&acc1_full[u1 & 7u], (u1 >> 3) & 1, tw0);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + ACC1_COL + 64u * slot;
           float v[4][10];                     // [2 * (conv row parity) + (conv x parity)][channel]
           tmem_ld10(taddr, v[0]); tmem_ld10(taddr + 16, v[1]); tmem_ld10(taddr + 32, v[2]); tmem_ld10(taddr + 48, v[3]);
           tmem_ld_wait();
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(&acc1_empty[slot]);
+          mbar_arrive(&acc1_empty[u1 & 7u]);
           const int R = 16 * rb + g, c = 8 * q + ci;
           const int gy = 2 * (tr.oy0 + R), gx = 2 * (tr.ox0 + c);
           float m[10];
@@ -449,14 +494,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
               m[co] = (mm == -INFINITY) ? 0.f : mm;
             }
           }
-#pragma unroll
-          for (int co = 0; co < 10; ++co) act_max = fmaxf(act_max, fabsf(m[co]));
           const int n = R * PL_PITCH + c;
-          *reinterpret_cast<uint4*>(smem + P1A_OFF + n * 16) =
+          uint8_t* p1 = smem + (k & 1) * P1_STRIDE;
+          *reinterpret_cast<uint4*>(p1 + P1A_OFF + n * 16) =
               make_uint4(pack_h2(m[0], m[1]), pack_h2(m[2], m[3]), pack_h2(m[4], m[5]), pack_h2(m[6], m[7]));
           // channels 8, 9 go to the side plane of the three pixels whose kx taps see this one
           const uint32_t w89 = pack_h2(m[8], m[9]);
-          uint32_t* side = reinterpret_cast<uint32_t*>(smem + P1B_OFF) + n * 4;
+          uint32_t* side = reinterpret_cast<uint32_t*>(p1 + P1B_OFF) + n * 4;
           side[0] = w89;
           if (c >= 1) side[-4 + 1] = w89;
           if (c >= 2) side[-8 + 2] = w89;
@@ -464,9 +508,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
       // The other set may own the tile's last M tile: wait for that one too before arriving, so that no warp can arrive for
       // the next tile before every warp has arrived for this one (conv1 of the next tile is issued behind conv2 of this one,
       // which waits for p1_ready).
-      mbar_wait_t(&acc1_full[(u1 - 1) & 1u], ((u1 - 1) >> 1) & 1, tw0);
+      mbar_wait_t(&acc1_full[(u1 - 1) & 7u], ((u1 - 1) >> 3) & 1, tw0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // p1 planes -> visible to the UMMA proxy
-      mbar_arrive(&p1_ready);
+      mbar_arrive(&p1_ready[k & 1]);
     }
   } else if (warp >= W_E2 && warp < W_E3) {
     // =================================================================== conv2 epilogue: bias, PReLU -> c2 planes
@@ -476,6 +520,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
     for (int k = 0; k < n_my; ++k, cursor_next(cur, p.blocks)) {
       const TileRef tr = tile_at(tile_s, cur);
       const int nq = ncg2(tr);
+      // conv3 of the previous tile (issued by the other MMA thread) must have finished reading the c2 planes
+      if (k >= 1) mbar_wait_t(&acc3_full[3], (k - 1) & 1, tw0);
       for (int q = 0; q < nq; ++q) {
         mbar_wait_t(&acc2_full[q], k & 1, tw0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -489,7 +535,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
 #pragma unroll
           for (int co = 0; co < 16; ++co) {
             x[co] = prelu(v[r][co] + p.b2[co], p.a2[co]);
-            act_max = fmaxf(act_max, fabsf(x[co]));
           }
           const int n = (2 * g + r) * PL_PITCH + 8 * q + ci;
           *reinterpret_cast<uint4*>(smem + C0_OFF + n * 16) =
@@ -505,7 +550,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
     }
   } else if (warp >= W_E3) {
     // =================================================================== conv3 epilogue: bias, PReLU, conv4_1 logit difference -> screen
-    const int lg = warp & 3;
+    const int lg = warp & 3, set3 = (warp - W_E3) >> 2;
     const int g = 4 * lg + (lane >> 3), ci = lane & 7;
     TileCursor cur = cursor_init(p.blocks);
     for (int k = 0; k < n_my; ++k, cursor_next(cur, p.blocks)) {
@@ -516,7 +561,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
         // dead groups are waited for as well (their barrier is committed empty): a warp without work must not run ahead and
         // arrive on acc3_empty for the next tile before the others have arrived for this one
         mbar_wait_t(&acc3_full[q], k & 1, tw0);
-        if (q >= nq) continue;
+        if (q >= nq || (q % E3_SETS) != set3) continue;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + ACC3_COL + 64u * q;
 #pragma unroll
@@ -525,10 +570,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
           float v[2][16];
           tmem_ld16(taddr + 32 * r, v[0]); tmem_ld16(taddr + 32 * r + 16, v[1]);
           tmem_ld_wait();
+          // logit = db + sum_c k1_c u_c + k2_c |u_c| with u = acc + b3 (PReLU(u) dw = k1 u + k2 |u|): four instructions per channel
+          // with constant-bank operands, two independent accumulation chains
+          float d2 = 0.f;
 #pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 16)
-#pragma unroll
-            for (int j = 0; j < 16; ++j) dsum = fmaf(prelu(v[c0 >> 4][j] + p.b3[c0 + j], p.a3[c0 + j]), p.dw[c0 + j], dsum);
+          for (int c0 = 0; c0 < 32; ++c0) {
+            const float u = v[c0 >> 4][c0 & 15] + p.b3[c0];
+            dsum = fmaf(u, p.k1[c0], dsum);
+            d2 = fmaf(fabsf(u), p.k2[c0], d2);
+          }
+          dsum += d2;
           const int row = 2 * g + r, col = 8 * q + ci;
           const int oy = tr.oy0 + row, ox = tr.ox0 + col;
           const bool live = row < tr.rows && col < tr.cols;
@@ -560,10 +611,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) pnet2_kernel(const uint32_t* __re
         const int slot = warp == W_E1 ? 8 : warp == W_E2 ? 10 : warp == W_E3 ? 12 : warp == W_TMA ? 14 : -1;
         if (slot >= 0) { atomicAdd(&g_pnet2_phase[slot], w); if (slot != 14) atomicAdd(&g_pnet2_phase[slot + 1], tot - w); }
       })
-  if (!(act_max <= ACT_MAX) && p.capflag) {      // also catches NaN
-    p.capflag->overflow = 1; p.capflag->stage = 5; p.capflag->frame = 0;
-    p.capflag->count = 0; p.capflag->capacity = (int)ACT_MAX;
-  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
@@ -643,6 +690,21 @@ int pnet2_pack_weights(trl_ctx* c, const float* h, size_t len) {
   memcpy(e + 52, b3, 128); memcpy(e + 84, a3, 128);
   for (int ci = 0; ci < 32; ++ci) e[116 + ci] = w41[32 + ci] - w41[ci];
   e[148] = b41[1] - b41[0];
+  // Range of the fp16 operands, bounded on the host instead of checked per value on the device: inputs are in [-1, 1], so
+  // |conv1| <= sum |w1| + |b1|, PReLU scales by at most max(1, |a|), and so on for conv2.  The hybrid P-Net is only offered
+  // when both bounds are far inside fp16's range (trl_create falls back to the 3-term kernel otherwise).
+  float bound1 = 0.f, bound2 = 0.f;
+  for (int co = 0; co < 10; ++co) {
+    float sa = fabsf(b1[co]);
+    for (int k = 0; k < 27; ++k) sa += fabsf(w1[co * 27 + k]);
+    bound1 = fmaxf(bound1, sa * fmaxf(1.f, fabsf(a1[co])));
+  }
+  for (int co = 0; co < 16; ++co) {
+    float sa = fabsf(b2[co]);
+    for (int k = 0; k < 90; ++k) sa += fabsf(w2[co * 90 + k]) * bound1;
+    bound2 = fmaxf(bound2, sa * fmaxf(1.f, fabsf(a2[co])));
+  }
+  c->pnet2_range_ok = (bound1 < ACT_MAX && bound2 < ACT_MAX && isfinite(bound1) && isfinite(bound2)) ? 1 : 0;
   TRL_CUDA(c, cudaFuncSetAttribute(pnet2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
   return TRL_OK;
 }
@@ -669,6 +731,8 @@ int launch_pnet2(trl_ctx* c, const uint4* d_pyr_hi, int B, const PyramidGeom& g,
     for (int t = 0; t < L.tiles; ++t) {
       const int ty = t / L.tiles_x, tx = t - ty * L.tiles_x;
       const int rows = std::min(T, L.oh - ty * T), cols = std::min(T, L.ow - tx * T);
+      if ((int)table.size() < MAX_TILES_PARAM)
+        p.groups[table.size()] = (uint16_t)(((cols + 4 + 7) >> 3) | ((rows + 4 > 16 ? 2 : 1) << 4) | (((cols + 2 + 7) >> 3) << 8) | (((cols + 7) >> 3) << 12));
       table.push_back(make_int4(k | (rows << 8) | (cols << 16), ty * T, tx * T, 0));
     }
     blocks += L.tiles;
@@ -680,6 +744,7 @@ int launch_pnet2(trl_ctx* c, const uint4* d_pyr_hi, int B, const PyramidGeom& g,
   }
   p.blocks = blocks; p.n_frames = B;
   if (blocks == 0) return TRL_OK;
+  if (blocks > MAX_TILES_PARAM) TRL_FAIL(c, TRL_E_INVALID, "frame has %d P-Net tiles, the group table holds %d", blocks, MAX_TILES_PARAM);
   if (blocks > MAX_TILES_PER_FRAME) TRL_FAIL(c, TRL_E_INVALID, "frame has %d P-Net tiles, the tile table holds %d", blocks, MAX_TILES_PER_FRAME);
   // the tile table of this frame geometry lives in the context; it is rebuilt (stream ordered) only when the geometry changes
   if (c->pnet2_tiles_n != blocks || c->pnet2_tiles_key != ((long long)g.hs[0] << 32 | (unsigned)g.ws[0]) || !c->d_pnet2_tiles) {
@@ -694,13 +759,17 @@ int launch_pnet2(trl_ctx* c, const uint4* d_pyr_hi, int B, const PyramidGeom& g,
   p.logit_lo = thr_lo <= 0.f ? -INFINITY : thr_lo >= 1.f ? INFINITY : logf(thr_lo / (1.f - thr_lo));
   p.screen = d_screen; p.screen_cnt = d_screen_cnt; p.screen_cap = screen_cap; p.capflag = c->d_cap;
   const float* e = c->h_pnet2_epi;
-  memcpy(p.b1, e + 0, 40); memcpy(p.a1, e + 10, 40);
-  memcpy(p.b2, e + 20, 64); memcpy(p.a2, e + 36, 64);
-  memcpy(p.b3, e + 52, 128); memcpy(p.a3, e + 84, 128);
-  memcpy(p.dw, e + 116, 128);
+  const float *b1 = e + 0, *a1 = e + 10, *b2 = e + 20, *a2 = e + 36, *b3 = e + 52, *a3 = e + 84, *dw = e + 116;
+  memcpy(p.b1, b1, 40); memcpy(p.a1, a1, 40);
+  memcpy(p.b2, b2, 64); memcpy(p.a2, a2, 64);
+  for (int ci = 0; ci < 32; ++ci) {
+    p.b3[ci] = b3[ci];
+    p.k1[ci] = dw[ci] * 0.5f * (1.f + a3[ci]);
+    p.k2[ci] = dw[ci] * 0.5f * (1.f - a3[ci]);
+  }
   p.db = e[148];
   p.conv1_monotone = 1;
-  for (int co = 0; co < 10; ++co) if (!(p.a1[co] >= 0.f)) p.conv1_monotone = 0;
+  for (int co = 0; co < 10; ++co) if (!(a1[co] >= 0.f)) p.conv1_monotone = 0;
   const long long total = (long long)blocks * B;
   const int grid = (int)(total < c->num_sms ? total : c->num_sms);
   pnet2_kernel<<<grid, NTHREADS, SMEM_BYTES + blocks * 16, s>>>(c->d_pnet2_packed, p);
