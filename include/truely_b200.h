@@ -82,6 +82,9 @@ typedef struct {
 } trl_config_t;
 
 void trl_default_config(trl_config_t* cfg);
+/* The P-Net mode the context actually runs (trl_create falls back from 2 / 3 to 0 when a host-side bound of the P-Net
+ * activations computed from the weights does not fit the fp16 operands of the screen). */
+int trl_pnet_precision(const trl_ctx_t* ctx);
 size_t trl_facenet_blob_len(void);
 
 /* Replaces MTCNN() + InceptionResnetV1(pretrained="vggface2").eval()   (server/model.py:18-19). */

@@ -38,6 +38,7 @@ _P = C.c_void_p
 SIGNATURES = {
     "trl_default_config": (None, [C.POINTER(Config)]),
     "trl_facenet_blob_len": (C.c_size_t, []),
+    "trl_pnet_precision": (C.c_int, [_P]),
     "trl_create": (C.c_int, [C.c_int, C.POINTER(Weights), C.POINTER(Config), C.POINTER(_P)]),
     "trl_destroy": (None, [_P]),
     "trl_last_error": (C.c_char_p, [_P]),

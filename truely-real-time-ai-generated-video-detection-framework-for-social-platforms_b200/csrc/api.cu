@@ -179,6 +179,8 @@ int trl_pyramid(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, floa
   return launch_pyramid(c, d_frames, B, H, W, g, d_out, false, (cudaStream_t)stream);
 }
 
+int trl_pnet_precision(const trl_ctx_t* c) { return c ? c->cfg.pnet_precision : TRL_E_INVALID; }
+
 int trl_pyramid_pairs(trl_ctx_t* c, const uint8_t* d_frames, int B, int H, int W, void* d_hi, void* d_lo, void* stream) {
   if (!c || !d_frames || !d_hi || !d_lo || B < 0) return TRL_E_INVALID;
   PyramidGeom g;

@@ -101,6 +101,7 @@ class Analyzer:
         if rc != L.TRL_OK:
             raise L.TrlError(rc, self.lib.trl_last_error(None).decode())
         self.ctx = ctx
+        self.pnet_precision = int(self.lib.trl_pnet_precision(ctx))       # the mode in effect (the library may fall back to 0)
         self.stream = torch.cuda.Stream(device=device)
         self.box_cap = cfg.box_cap_frame
         self.crop_size = crop_size
