@@ -219,6 +219,23 @@ int trl_process(trl_ctx_t* ctx, const uint8_t* d_frames, int B, int H, int W, co
                 int* d_box_int, uint8_t* d_valid, float* d_emb, float* d_sim, uint8_t* d_below, uint8_t* d_has_sim,
                 int* d_nfaces, float* d_last_emb, uint8_t* d_last_valid, void* stream);
 
+/* Device-side annotation of processed frames, in place (replaces cv2.rectangle + cv2.putText, server/model.py:67-74;
+ * SURVEY.md 8f).  d_state uint8 [B]: 0 = leave the frame alone, 1 = green box + "Real Frame" at (x1, y1 - 10),
+ * 2 = red box + "AI Detected - Frame n" at (10, 30) with n = d_frame_index[b]; d_box int32 [B,4] = (x1, y1, x2, y2) as
+ * written by trl_process.  Bit exact with OpenCV: the thickness-2 rectangle by rule, the anti-aliased text through stamps
+ * of per-pixel look-up tables that the host builds once with OpenCV's own rasteriser (overlay.py::build_stamps) and
+ * registers with trl_overlay_set_stamps -- h_lut uint8 [n_lut][2][256] (blend towards 0 / towards 255 as a function of the
+ * background value), twelve stamps ("Real Frame", the "AI Detected - Frame " prefix, the digits 0-9 in the first digit
+ * slot; box relative to the text origin, index map uint16 [h][w] at h_idx + idx_off, 0 = untouched, k = table k - 1) and
+ * the font's digit advance in pixels.  Text that would leave the frame is not drawn (OpenCV's clipped rasterisation is not
+ * translation invariant): d_text_pending uint8 [B] (may be NULL) is set to 1 for such frames and the caller draws their
+ * text on the host; the rectangle is always drawn here. */
+typedef struct { int ox, oy, w, h; long long idx_off; } trl_stamp_t;
+int trl_overlay_set_stamps(trl_ctx_t* ctx, const uint8_t* h_lut, int n_lut, const trl_stamp_t* h_stamps, int n_stamps,
+                           const uint16_t* h_idx, long long n_idx, int digit_advance);
+int trl_overlay(trl_ctx_t* ctx, uint8_t* d_frames, int B, int H, int W, const int* d_box, const uint8_t* d_state,
+                const int* d_frame_index, uint8_t* d_text_pending, void* stream);
+
 /* First half of trl_process: detect + crop-align only (server/model.py:47-57), writing the crops of this batch into a
  * caller-owned buffer d_crops uint8 [B,S,S,3].  Lets a host that holds a whole clip run the cascade chunk by chunk
  * and then embed every crop with ONE trl_facenet call (large-M GEMMs) followed by one trl_consistency call. */

@@ -456,3 +456,23 @@ def test_annotated_frames_equal_the_oracle_loop(analyzer):
     for i in range(140):
         if i not in processed:
             assert np.array_equal(got_sink.frames[i], frames[i]), f"frame {i} must pass through untouched"
+
+
+def test_device_overlay_stream_equals_the_host_overlay(analyzer):
+    """SURVEY.md 8f (device overlay): with device_overlay=True the boxes and captions are drawn by trl_overlay on the
+    resident frames; the stream handed to the writer is the same, pixel for pixel, as with OpenCV on the host copies
+    (240x320 frames: the 'AI Detected - Frame n' caption does not fit, so the pending-caption hand-back is exercised too;
+    480x640: it fits and is drawn on the device)."""
+    for (h, w, seed) in ((240, 320, 31), (480, 640, 33)):
+        clip = SyntheticClip(h, w, 30, 140, n_faces=(1, 1), face_h=(0.3 * h, 0.45 * h), jitter=1.6, seed=seed)
+        frames = [f for f in clip]
+        host_sink, dev_sink = _FrameSink(), _FrameSink()
+        tr_h = M.analyze_stream(iter([f.copy() for f in frames]), 30, w, h, writer=host_sink, analyzer=analyzer, chunk=8,
+                                device_overlay=False)
+        tr_d = M.analyze_stream(iter([f.copy() for f in frames]), 30, w, h, writer=dev_sink, analyzer=analyzer, chunk=8,
+                                device_overlay=True)
+        assert tr_h.flagged == tr_d.flagged and tr_h.score == tr_d.score
+        assert sum(tr_h.flagged) > 0 and sum(s is not None and not f for s, f in zip(tr_h.sim, tr_h.flagged)) > 0
+        assert len(host_sink.frames) == len(dev_sink.frames) == 140
+        for i in range(140):
+            assert np.array_equal(host_sink.frames[i], dev_sink.frames[i]), f"{h}x{w} frame {i}: overlays differ"

@@ -54,7 +54,7 @@ def run_pairs(an, frames):
     return d_hi, d_lo, off, pitch
 
 
-@pytest.mark.parametrize("shape", [(360, 640), (233, 417)])
+@pytest.mark.parametrize("shape", [(360, 640), (233, 417), (720, 1280), (1080, 1920), (96, 176)])
 def test_pair_pyramid_restores_the_fp32_pyramid(analyzer, shape):
     an = analyzer
     h, w = shape

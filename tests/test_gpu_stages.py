@@ -405,3 +405,43 @@ def test_facenet_valid_only_equals_full_batch_on_the_valid_rows(analyzer):
                 assert np.array_equal(part[i], full[i]), f"{pattern}: row {i}"
             else:
                 assert not part[i].any(), f"{pattern}: row {i} must be zero"
+
+
+def test_overlay_kernel_equals_opencv(analyzer):
+    """trl_overlay (server/model.py:67-74): rectangle + anti-aliased caption, bit exact with cv2.rectangle /
+    cv2.putText on random frames, boxes (clamped ones and boxes at the frame edge included) and frame numbers; captions
+    that would leave the frame come back as pending and are completed with cv2.putText on the host."""
+    from truely_b200 import model as M
+    from truely_b200 import overlay as O
+    an = analyzer
+    rng = np.random.default_rng(5)
+    for (h, w) in ((360, 640), (720, 1280), (96, 176), (233, 417)):
+        B = 24
+        frames = rng.integers(0, 256, (B, h, w, 3), dtype=np.uint8)
+        box = np.zeros((B, 4), np.int32)
+        state = rng.integers(0, 3, B).astype(np.uint8)
+        fidx = rng.choice([0, 7, 10, 48, 123, 999, 1234, 56789, 100000], B).astype(np.int32)
+        for b in range(B):
+            x1 = int(rng.integers(0, w - 2)); x2 = int(rng.integers(x1 + 1, w + 1))
+            y1 = int(rng.integers(0, h - 2)); y2 = int(rng.integers(y1 + 1, h + 1))
+            box[b] = (x1, y1, x2, y2)
+        box[0] = (0, 0, w, h); box[1] = (w - 1, h - 1, w, h); box[2] = (0, 40, 50, 90)
+        d_frames = torch.from_numpy(frames).cuda()
+        d_box = torch.from_numpy(box).cuda()
+        pend = an.overlay_device(d_frames, d_box, state, fidx)
+        an.stream.synchronize()
+        got = d_frames.cpu().numpy()
+        pend = pend.cpu().numpy()
+        n_dev = 0
+        for b in range(B):
+            ref = frames[b].copy()
+            if state[b] != 0:
+                M.annotate_frame(ref, box[b], state[b] == 2, int(fidx[b]))
+            out = got[b].copy()
+            if pend[b]:
+                O.draw_text_host(out, box[b], int(state[b]), int(fidx[b]))
+            elif state[b] != 0:
+                n_dev += 1
+            assert np.array_equal(out, ref), f"{h}x{w} frame {b} state {state[b]} box {box[b]}"
+        if w >= 640:
+            assert n_dev > 0

@@ -279,3 +279,37 @@ def test_vectorised_score_equals_the_frame_by_frame_machine():
         score, fl, got = M.score_from_flags(valid, has, below, max(frame_count, 0), fps, stride)
         assert fl == flagged and score == want
         assert (got.deepfake_count, got.deep_fake_frame_count) == (rl.deepfake_count, rl.deep_fake_frame_count)
+
+
+def test_overlay_stamps_reproduce_opencv():
+    """The stamps behind trl_overlay (overlay.py::build_stamps, made with OpenCV's own rasteriser) and the rectangle rule,
+    applied in numpy exactly as overlay.cu applies them, against cv2.rectangle + cv2.putText(LINE_AA) of
+    server/model.py:67-74 on random frames, boxes and frame numbers (captions that would be clipped are completed on the
+    host, as the product does)."""
+    import cv2
+    from truely_b200 import overlay as O
+    st = O.stamps()
+    assert len(st.boxes) == 12 and st.digit_advance > 0 and st.idx.max() <= st.lut.shape[0]
+    rng = np.random.default_rng(0)
+    n_device_text = 0
+    for trial in range(240):
+        h, w = [(360, 640), (720, 1280), (96, 176), (233, 417)][trial % 4]
+        frame = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        x1 = int(rng.integers(0, w - 2)); x2 = int(rng.integers(x1 + 1, w + 1))
+        y1 = int(rng.integers(0, h - 2)); y2 = int(rng.integers(y1 + 1, h + 1))
+        state = int(rng.integers(1, 3))
+        fi = int(rng.choice([0, 7, 10, 48, 123, 999, 1234, 56789, 100000]))
+        ref = frame.copy()
+        if state == O.STATE_AI:
+            cv2.rectangle(ref, (x1, y1), (x2, y2), (0, 0, 255), 2)
+            cv2.putText(ref, f"AI Detected - Frame {fi}", (10, 30), cv2.FONT_HERSHEY_SIMPLEX, 1, (0, 0, 255), 2, cv2.LINE_AA)
+        else:
+            cv2.rectangle(ref, (x1, y1), (x2, y2), (0, 255, 0), 2)
+            cv2.putText(ref, "Real Frame", (x1, y1 - 10), cv2.FONT_HERSHEY_SIMPLEX, 0.5, (0, 255, 0), 2, cv2.LINE_AA)
+        got = frame.copy()
+        if O.apply_numpy(got, (x1, y1, x2, y2), state, fi, st):
+            O.draw_text_host(got, (x1, y1, x2, y2), state, fi)
+        else:
+            n_device_text += 1
+        assert np.array_equal(got, ref), f"trial {trial}: {h}x{w} state {state} box {(x1, y1, x2, y2)} frame {fi}"
+    assert n_device_text > 60

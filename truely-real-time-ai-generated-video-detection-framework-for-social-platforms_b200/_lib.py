@@ -33,6 +33,10 @@ class Config(C.Structure):
                 ("mode", C.c_int), ("margin", C.c_int)]
 
 
+class Stamp(C.Structure):
+    _fields_ = [("ox", C.c_int), ("oy", C.c_int), ("w", C.c_int), ("h", C.c_int), ("idx_off", C.c_longlong)]
+
+
 _P = C.c_void_p
 # name -> (restype, argtypes); exactly the symbols include/truely_b200.h declares
 SIGNATURES = {
@@ -66,6 +70,8 @@ SIGNATURES = {
     "trl_shard_record_bytes": (C.c_size_t, [C.c_int]),
     "trl_shard_pack": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "trl_shard_resolve": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P]),
+    "trl_overlay_set_stamps": (C.c_int, [_P, _P, C.c_int, C.POINTER(Stamp), C.c_int, _P, C.c_longlong, C.c_int]),
+    "trl_overlay": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "trl_process": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trl_detect_align": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "trl_detect_align_async": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),

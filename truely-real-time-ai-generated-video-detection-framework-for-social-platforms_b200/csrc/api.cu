@@ -1,6 +1,7 @@
 // C ABI of libtruely_b200.so (include/truely_b200.h): context, workspace and the device-side MTCNN cascade driver.
 #include <string.h>
 
+#include <stdlib.h>
 #include "common.cuh"
 
 static thread_local std::string g_create_err;
@@ -106,6 +107,7 @@ void trl_destroy(trl_ctx_t* c) {
   if (c->d_onet) cudaFree(c->d_onet);
   if (c->d_nms_tmp) cudaFree(c->d_nms_tmp);
   if (c->d_pyr_tab) cudaFree(c->d_pyr_tab);
+  overlay_destroy(c);
   if (c->h_cap) cudaFreeHost(c->h_cap);
   delete c;
 }
@@ -154,6 +156,19 @@ int trl_create(int device, const trl_weights_t* w, const trl_config_t* cfg, trl_
   if (w->h_facenet && (rc = facenet_create(c, w->h_facenet, w->facenet_len)) != TRL_OK) return fail(rc);
   *out = c;
   return TRL_OK;
+}
+
+int trl_overlay_set_stamps(trl_ctx_t* c, const uint8_t* h_lut, int n_lut, const trl_stamp_t* h_stamps, int n_stamps,
+                           const uint16_t* h_idx, long long n_idx, int digit_advance) {
+  if (!c) return TRL_E_INVALID;
+  return overlay_set_stamps(c, h_lut, n_lut, h_stamps, n_stamps, h_idx, n_idx, digit_advance);
+}
+
+int trl_overlay(trl_ctx_t* c, uint8_t* d_frames, int B, int H, int W, const int* d_box, const uint8_t* d_state,
+                const int* d_frame_index, uint8_t* d_text_pending, void* stream) {
+  if (!c) return TRL_E_INVALID;
+  if (!d_frames || !d_box || !d_state || !d_frame_index || B < 0 || H <= 0 || W <= 0) TRL_FAIL(c, TRL_E_INVALID, "trl_overlay: bad argument");
+  return launch_overlay(c, d_frames, B, H, W, d_box, d_state, d_frame_index, d_text_pending, (cudaStream_t)stream);
 }
 
 int trl_pyramid_geometry(const trl_ctx_t* ctx, int H, int W, double* scales, int* hs, int* ws, int* oh, int* ow) {

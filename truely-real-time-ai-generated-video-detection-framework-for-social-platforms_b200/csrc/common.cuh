@@ -63,6 +63,7 @@ struct PyrParams {
   int tab_off[TRL_MAX_SCALES];         // offset of level k's window tables
   int kwmin[TRL_MAX_SCALES];           // narrowest horizontal window of level k; > 0: every window is kwmin or kwmin + 1 columns
                                        // wide and kwmin <= 5 (branch-free pass 2), 0: general loop
+  unsigned magic[TRL_MAX_SCALES];      // floor(2^32 / ws) + 1: flat pixel index of a CTA -> row by one multiply-high
 };
 
 
@@ -167,6 +168,7 @@ struct trl_ctx {
   float* d_rnet = nullptr;          // packed R-Net (mtcnn_ro.cu layout)
   float* d_onet = nullptr;
   FaceNetEngine* facenet = nullptr;
+  void* overlay = nullptr;          // overlay::Stamps (overlay.cu)
 
   // workspace for trl_detect / trl_process, sized for (ws_B, ws_H, ws_W)
   int ws_B = 0, ws_H = 0, ws_W = 0;
@@ -298,6 +300,12 @@ int facenet_forward(trl_ctx* c, const uint8_t* d_crops, int n, int S, int norm, 
 // only the crops with d_valid[i] != 0 are embedded (packed on the device, no host synchronisation); other rows of d_emb = 0
 int facenet_forward_valid(trl_ctx* c, const uint8_t* d_crops, const uint8_t* d_valid, int n, int S, int norm, float* d_emb,
                           cudaStream_t s);
+
+void overlay_destroy(trl_ctx* c);                                                                  // overlay.cu
+int overlay_set_stamps(trl_ctx* c, const uint8_t* h_lut, int n_lut, const trl_stamp_t* h_stamps, int n_stamps,
+                       const uint16_t* h_idx, long long n_idx, int digit_advance);
+int launch_overlay(trl_ctx* c, uint8_t* d_frames, int B, int H, int W, const int* d_box, const uint8_t* d_state,
+                   const int* d_frame_index, uint8_t* d_text_pending, cudaStream_t s);
 
 int nms_init(trl_ctx* c);
 int nms_max_n();

@@ -13,7 +13,7 @@
 #include <string.h>
 
 #include "common.cuh"
-#include <cuda_fp16.h>
+#include "pyramid.cuh"
 
 // ----------------------------------------------------------------------------- shared device helpers
 
@@ -58,14 +58,6 @@ __device__ __forceinline__ float area_norm(int s, int kh, int kw) {
 // (Markstein's correction step, 3 instructions).  It equals the IEEE quotient for every operand this kernel can see:
 // div_verify_kernel checks all s in [0, 255 kh kw] for every (kh, kw) pair of a level against __fdiv_rn when the
 // tables are built, and a level that failed would use __fdiv_rn instead (p.fastdiv).
-constexpr int PYR_MAX_KH = 257;
-
-__device__ __forceinline__ float div_small(float a, float b, float r) {
-  const float q0 = __fmul_rn(a, r);
-  const float e = __fmaf_rn(-q0, b, a);
-  return __fmaf_rn(e, r, q0);
-}
-
 // pairs: int2 (kh, kw); bad[pair] set when the fast division differs from IEEE for some window sum
 __global__ void __launch_bounds__(256) div_verify_kernel(const int2* __restrict__ pairs, int* __restrict__ bad) {
   const int2 k = pairs[blockIdx.y];
@@ -106,41 +98,32 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t* __restrict__ frames
 // all-tensor-pipe P-Net's input (pnet2.cu): per pixel 4 halves (B, G, R, 0) = 8 bytes in a "hi" image (fp16(v): the screen's
 // operand) and a "lo" image (fp16(v - hi): with hi it restores v to 2^-23 relative for the exact re-evaluation,
 // pnet_refine.cu); one 8-byte store each instead of three 4-byte planar stores.
-template <int OUT> struct PyrOut;
-template <> struct PyrOut<0> {
-  typedef float T;
-  static __device__ __forceinline__ void store(float* o, long long plane, float v0, float v1, float v2) {
-    o[0] = v0; o[plane] = v1; o[2 * plane] = v2;
-  }
-};
-template <> struct PyrOut<1> {
-  typedef uint2 T;
-  static __device__ __forceinline__ void store(uint2* o, long long lo_off, float v0, float v1, float v2) {
-    const __half2 h01 = __floats2half2_rn(v0, v1);
-    const __half2 h2 = __floats2half2_rn(v2, 0.f);
-    const float2 f01 = __half22float2(h01);
-    const float f2 = __low2float(h2);
-    const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y);
-    const __half2 l2 = __floats2half2_rn(v2 - f2, 0.f);
-    o[0] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h2));
-    o[lo_off] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l2));
-  }
-};
-
+// The CTA's rows are one flattened [rows][ws] index space (idx -> row by a multiply-high with floor(2^32 / ws) + 1): on a
+// 769-pixel row a quarter of the lanes of a row-by-row loop idle (769 = 3 x 256 + 1), and the per-row constants {kh, RN(1 / kh)}
+// come from shared memory instead of being rebuilt per thread and row.  (a - 127.5) * 2^-7 is one FMA: scaling by a power of
+// two commutes with the rounding of the subtraction.
 template <int KMIN, int OUT>
-__device__ __forceinline__ void hpass_fixed(const uint16_t* __restrict__ vr, const int2* __restrict__ tw, int ws, int tid,
-                                            float fkh, float rkh, bool fast, typename PyrOut<OUT>::T* __restrict__ o0, long long plane) {
-  for (int i = tid; i < ws; i += 256, o0 += 256, tw += 256) {
-    const int2 e = __ldg(tw);
+__device__ __forceinline__ void hpass_fixed(const uint16_t* __restrict__ v16, int vpitch, const float2* __restrict__ rowc,
+                                            const int2* __restrict__ tw, int ws, int nrows, uint32_t magic, int tid, bool fast,
+                                            typename PyrOut<OUT>::T* __restrict__ obase, int pitch, long long plane) {
+  const uint32_t total = (uint32_t)(nrows * ws);
+#pragma unroll 2
+  for (uint32_t idx = tid; idx < total; idx += 256) {
+    const uint32_t row = __umulhi(idx, magic);
+    const uint32_t col = idx - row * (uint32_t)ws;
+    const float2 rc = rowc[row];
+    const float fkh = rc.x, rkh = rc.y;
+    const int2 e = __ldg(tw + col);
     const int xw = e.x;
     const float rkw = __int_as_float(e.y);
     const int kw = xw >> 16;
-    const uint16_t* vp = vr + 3 * (xw & 0xFFFF);
+    const uint16_t* vp = v16 + row * vpitch + 3 * (xw & 0xFFFF);
     int s0 = vp[0], s1 = vp[1], s2 = vp[2];
 #pragma unroll
     for (int x = 1; x < KMIN; ++x) { s0 += vp[3 * x]; s1 += vp[3 * x + 1]; s2 += vp[3 * x + 2]; }
-    if (kw > KMIN) { s0 += vp[3 * KMIN]; s1 += vp[3 * KMIN + 1]; s2 += vp[3 * KMIN + 2]; }
-    const float fkw = (float)kw;
+    const bool wide = kw > KMIN;
+    if (wide) { s0 += vp[3 * KMIN]; s1 += vp[3 * KMIN + 1]; s2 += vp[3 * KMIN + 2]; }
+    const float fkw = wide ? (float)(KMIN + 1) : (float)KMIN;
     float a0, a1, a2;
     if (fast) {
       a0 = div_small(div_small((float)s0, fkh, rkh), fkw, rkw);
@@ -151,8 +134,8 @@ __device__ __forceinline__ void hpass_fixed(const uint16_t* __restrict__ vr, con
       a1 = __fdiv_rn(__fdiv_rn((float)s1, fkh), fkw);
       a2 = __fdiv_rn(__fdiv_rn((float)s2, fkh), fkw);
     }
-    PyrOut<OUT>::store(o0, plane, __fmul_rn(__fsub_rn(a0, 127.5f), 0.0078125f), __fmul_rn(__fsub_rn(a1, 127.5f), 0.0078125f),
-                       __fmul_rn(__fsub_rn(a2, 127.5f), 0.0078125f));
+    PyrOut<OUT>::store(obase + row * pitch + col, plane, __fmaf_rn(a0, 0.0078125f, -0.99609375f),
+                       __fmaf_rn(a1, 0.0078125f, -0.99609375f), __fmaf_rn(a2, 0.0078125f, -0.99609375f));
   }
 }
 
@@ -174,6 +157,11 @@ __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restr
   const int* ty1 = ty0 + hs;
   const size_t fbase = (size_t)b * H * rowbytes;
   const int tid = threadIdx.x;
+  __shared__ float2 rowc[8];                          // {kh, RN(1 / kh)} of the CTA's rows (R <= 4), read after the barrier below
+  if (tid < nrows) {
+    const float fkh = (float)(__ldg(ty1 + tid) - __ldg(ty0 + tid));
+    rowc[tid] = make_float2(fkh, __frcp_rn(fkh));
+  }
 
   constexpr bool ALIGNED = MODE >= 1;
   if (MODE == 2) {
@@ -184,15 +172,19 @@ __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restr
       if (q >= nq) continue;
       for (int jj = 0; jj < nrows; ++jj) {
         const int y0 = __ldg(ty0 + jj), y1 = __ldg(ty1 + jj);
-        uint32_t ae0 = 0, ao0 = 0, ae1 = 0, ao1 = 0, ae2 = 0, ao2 = 0, ae3 = 0, ao3 = 0;
+        // per source row and word: the raw word into one register, its odd bytes (PRMT) into a second one; the even-byte
+        // lanes follow once per output row from  sum(w) - (odd << 8)  (mod 2^32; exact, both 16-bit lanes of the result are
+        // < 2^16).  Three instructions per word and row instead of four, and two rows fold into one three-input add.
+        uint32_t sw0 = 0, ao0 = 0, sw1 = 0, ao1 = 0, sw2 = 0, ao2 = 0, sw3 = 0, ao3 = 0;
         const uint4* row = reinterpret_cast<const uint4*>(frames + fbase) + (size_t)y0 * nq + q;
         for (int y = y0; y < y1; ++y, row += nq) {
           const uint4 w = __ldg(row);
-          ae0 += w.x & 0x00FF00FFu; ao0 += __byte_perm(w.x, 0, 0x4341);
-          ae1 += w.y & 0x00FF00FFu; ao1 += __byte_perm(w.y, 0, 0x4341);
-          ae2 += w.z & 0x00FF00FFu; ao2 += __byte_perm(w.z, 0, 0x4341);
-          ae3 += w.w & 0x00FF00FFu; ao3 += __byte_perm(w.w, 0, 0x4341);
+          sw0 += w.x; ao0 += __byte_perm(w.x, 0, 0x4341);
+          sw1 += w.y; ao1 += __byte_perm(w.y, 0, 0x4341);
+          sw2 += w.z; ao2 += __byte_perm(w.z, 0, 0x4341);
+          sw3 += w.w; ao3 += __byte_perm(w.w, 0, 0x4341);
         }
+        const uint32_t ae0 = sw0 - (ao0 << 8), ae1 = sw1 - (ao1 << 8), ae2 = sw2 - (ao2 << 8), ae3 = sw3 - (ao3 << 8);
         uint4* vrow = reinterpret_cast<uint4*>(vs) + jj * (nw >> 1) + 2 * q;      // 2 words of sums per source word
         vrow[0] = make_uint4(__byte_perm(ae0, ao0, 0x5410), __byte_perm(ae0, ao0, 0x7632),
                              __byte_perm(ae1, ao1, 0x5410), __byte_perm(ae1, ao1, 0x7632));
@@ -248,22 +240,21 @@ __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restr
   const long long plane = OUT == 0 ? (long long)hs * pitch : lo_off;
   OT* obase = out + p.off[lvl] + (size_t)b * (OUT == 0 ? 3 : 1) * hs * pitch + (size_t)j0 * pitch;
   const bool fast = p.fastdiv[lvl] != 0;
-  for (int jj = 0; jj < nrows; ++jj) {
-    const int kh = __ldg(ty1 + jj) - __ldg(ty0 + jj);
-    const float fkh = (float)kh, rkh = __frcp_rn(fkh);
-    const uint16_t* vr = v16 + jj * (4 * nw);
-    if (p.kwmin[lvl] > 0) {
-      const int2* twf = reinterpret_cast<const int2*>(t) + tid;
-      OT* of = obase + jj * pitch + tid;
-      switch (p.kwmin[lvl]) {
-        case 1: hpass_fixed<1, OUT>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
-        case 2: hpass_fixed<2, OUT>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
-        case 3: hpass_fixed<3, OUT>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
-        case 4: hpass_fixed<4, OUT>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
-        default: hpass_fixed<5, OUT>(vr, twf, ws, tid, fkh, rkh, fast, of, plane); break;
-      }
-      continue;
+  if (p.kwmin[lvl] > 0) {
+    const int2* tw = reinterpret_cast<const int2*>(t);
+    const uint32_t magic = p.magic[lvl];
+    switch (p.kwmin[lvl]) {
+      case 1: hpass_fixed<1, OUT>(v16, 4 * nw, rowc, tw, ws, nrows, magic, tid, fast, obase, pitch, plane); break;
+      case 2: hpass_fixed<2, OUT>(v16, 4 * nw, rowc, tw, ws, nrows, magic, tid, fast, obase, pitch, plane); break;
+      case 3: hpass_fixed<3, OUT>(v16, 4 * nw, rowc, tw, ws, nrows, magic, tid, fast, obase, pitch, plane); break;
+      case 4: hpass_fixed<4, OUT>(v16, 4 * nw, rowc, tw, ws, nrows, magic, tid, fast, obase, pitch, plane); break;
+      default: hpass_fixed<5, OUT>(v16, 4 * nw, rowc, tw, ws, nrows, magic, tid, fast, obase, pitch, plane); break;
     }
+    return;
+  }
+  for (int jj = 0; jj < nrows; ++jj) {
+    const float fkh = rowc[jj].x, rkh = rowc[jj].y;
+    const uint16_t* vr = v16 + jj * (4 * nw);
     // per-thread running pointers: one 64-bit add per plane and step instead of rebuilding three addresses per pixel
     OT* o0 = obase + jj * pitch + tid;
     const int2* tw = reinterpret_cast<const int2*>(t) + tid;      // {x0 | kw << 16, bits of RN(1 / kw)}
@@ -397,6 +388,7 @@ static int launch_pyramid_any(trl_ctx* c, const uint8_t* d_frames, int B, int H,
     p.tab_off[k] = c->pyr_tab_off[k];
     p.fastdiv[k] = c->pyr_fastdiv[k];
     p.kwmin[k] = c->pyr_kwmin[k];
+    p.magic[k] = (unsigned)((1ull << 32) / (unsigned)g.ws[k]) + 1u;
     // rows per CTA: about 8-12 source rows of work, bounded by 64 KB of column sums
     int R = (int)(8.0 * g.hs[k] / H);
     R = std::max(1, std::min(R, 4));

@@ -161,6 +161,30 @@ class Analyzer:
         finally:
             self.set_capacity(*saved)
 
+    def overlay_device(self, d_frames, d_box, state, frame_index):
+        """Annotate resident frames in place (``trl_overlay``; server/model.py:67-74 on the device, bit exact with
+        OpenCV).  ``d_frames`` uint8 [n,H,W,3] and ``d_box`` int32 [n,4] live on the device; ``state`` (0 untouched /
+        1 "Real Frame" / 2 "AI Detected") and ``frame_index`` are host sequences.  Enqueued on ``self.stream``; returns
+        the device uint8 [n] tensor of frames whose caption would leave the frame and is therefore left to the host
+        (``overlay.draw_text_host``)."""
+        from . import overlay as O
+        t = self.torch
+        if not getattr(self, "_overlay_ready", False):
+            O.register(self.lib, self.ctx)
+            self._overlay_ready = True
+        n, H, W = int(d_frames.shape[0]), int(d_frames.shape[1]), int(d_frames.shape[2])
+        dev = f"cuda:{self.device}"
+        h_state = t.as_tensor(np.asarray(state, dtype=np.uint8)).pin_memory()
+        h_index = t.as_tensor(np.asarray(frame_index, dtype=np.int32)).pin_memory()
+        with t.cuda.stream(self.stream):
+            d_state = h_state.to(dev, non_blocking=True)
+            d_index = h_index.to(dev, non_blocking=True)
+            pending = t.zeros(n, dtype=t.uint8, device=dev)
+            self._check(self.lib.trl_overlay(self.ctx, _vp(d_frames), n, H, W, _vp(d_box), _vp(d_state), _vp(d_index),
+                                             _vp(pending), self._sptr()))
+        self._overlay_keep = (h_state, h_index, d_state, d_index)      # alive until the stream has consumed them
+        return pending
+
     def launch_count(self) -> int:
         return int(self.lib.trl_launch_count(self.ctx))
 
@@ -561,13 +585,20 @@ class _Chunk:
 
 
 def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, analyzer: Analyzer | None = None,
-                   chunk: int | None = None, keep_emb: bool = False) -> Trace:
+                   chunk: int | None = None, keep_emb: bool = False, device_overlay: bool | None = None) -> Trace:
     """The hot loop of server/model.py:42-77 as a two-deep software pipeline.
 
     While the GPU works on chunk k (H2D copy + trl_process, all asynchronous), the host decodes chunk k+1;
     when chunk k's small result arrays are back, its frames are annotated and written in order.
     ``frame_iter`` yields BGR uint8 frames; ``writer`` (optional) is a cv2.VideoWriter.
+    ``device_overlay`` (default: environment TRUELY_DEVICE_OVERLAY=1): boxes and captions are drawn by ``trl_overlay`` on the
+    chunk's resident frames, which are then read back for the encoder, instead of by OpenCV on the host copies -- the
+    same pixels either way (tests/test_gpu_e2e.py); the host path stays the default because the decoded frames already
+    are on the host and this box has no NVENC to hand the resident frames to.
     """
+    if device_overlay is None:
+        device_overlay = os.environ.get("TRUELY_DEVICE_OVERLAY", "0") == "1"
+    device_overlay = bool(device_overlay) and writer is not None
     an = analyzer or get_analyzer()
     t = an.torch
     stride = frame_stride(fps)
@@ -665,6 +696,24 @@ def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, a
                 for q in [c] + list(pending):
                     h = redo_uncapped(q, h) if q.n > 0 else h
         host = {k: v[:c.n].numpy() for k, v in c.host.items()}
+        drawn = None
+        if device_overlay and c.n > 0:
+            # the run-length state of every processed frame first (host, exact integers), then one overlay launch on the
+            # chunk's resident frames and their copy back for the encoder
+            rl2 = RunLength()
+            rl2.deepfake_count, rl2.deep_fake_frame_count = rl.deepfake_count, rl.deep_fake_frame_count
+            states = np.zeros(c.n, np.uint8)
+            for j in range(c.n):
+                if host["valid"][j] and host["has_sim"][j]:
+                    states[j] = 2 if rl2.step(bool(host["below"][j])) else 1
+            if "host_frames_out" not in c.out:       # page-locked and cacheable (the staging buffer is write-combined)
+                c.out["host_frames_out"] = t.empty((chunk, height, width, 3), dtype=t.uint8, pin_memory=True)
+            pend = an.overlay_device(c.out["frames"][:c.n], c.out["box"][:c.n], states, c.proc_idx[:c.n])
+            with t.cuda.stream(an.stream):
+                c.out["host_frames_out"][:c.n].copy_(c.out["frames"][:c.n], non_blocking=True)
+                pend_h = pend.cpu()
+            an.stream.synchronize()
+            drawn = (c.out["host_frames_out"][:c.n].numpy(), states, pend_h.numpy())
         k = 0
         for pos, frame in enumerate(c.frames):
             if k < c.n and c.proc_pos[k] == pos:
@@ -674,7 +723,12 @@ def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, a
                 flagged = False
                 if valid and host["has_sim"][k]:
                     flagged = rl.step(bool(host["below"][k]))
-                    if writer is not None:
+                    if drawn is not None:
+                        frame = drawn[0][k]
+                        if drawn[2][k]:
+                            from . import overlay as O
+                            O.draw_text_host(frame, box, int(drawn[1][k]), fidx)
+                    elif writer is not None:
                         annotate_frame(frame, box, flagged, fidx)
                 tr.frame_index.append(fidx)
                 tr.valid.append(valid)
