@@ -107,6 +107,7 @@ void trl_destroy(trl_ctx_t* c) {
   if (c->d_onet) cudaFree(c->d_onet);
   if (c->d_nms_tmp) cudaFree(c->d_nms_tmp);
   if (c->d_pyr_tab) cudaFree(c->d_pyr_tab);
+  if (c->d_pyr_blk) cudaFree(c->d_pyr_blk);
   overlay_destroy(c);
   if (c->h_cap) cudaFreeHost(c->h_cap);
   delete c;

@@ -181,6 +181,8 @@ struct trl_ctx {
   int screen_cap = 0;
   size_t pyr_smem_set = 0;       // dynamic shared memory the pyramid kernel has been opted in to
   int* d_pyr_tab = nullptr;      // adaptive-average window tables of the current frame shape
+  void* d_pyr_blk = nullptr;     // pyramid kernel: (level, first output row) of every CTA of one frame
+  long long pyr_blk_key = 0;
   int pyr_tab_H = 0, pyr_tab_W = 0;
   int pyr_tab_off[TRL_MAX_SCALES] = {0};
   int pyr_fastdiv[TRL_MAX_SCALES] = {0};

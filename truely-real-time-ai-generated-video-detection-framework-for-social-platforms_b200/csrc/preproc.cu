@@ -142,12 +142,12 @@ __device__ __forceinline__ void hpass_fixed(const uint16_t* __restrict__ v16, in
 template <int MODE, int OUT>     // MODE 0: byte-aligned rows, 1: 4-byte aligned rows, 2: 16-byte aligned rows (one 128-bit load per thread and row)
 __global__ void __launch_bounds__(256) pyramid_sep_kernel(const uint8_t* __restrict__ frames, int H, int W, size_t total_bytes,
                                                          const __grid_constant__ PyrParams p, const int* __restrict__ tab,
+                                                         const int2* __restrict__ blk_tab,
                                                          typename PyrOut<OUT>::T* __restrict__ out, long long lo_off) {
   extern __shared__ __align__(16) uint32_t vs[];      // [R][nw] x 2 words = u16 column sums [R][4*nw]
-  int lvl = 0;
-  while (lvl + 1 < p.n && (int)blockIdx.x >= p.blk_start[lvl + 1]) ++lvl;
+  const int2 bi = __ldg(blk_tab + blockIdx.x);        // (level, first output row) of this CTA: one load instead of a search
+  const int lvl = bi.x, j0 = bi.y;
   const int hs = p.hs[lvl], ws = p.ws[lvl], R = p.rows[lvl];
-  const int j0 = ((int)blockIdx.x - p.blk_start[lvl]) * R;
   const int nrows = min(R, hs - j0);
   const int b = blockIdx.y;
   const int rowbytes = 3 * W;
@@ -416,17 +416,29 @@ static int launch_pyramid_any(trl_ctx* c, const uint8_t* d_frames, int B, int H,
     TRL_CUDA(c, cudaFuncSetAttribute(pyramid_sep_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     c->pyr_smem_set = cap;
   }
+  // (level, first row) of every CTA of one frame, rebuilt when the frame shape (hence the row grouping) changes
+  const long long blk_key = ((long long)H << 40) ^ ((long long)W << 16) ^ (long long)blocks;
+  if (c->d_pyr_blk == nullptr || c->pyr_blk_key != blk_key) {
+    std::vector<int2> blks;
+    for (int k = 0; k < g.n; ++k)
+      for (int j0 = 0; j0 < g.hs[k]; j0 += p.rows[k]) blks.push_back(make_int2(k, j0));
+    if (c->d_pyr_blk) { TRL_CUDA(c, cudaStreamSynchronize(s)); TRL_CUDA(c, cudaFree(c->d_pyr_blk)); c->d_pyr_blk = nullptr; }
+    TRL_CUDA(c, cudaMalloc(&c->d_pyr_blk, blks.size() * sizeof(int2)));
+    TRL_CUDA(c, cudaMemcpy(c->d_pyr_blk, blks.data(), blks.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    c->pyr_blk_key = blk_key;
+  }
+  const int2* blk_tab = reinterpret_cast<const int2*>(c->d_pyr_blk);
   dim3 grid(blocks, B);
   const bool rows16 = (3 * W) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 15) == 0;
   if (pairs) {
     uint2* hi = reinterpret_cast<uint2*>(d_hi);
     const long long lo_off = reinterpret_cast<uint2*>(d_lo) - hi;
-    if (rows16) pyramid_sep_kernel<2, 1><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, hi, lo_off);
-    else if (aligned) pyramid_sep_kernel<1, 1><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, hi, lo_off);
-    else pyramid_sep_kernel<0, 1><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, hi, lo_off);
-  } else if (rows16) pyramid_sep_kernel<2, 0><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out, 0);
-  else if (aligned) pyramid_sep_kernel<1, 0><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out, 0);
-  else pyramid_sep_kernel<0, 0><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, d_out, 0);
+    if (rows16) pyramid_sep_kernel<2, 1><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, blk_tab, hi, lo_off);
+    else if (aligned) pyramid_sep_kernel<1, 1><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, blk_tab, hi, lo_off);
+    else pyramid_sep_kernel<0, 1><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, blk_tab, hi, lo_off);
+  } else if (rows16) pyramid_sep_kernel<2, 0><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, blk_tab, d_out, 0);
+  else if (aligned) pyramid_sep_kernel<1, 0><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, blk_tab, d_out, 0);
+  else pyramid_sep_kernel<0, 0><<<grid, 256, smem, s>>>(d_frames, H, W, total, p, c->d_pyr_tab, blk_tab, d_out, 0);
   TRL_LAUNCH_CHECK(c);
   return TRL_OK;
 }
