@@ -682,7 +682,8 @@ def main():
         roof = {"kernel": "pyramid_sep_kernel", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": None,
                 "note": "algorithmic bytes = frame read once (3 H W) + pyramid written once (%d B per pyramid pixel, %d pixels per "
-                        "frame); the kernel is bound by instruction issue on its exact integer window sums (ncu: issue slots 76 %% "
+                        "frame); the kernel is bound by the SM's load/store data pipe (shared-memory wavefronts of the horizontal pass) and "
+                        "integer issue on its exact window sums (ncu: LSU data-pipe wavefronts 73-82 %% of peak, issue slots 66-76 %% "
                         "busy, DRAM traffic == algorithmic bytes), not by HBM" % (16 if hybrid else 12, pyr_px)}
         roof["algorithmic_bytes_per_launch"] = ab * frames_per_launch
     else:

@@ -104,8 +104,8 @@ def traffic(out_path, workload, frames_per_launch, *reports):
         hdr, units, r = rows[0], rows[1], rows[2]
         rd, wr, du = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
         full_name = r[hdr.index("Kernel Name")]
-        m = re.search(r"(\w+)\s*(<|\(|$)", re.sub(r"^void\s+", "", full_name).split("::")[-1])
-        name = m.group(1) if m else full_name
+        m = re.match(r"(?:void\s+)?([\w:]+)", full_name)            # up to the template / argument list; namespaces dropped
+        name = m.group(1).split("::")[-1] if m else full_name
         recs.append({"kernel": name, "workload": workload, "frames_per_launch": float(frames_per_launch),
                      "dram_bytes_read": _to_bytes(r[rd], units[rd]), "dram_bytes_write": _to_bytes(r[wr], units[wr]),
                      "dram_bytes_per_launch": _to_bytes(r[rd], units[rd]) + _to_bytes(r[wr], units[wr]),
