@@ -445,3 +445,19 @@ def test_overlay_kernel_equals_opencv(analyzer):
             assert np.array_equal(out, ref), f"{h}x{w} frame {b} state {state[b]} box {box[b]}"
         if w >= 640:
             assert n_dev > 0
+
+
+def test_facenet_upstream_weights_parity_when_present(analyzer):
+    """ADVICE (round 1): the bf16 trunk is demonstrated on the seeded stand-in network only.  When the upstream vggface2
+    checkpoint is installed (TRUELY_WEIGHTS_DIR / TORCH_HOME / the facenet_pytorch package data) this holds the tcgen05
+    path to what a 1e-3 band around the 0.99 similarity threshold needs -- 1 - cos <= 1e-4 against the fp32 oracle and
+    consecutive-frame similarities within 1e-3 -- and otherwise reports that bar as unverified (skip)."""
+    if analyzer.facenet_source == "synthetic":
+        pytest.skip("upstream vggface2 weights absent: bf16-trunk parity with real weights unverified (stand-in network only)")
+    crops = _face_crops(12, 40)
+    got, ref = _run_facenet(analyzer, crops), _oracle_emb(crops)
+    cos = [H.cosine(a, b) for a, b in zip(got, ref)]
+    assert 1.0 - min(cos) <= 1e-4, cos
+    sim_g = [float(np.dot(got[i], got[i + 1])) for i in range(len(got) - 1)]
+    sim_r = [float(np.dot(ref[i], ref[i + 1]) / (np.linalg.norm(ref[i]) * np.linalg.norm(ref[i + 1]))) for i in range(len(ref) - 1)]
+    assert max(abs(a - b) for a, b in zip(sim_g, sim_r)) < 1e-3
