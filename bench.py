@@ -686,6 +686,19 @@ def main():
                         "integer issue on its exact window sums (ncu: LSU data-pipe wavefronts 73-82 %% of peak, issue slots 66-76 %% "
                         "busy, DRAM traffic == algorithmic bytes), not by HBM" % (16 if hybrid else 12, pyr_px)}
         roof["algorithmic_bytes_per_launch"] = ab * frames_per_launch
+    elif dom in ("rnet", "onet"):
+        # workloads with many candidates per frame (real video): an fp32 FMA kernel, one candidate per CTA.  Roof = the FMA
+        # pipe (SMs x 128 lanes x 2 flop x clock; outside the hbm / tensor pair the contract names for the headline workload)
+        smp = np.stack(wl.sample_frames(min(32, n_local)))
+        cnt = an.process_frames(smp, detail=True).counts.astype(np.float64)
+        per_frame = float(cnt[:, 1].mean() if dom == "rnet" else cnt[:, 2].mean())
+        flops_c = 3.06e6 if dom == "rnet" else 25.8e6                       # SURVEY.md 8d, per candidate
+        prop = torch.cuda.get_device_properties(torch.cuda.current_device())
+        peak = prop.multi_processor_count * 128 * 2 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+        ach = flops_c * per_frame * n_local / (per_step[dom] * 1e-3) / 1e12
+        roof = {"kernel": dom + "_kernel", "bound": "fma", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None, "note": "%.1f %s inputs per frame on the first %d frames of the workload; fp32 FMA peak from the SM "
+                                         "count and clock" % (per_frame, "R-Net" if dom == "rnet" else "O-Net", smp.shape[0])}
     else:
         ach = (3 * H * W) * n_local / (per_step[dom] * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -696,7 +709,7 @@ def main():
         roof["traffic"] = rec["bytes"]
         roof["traffic_unit"] = "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
         roof["traffic_source"] = rec["source"]
-    roof["peak_source"] = pk["source"]
+    roof["peak_source"] = pk["source"] if roof["bound"] != "fma" else "SM count x 128 fp32 lanes x 2 x max SM clock"
     roof["launch_ms"] = dom_ms_launch
     roof["frames_per_launch"] = frames_per_launch
 
