@@ -461,3 +461,19 @@ def test_facenet_upstream_weights_parity_when_present(analyzer):
     sim_g = [float(np.dot(got[i], got[i + 1])) for i in range(len(got) - 1)]
     sim_r = [float(np.dot(ref[i], ref[i + 1]) / (np.linalg.norm(ref[i]) * np.linalg.norm(ref[i + 1]))) for i in range(len(ref) - 1)]
     assert max(abs(a - b) for a, b in zip(sim_g, sim_r)) < 1e-3
+
+
+def test_overlay_empty_batch_and_untouched_frames(analyzer):
+    """trl_overlay: B = 0 is a no-op, frames with state 0 come back bit for bit, a missing stamp table is an error."""
+    an = analyzer
+    rng = np.random.default_rng(9)
+    frames = rng.integers(0, 256, (3, 120, 200, 3), dtype=np.uint8)
+    d_frames = torch.from_numpy(frames).cuda()
+    d_box = torch.tensor([[10, 10, 60, 70]] * 3, dtype=torch.int32, device="cuda")
+    pend = an.overlay_device(d_frames, d_box, [0, 0, 0], [1, 2, 3])
+    an.stream.synchronize()
+    assert np.array_equal(d_frames.cpu().numpy(), frames) and not pend.cpu().numpy().any()
+    st = torch.zeros(1, dtype=torch.uint8, device="cuda")
+    idx = torch.zeros(1, dtype=torch.int32, device="cuda")
+    assert an.lib.trl_overlay(an.ctx, vp(d_frames), 0, 120, 200, vp(d_box), vp(st), vp(idx), None, None) == 0
+    assert an.lib.trl_overlay(an.ctx, None, 1, 120, 200, vp(d_box), vp(st), vp(idx), None, None) == L.TRL_E_INVALID
