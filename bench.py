@@ -425,8 +425,10 @@ def parity_check(wl, mt, fn, helpers, ref_trace, out, n, thr=0.99):
     return res
 
 
-def facenet_sweep(an, torch, pk, batches=(64, 128, 256, 512, 1024, 2048, 4096), sizes=(160,), iters=5):
-    """BASELINE.json configs[2]: InceptionResnetV1-only sweep over crop batches resident in HBM (random uint8 crops)."""
+def facenet_sweep(an, torch, pk, batches=(64, 128, 256, 512, 1024, 2048, 4096), sizes=(160, 80), iters=5):
+    """BASELINE.json configs[2]: InceptionResnetV1-only sweep over crop batches resident in HBM
+    (random uint8 crops, seed 0) at 160x160 and at the reference's 80x80, F.to_tensor normalisation (x / 255, norm 0); the
+    largest batch also with fixed_image_standardization ((x - 127.5) / 128, norm 1: folded into the stem, same work)."""
     from truely_b200.model import _vp
     rows = []
     for S in sizes:
@@ -435,21 +437,47 @@ def facenet_sweep(an, torch, pk, batches=(64, 128, 256, 512, 1024, 2048, 4096), 
             g = torch.Generator(device="cuda").manual_seed(0)
             crops = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, device="cuda", generator=g)
             emb = torch.empty((B, 512), dtype=torch.float32, device="cuda")
-            with torch.cuda.stream(an.stream):
-                for _ in range(3):
-                    an._check(an.lib.trl_facenet(an.ctx, _vp(crops), B, S, _vp(emb), an._sptr()))
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(an.stream)
-                for _ in range(iters):
-                    an._check(an.lib.trl_facenet(an.ctx, _vp(crops), B, S, _vp(emb), an._sptr()))
-                e1.record(an.stream)
-            an.stream.synchronize()
-            ms = e0.elapsed_time(e1) / iters
-            tf = flops * B / (ms * 1e-3) / 1e12
-            rows.append({"crop": S, "batch": B, "ms": ms, "tflops_bf16": tf, "frac_of_sustained": tf / pk["bf16_sustained"],
-                         "frac_of_burst": tf / pk["bf16_burst"]})
+            for norm in ((0, 1) if B == batches[-1] else (0,)):
+                with torch.cuda.stream(an.stream):
+                    for _ in range(3):
+                        an._check(an.lib.trl_facenet_norm(an.ctx, _vp(crops), B, S, norm, _vp(emb), an._sptr()))
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(an.stream)
+                    for _ in range(iters):
+                        an._check(an.lib.trl_facenet_norm(an.ctx, _vp(crops), B, S, norm, _vp(emb), an._sptr()))
+                    e1.record(an.stream)
+                an.stream.synchronize()
+                ms = e0.elapsed_time(e1) / iters
+                tf = flops * B / (ms * 1e-3) / 1e12
+                rows.append({"crop": S, "batch": B, "norm": "x/255" if norm == 0 else "(x-127.5)/128", "ms": ms, "tflops_bf16": tf,
+                             "frac_of_sustained": tf / pk["bf16_sustained"], "frac_of_burst": tf / pk["bf16_burst"]})
             del crops, emb
     return rows
+
+
+def candidate_counts(an, wl, n_local, np):
+    """Mean / max number of candidates per frame after each cascade stage on the first frames of the workload (SURVEY.md 8d:
+    they define the NMS / R-Net / O-Net work; with the synthetic MTCNN weights they are a property of those weights)."""
+    smp = np.stack(wl.sample_frames(min(32, n_local)))
+    c = an.process_frames(smp, detail=True).counts.astype(np.float64)
+    names = ("after_per_scale_nms", "rnet_inputs", "onet_inputs", "faces")
+    return {"frames": int(smp.shape[0]), **{n: {"mean": round(float(c[:, k].mean()), 2), "max": int(c[:, k].max())} for k, n in enumerate(names)}}
+
+
+def run_api_timing(path, an):
+    """The public entry point on a video file, decode included: model.run_trace(path, None) = run() without the output
+    video (the decode-inclusive number; decode is OpenCV on the host, server/model.py:23,43)."""
+    import contextlib
+    import io
+    from truely_b200 import model as M
+    with contextlib.redirect_stdout(io.StringIO()):
+        M.run_trace(path, None, analyzer=an)                      # warm-up (file cache, workspace for this shape)
+        t0 = time.perf_counter()
+        tr = M.run_trace(path, None, analyzer=an)
+        dt = time.perf_counter() - t0
+    n = len(tr.frame_index)
+    return {"video": os.path.basename(path), "processed_frames": n, "frames": tr.frame_count, "seconds": dt,
+            "processed_frames_per_s": n / dt, "host_decode_s": tr.timings.get("decode_s"), "score": tr.score}
 
 
 def main():
@@ -762,6 +790,10 @@ def main():
     }
     if wl.kind == "file":
         line["host_decode_s"] = wl.decode_s
+    if world == 1:
+        line["candidates_per_frame"] = candidate_counts(an, wl, n_local, np)
+        if wl.kind == "file":
+            line["run_api"] = run_api_timing(WORKLOADS[args.workload]["path"], an)
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

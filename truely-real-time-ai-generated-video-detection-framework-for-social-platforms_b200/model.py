@@ -581,7 +581,7 @@ def annotate_frame(frame, box, flagged: bool, frame_index: int):
 
 
 class _Chunk:
-    __slots__ = ("frames", "proc_pos", "proc_idx", "pinned", "out", "host", "event", "n", "halo")
+    __slots__ = ("frames", "proc_pos", "proc_idx", "pinned", "pinned_np", "out", "host", "event", "n", "halo")
 
 
 def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, analyzer: Analyzer | None = None,
@@ -613,13 +613,25 @@ def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, a
     halo = None
     frame_count = 0
 
+    # chunk buffers (page-locked staging, device frames, result arrays) outlive the call: allocating and, above all, freeing
+    # page-locked memory costs ~0.25 s per buffer, more than a short clip takes to analyse (experiments/run_api_profile.py)
+    buf_key = (chunk, height, width, bool(keep_emb))
+    cache = getattr(an, "_stream_bufs", None)
+    if cache is None or cache[0] != buf_key:
+        cache = (buf_key, [])
+        an._stream_bufs = cache
+    free_bufs.extend(cache[1])
+    del cache[1][:]
+
     def new_chunk():
         c = _Chunk()
         c.frames, c.proc_pos, c.proc_idx, c.n, c.halo = [], [], [], 0, None
         if free_bufs:
             c.pinned, c.out, c.host = free_bufs.pop()
+            c.pinned_np = c.pinned.numpy()
         else:
             c.pinned = staging_empty(t, (chunk, height, width, 3))
+            c.pinned_np = c.pinned.numpy()
             c.out = an.alloc_outputs(chunk)
             c.out["frames"] = t.empty((chunk, height, width, 3), dtype=t.uint8, device=dev)
             # this chunk's own copy of the incoming halo (the producing chunk's buffers are recycled two chunks later)
@@ -750,7 +762,9 @@ def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, a
     for frame in frame_iter:
         tr.timings["decode_s"] += time.perf_counter() - t_dec
         if frame_count % stride == 0:                             # server/model.py:46
-            cur.pinned[cur.n].copy_(t.from_numpy(frame))
+            # plain memcpy into the staging buffer: a torch copy_ goes through the intra-op thread pool, whose spinning
+            # workers take the cores the video decoder's threads need (cap.read was 5x slower next to it)
+            np.copyto(cur.pinned_np[cur.n], frame)
             cur.proc_pos.append(len(cur.frames))
             cur.proc_idx.append(frame_count)
             cur.n += 1
@@ -769,6 +783,7 @@ def analyze_stream(frame_iter, fps: int, width: int, height: int, writer=None, a
         submit(cur)
     while pending:
         finish(pending.popleft())
+    an._stream_bufs[1].extend(free_bufs)                         # keep the buffers for the next call on this shape
     tr.frame_count = frame_count
     tr.flagged_count = rl.deep_fake_frame_count
     tr.final_run = rl.deepfake_count
