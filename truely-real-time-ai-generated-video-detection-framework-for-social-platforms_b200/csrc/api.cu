@@ -1,7 +1,6 @@
 // C ABI of libtruely_b200.so (include/truely_b200.h): context, workspace and the device-side MTCNN cascade driver.
 #include <string.h>
 
-#include <stdlib.h>
 #include "common.cuh"
 
 static thread_local std::string g_create_err;

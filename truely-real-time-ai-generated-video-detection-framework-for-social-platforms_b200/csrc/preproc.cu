@@ -44,14 +44,17 @@ __device__ __forceinline__ float area_norm(int s, int kh, int kw) {
 // tab + tab_off[k] holds ws pairs {x0 | kw << 16, bits of RN(1 / kw)}, then y0[hs], y1[hs] -- no integer
 // division on the device.
 //
-// One CTA = (frame, level, R consecutive output rows).
+// One CTA = (frame, level, R consecutive output rows); (level, first row) come from a per-CTA table.
 //  pass 1 (vertical): the source rows are read as a flat array of 32-bit words straight from the packed BGR bytes
-//    (no BGRx staging copy): a thread owns word columns tid, tid+256, tid+512, tid+768 of a 1024-word chunk and adds
-//    the bytes of rows [y0, y1) in two registers of 2 x 16-bit lanes each (even / odd bytes); the four loads of a row
-//    are independent.  Integer sums are exact in any order.  The column sums go to shared memory as a u16 array indexed
-//    by byte column.  Coalesced 128 B per warp and row.
-//  pass 2 (horizontal): one thread per output pixel adds its kw column sums per channel, divides (s / kh) / kw exactly
-//    like ATen's adaptive_avg_pool2d, normalises and stores planar fp32 (coalesced along x).
+//    (no BGRx staging copy).  With 16-byte rows (every production shape) a thread owns four consecutive words: one
+//    LDG.128 per source row; per word the raw word goes into one register and its odd bytes (PRMT) into a second one, the
+//    even-byte lanes follow once per output row from  sum(w) - (odd << 8)  (mod 2^32: exact, both 16-bit lanes < 2^16).
+//    Other shapes: word columns tid, tid+256, ... with even / odd byte lanes.  Integer sums are exact in any order.  The
+//    column sums go to shared memory as a u16 array indexed by byte column.
+//  pass 2 (horizontal): the CTA's rows are ONE flattened [rows][ws] index space, one thread per output pixel: kw column
+//    sums per channel, (s / kh) / kw exactly like ATen's adaptive_avg_pool2d, normalise (one FMA), store planar fp32 or the
+//    fp16 hi / lo pair pixel (coalesced along x).  Bound by the shared-memory wavefronts of its 2-byte loads and by integer
+//    issue, not by HBM (profiles/r02d_pyr_full.md).
 // A 16-bit lane holds at most 255 * kh, so kh <= 257 (frames up to ~4000 px on the short side with minsize 20).
 //
 // Division: a / b with b a small integer, r = RN(1/b): q0 = RN(a r), e = a - q0 b (exact, FMA), q = RN(q0 + e r)
