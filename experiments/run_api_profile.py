@@ -18,3 +18,12 @@ while True:
     if not ok: break
     n += 1
 print("decode only", n, time.perf_counter() - t0)
+
+# with the annotated output video (what server.py calls): decode + GPU + annotate + encode
+import tempfile
+outp = os.path.join(tempfile.mkdtemp(), "out.mp4")
+M.run_trace(path, outp, analyzer=an)
+t0 = time.perf_counter(); tr = M.run_trace(path, outp, analyzer=an); dt = time.perf_counter() - t0
+print("with writer: total", dt, tr.timings, "output bytes", os.path.getsize(outp))
+pr = cProfile.Profile(); pr.enable(); tr = M.run_trace(path, outp, analyzer=an); pr.disable()
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(8); print(s.getvalue()[:2500])
