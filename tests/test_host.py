@@ -118,7 +118,8 @@ def test_chunk_schedule_covers_every_frame_once():
                 assert all(r[i][1] == r[i + 1][0] for i in range(len(r) - 1))
     r = chunk_schedule(450, 90, ramp=True)
     sz = [b - a for a, b in r]
-    assert sz[0] == 22 and 90 // 4 <= sz[-1] < 45                       # short first copy, last cascade on a quarter of a chunk
+    assert sz[0] == 22 and 90 // 10 <= sz[-1] < 45                      # short first copy, last cascade on a small chunk
+    assert all(sz[i] >= sz[i + 1] for i in range(sz.index(90), len(sz) - 1))      # the tail only shrinks
     k = sz.index(max(sz))
     assert all(sz[i] >= sz[i + 1] for i in range(k, len(sz) - 1))       # after the full-size chunks the tail only shrinks
 

@@ -385,20 +385,20 @@ class Analyzer:
 
 
 # tail rule of chunk_schedule (next = SCHED_A * size + SCHED_B frames); environment overrides are for tuning runs only
-SCHED_A = float(os.environ.get("TRL_SCHED_A", 0.6))
-SCHED_B = float(os.environ.get("TRL_SCHED_B", 8))
+SCHED_A = float(os.environ.get("TRL_SCHED_A", 0.35))
+SCHED_B = float(os.environ.get("TRL_SCHED_B", 6))
 SCHED_STEPS = int(os.environ.get("TRL_SCHED_STEPS", 6))
-SCHED_MIN_DIV = int(os.environ.get("TRL_SCHED_MIN_DIV", 4))
+SCHED_MIN_DIV = int(os.environ.get("TRL_SCHED_MIN_DIV", 10))
 
 
 def chunk_schedule(n: int, chunk: int, ramp: bool = False):
     """[(start, end)] ranges of at most ``chunk`` frames.  With ``ramp`` (host frames: the H2D copy of chunk k+1 overlaps
     the cascade on chunk k) the chunks grow at the start and shrink towards the end: the copy of the first chunk and the
-    cascade of the last one are the parts of the pipeline that nothing overlaps.  A cascade costs about
-    0.4 ms + 0.028 ms/frame and a copy 0.05 ms/frame (720p, B200, experiments/e2e_timeline.py), so a chunk keeps up
-    with the copy of its successor only if the successor is at least ~0.57 of its size + 8 frames: the tail shrinks by
-    next = 0.6 size + 8 (at most six steps, not below a quarter of a chunk; 90 -> 62, 45, 35, 29, 25, 23 frames).
-    Measured on the bench clip: 25.0 ms per 450 frames against 25.4 ms with the earlier 0.65 size + 10 rule."""
+    cascade of the last one are the parts of the pipeline that nothing overlaps.  With the round-2 kernels a cascade costs
+    about 0.4 ms + 0.016 ms/frame and a copy 0.05 ms/frame (720p, B200), so a chunk keeps up with the copy of its successor
+    if the successor is at least ~0.32 of its size + 8 frames: the tail shrinks by next = 0.35 size + 6 (at most six steps,
+    not below a tenth of a chunk; 90 -> 37, 18, 12, 10, 9 frames).  Measured on the bench clip (experiments/variants/sweep_sched.sh):
+    24.50 ms per 450 frames against 24.66 ms with the round-1 rule (0.6 size + 8, not below a quarter), H2D alone 22.42 ms."""
     if not ramp or n <= chunk:
         return [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
     head = [max(1, chunk // 4), max(1, chunk // 2)]
