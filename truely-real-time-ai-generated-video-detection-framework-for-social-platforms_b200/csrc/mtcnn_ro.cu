@@ -15,6 +15,13 @@
 #ifndef RO_FFMA2
 #define RO_FFMA2 1
 #endif
+// RO_CGP2: O-Net layers that compute two output-channel groups per pixel quad (conv_rows CGP = 2; same accumulation order,
+// bit identical): 0 none, 1 conv1, 2 conv1 + conv2.  Measured on B200 (experiments/variants/ab_lib.sh), O-Net stage per step:
+// 0.826 / 0.795 / 0.759 ms (720p bench clip), 18.13 / 17.43 / 16.63 ms (1080p clip batch).  Neutral for R-Net's conv2 (one item
+// per thread leaves half of its 256 threads idle) and slower with four-row bands for O-Net's conv2 (0.781 ms): not used there.
+#ifndef RO_CGP2
+#define RO_CGP2 2
+#endif
 
 namespace ro {
 
@@ -26,13 +33,16 @@ __device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : 
 // buffered in wbuf): one coalesced L2 read per slab for the whole CTA instead of a dependent global load in front of
 // every 16 FMAs of every thread (that chain, not the FMA pipe, set the single-candidate latency).
 // The accumulation order over (ci, ky, kx) is unchanged.
-template <int CIN, int COUT, int K, int HIN, int WIN, int CC, int MAXI>
+// CGP: groups of 4 output channels per item (the same 4 pixels): the activation loads are shared by CGP x 4 channels, so the
+// shared-memory loads per FMA drop by a third at CGP = 2 (the conv rows are bound by that traffic, profiles/r02d_rnet_full.md).
+template <int CIN, int COUT, int K, int HIN, int WIN, int CC, int MAXI, int CGP = 1>
 __device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* __restrict__ out, int r0, int r1,
                                           const float* __restrict__ w, const float* __restrict__ bias,
                                           const float* __restrict__ alpha, float* __restrict__ wbuf) {
   constexpr int WOUT = WIN - K + 1;
   constexpr int PXG = (WOUT + 3) / 4;
-  constexpr int CG = COUT / 4;
+  constexpr int CG = COUT / (4 * CGP);              // items along the channel axis
+  static_assert(COUT % (4 * CGP) == 0, "conv_rows channel grouping");
   constexpr int SLAB = CC * K * K * COUT;          // floats per slab
   constexpr int NCH = CIN / CC;
   static_assert(COUT % 4 == 0 && CIN % CC == 0 && SLAB % 4 == 0, "conv_rows tiling");
@@ -50,9 +60,9 @@ __device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* _
     int cg[MAXI], row[MAXI], x0[MAXI];
     bool live[MAXI];
 #if RO_FFMA2
-    unsigned long long acc2[MAXI][4][2];
+    unsigned long long acc2[MAXI][CGP][4][2];
 #else
-    float accs[MAXI][4][4];
+    float accs[MAXI][CGP][4][4];
 #endif
 #pragma unroll
     for (int i = 0; i < MAXI; ++i) {
@@ -64,12 +74,14 @@ __device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* _
       row[i] = rem / PXG;
       x0[i] = (rem - row[i] * PXG) * 4;
 #pragma unroll
-#if RO_FFMA2
-      for (int px = 0; px < 4; ++px) acc2[i][px][0] = acc2[i][px][1] = 0ull;
-#else
-      for (int px = 0; px < 4; ++px)
+      for (int g = 0; g < CGP; ++g)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) accs[i][px][j] = 0.f;
+#if RO_FFMA2
+        for (int px = 0; px < 4; ++px) acc2[i][g][px][0] = acc2[i][g][px][1] = 0ull;
+#else
+        for (int px = 0; px < 4; ++px)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) accs[i][g][px][j] = 0.f;
 #endif
     }
     stage(0);
@@ -97,25 +109,28 @@ __device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* _
             for (int t = 0; t < 4 + K - 1; ++t) v[t] = (x0[i] + t < WIN) ? ir[t] : 0.f;
 #pragma unroll
             for (int kx = 0; kx < K; ++kx) {
-              const float4 wv = *reinterpret_cast<const float4*>(ws + ((cl * K + ky) * K + kx) * COUT + cg[i] * 4);
-#if RO_FFMA2
-              const unsigned long long w01 = pack_f32x2(wv.x, wv.y), w23 = pack_f32x2(wv.z, wv.w);
 #pragma unroll
-              for (int px = 0; px < 4; ++px) {
-                const unsigned long long vv = pack_f32x2(v[px + kx], v[px + kx]);
-                ffma2(acc2[i][px][0], vv, w01);
-                ffma2(acc2[i][px][1], vv, w23);
-              }
+              for (int g = 0; g < CGP; ++g) {
+                const float4 wv = *reinterpret_cast<const float4*>(ws + ((cl * K + ky) * K + kx) * COUT + (cg[i] * CGP + g) * 4);
+#if RO_FFMA2
+                const unsigned long long w01 = pack_f32x2(wv.x, wv.y), w23 = pack_f32x2(wv.z, wv.w);
+#pragma unroll
+                for (int px = 0; px < 4; ++px) {
+                  const unsigned long long vv = pack_f32x2(v[px + kx], v[px + kx]);
+                  ffma2(acc2[i][g][px][0], vv, w01);
+                  ffma2(acc2[i][g][px][1], vv, w23);
+                }
 #else
 #pragma unroll
-              for (int px = 0; px < 4; ++px) {
-                const float vv = v[px + kx];
-                accs[i][px][0] = fmaf(vv, wv.x, accs[i][px][0]);
-                accs[i][px][1] = fmaf(vv, wv.y, accs[i][px][1]);
-                accs[i][px][2] = fmaf(vv, wv.z, accs[i][px][2]);
-                accs[i][px][3] = fmaf(vv, wv.w, accs[i][px][3]);
-              }
+                for (int px = 0; px < 4; ++px) {
+                  const float vv = v[px + kx];
+                  accs[i][g][px][0] = fmaf(vv, wv.x, accs[i][g][px][0]);
+                  accs[i][g][px][1] = fmaf(vv, wv.y, accs[i][g][px][1]);
+                  accs[i][g][px][2] = fmaf(vv, wv.z, accs[i][g][px][2]);
+                  accs[i][g][px][3] = fmaf(vv, wv.w, accs[i][g][px][3]);
+                }
 #endif
+              }
             }
           }
         }
@@ -125,24 +140,27 @@ __device__ __forceinline__ void conv_rows(const float* __restrict__ in, float* _
 #pragma unroll
     for (int i = 0; i < MAXI; ++i) {
       if (!live[i]) continue;
-      float acc[4][4];
 #pragma unroll
-      for (int px = 0; px < 4; ++px) {
+      for (int g = 0; g < CGP; ++g) {
+        float acc[4][4];
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
 #if RO_FFMA2
-        unpack_f32x2(acc2[i][px][0], acc[px][0], acc[px][1]);
-        unpack_f32x2(acc2[i][px][1], acc[px][2], acc[px][3]);
+          unpack_f32x2(acc2[i][g][px][0], acc[px][0], acc[px][1]);
+          unpack_f32x2(acc2[i][g][px][1], acc[px][2], acc[px][3]);
 #else
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[px][j] = accs[i][px][j];
+          for (int j = 0; j < 4; ++j) acc[px][j] = accs[i][g][px][j];
 #endif
-      }
+        }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int co = cg[i] * 4 + j;
-        const float b = __ldg(bias + co), a = __ldg(alpha + co);
+        for (int j = 0; j < 4; ++j) {
+          const int co = (cg[i] * CGP + g) * 4 + j;
+          const float b = __ldg(bias + co), a = __ldg(alpha + co);
 #pragma unroll
-        for (int px = 0; px < 4; ++px)
-          if (x0[i] + px < WOUT) out[(co * rows + row[i]) * WOUT + x0[i] + px] = prelu(acc[px][j] + b, a);
+          for (int px = 0; px < 4; ++px)
+            if (x0[i] + px < WOUT) out[(co * rows + row[i]) * WOUT + x0[i] + px] = prelu(acc[px][j] + b, a);
+        }
       }
     }
   }
@@ -174,7 +192,7 @@ __device__ __forceinline__ void pool_rows(const float* __restrict__ band, int ba
 }
 
 // conv + PReLU + ceil-mode maxpool, banded over PR pooled rows at a time
-template <int CIN, int COUT, int K, int HIN, int WIN, int PK, int PS, int PR, int CC, int MAXI>
+template <int CIN, int COUT, int K, int HIN, int WIN, int PK, int PS, int PR, int CC, int MAXI, int CGP = 1>
 __device__ __forceinline__ void conv_pool(const float* in, float* band, float* out, const float* w, const float* b,
                                           const float* a, float* wbuf) {
   constexpr int HC = HIN - K + 1, WC = WIN - K + 1;
@@ -182,7 +200,7 @@ __device__ __forceinline__ void conv_pool(const float* in, float* band, float* o
   for (int p0 = 0; p0 < HP; p0 += PR) {
     const int p1 = min(p0 + PR, HP);
     const int r0 = p0 * PS, r1 = min((p1 - 1) * PS + PK, HC);
-    conv_rows<CIN, COUT, K, HIN, WIN, CC, MAXI>(in, band, r0, r1, w, b, a, wbuf);
+    conv_rows<CIN, COUT, K, HIN, WIN, CC, MAXI, CGP>(in, band, r0, r1, w, b, a, wbuf);
     __syncthreads();
     pool_rows<COUT, HC, WC, PK, PS, HP, WP>(band, r0, r1 - r0, out, p0, p1);
     __syncthreads();
@@ -361,10 +379,18 @@ __global__ void __launch_bounds__(512) onet_kernel(const float* __restrict__ in,
     reinterpret_cast<float4*>(sm + S_IN)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
   __syncthreads();
   OT_MARK(0);
+#if RO_CGP2
+  conv_pool<3, 32, 3, 48, 48, 3, 2, 4, 3, 1, 2>(sm + S_IN, sm + S_BAND, sm + S_P1, wp + W1, wp + B1, wp + A1, sm + S_WB);     // -> 32x23x23
+#else
   conv_pool<3, 32, 3, 48, 48, 3, 2, 4, 3, 2>(sm + S_IN, sm + S_BAND, sm + S_P1, wp + W1, wp + B1, wp + A1, sm + S_WB);     // -> 32x23x23
+#endif
   OT_MARK(1);
   float* p2 = sm + S_IN;                                                                                  // input is dead
+#if RO_CGP2 >= 2
+  conv_pool<32, 64, 3, 23, 23, 3, 2, 5, 8, 2, 2>(sm + S_P1, sm + S_BAND, p2, wp + W2, wp + B2, wp + A2, sm + S_WB);        // -> 64x10x10
+#else
   conv_pool<32, 64, 3, 23, 23, 3, 2, 5, 8, 3>(sm + S_P1, sm + S_BAND, p2, wp + W2, wp + B2, wp + A2, sm + S_WB);           // -> 64x10x10
+#endif
   OT_MARK(2);
   conv_pool<64, 64, 3, 10, 10, 2, 2, 4, 8, 1>(p2, sm + S_BAND, sm + S_P3, wp + W3, wp + B3, wp + A3, sm + S_WB);           // -> 64x4x4
   OT_MARK(3);
